@@ -1,0 +1,919 @@
+// footsies_kernels.cu -- sm_100a kernels + C ABI of the batched FOOTSIES simulator.
+//
+// One CUDA thread owns one battle.  The whole reference frame update
+//   BattleCore.FixedUpdate/UpdateFightState (BattleCore.cs:201-220, 347-364)
+//   -> Fighter.UpdateInput / IncrementActionFrame / UpdateActionRequest / UpdateMovement / UpdateBoxes
+//      (Fighter.cs:140-324, 472-510, 546-635, 671-719)
+//   -> push / wall clamp / hitbox-hurtbox collision + damage (BattleCore.cs:483-591, Fighter.cs:352-454)
+//   -> in-game bot (BattleAI.cs:41-403, queried as TrainingManager.cs:59-77 does)
+//   -> observation, info, reward, termination (footsies.py:336-405, 518-570)
+// runs in registers between one 64-byte state load and one 64-byte state store per env (four 16-byte
+// SoA planes, fully coalesced 128-bit accesses).  Frame data is pre-expanded per (action, frame)
+// (frame_tables.h) and staged once per CTA into shared memory; CTAs are persistent (grid-stride).
+// No tensor cores: nothing here is a contraction.  The bound is HBM bandwidth (K = 1) or issue slots (K > 1).
+//
+// fp32 discipline: compiled with -fmad=false; every add/mul below rounds on its own exactly like the
+// scalar C# expression it restates.  Multiplications by the facing sign (+-1) and by 0.5 are exact.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "state_codec.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kFull = 0xffffffffu;
+
+// action indices (moves.py order)
+enum : uint32_t { STAND = FT_IDX_STAND, FORWARD = FT_IDX_FORWARD, BACKWARD = FT_IDX_BACKWARD,
+                  DASH_FORWARD = FT_IDX_DASH_FORWARD, DASH_BACKWARD = FT_IDX_DASH_BACKWARD,
+                  N_ATTACK = FT_IDX_N_ATTACK, B_ATTACK = FT_IDX_B_ATTACK, N_SPECIAL = FT_IDX_N_SPECIAL,
+                  B_SPECIAL = FT_IDX_B_SPECIAL, DAMAGE = FT_IDX_DAMAGE, GUARD_BREAK = FT_IDX_GUARD_BREAK,
+                  GUARD_PROXIMITY = FT_IDX_GUARD_PROXIMITY, DEAD = FT_IDX_DEAD, WIN = FT_IDX_WIN };
+
+// ---- bot input patterns (BattleAI.cs:192-342); move values: 0 none, 1 forward, 2 backward ----
+// move pattern ids: 1 Neutral, 2 FarApproach1, 3 FarApproach2, 4 MidApproach1, 5 MidApproach2, 6 FallBack1, 7 FallBack2
+// attack pattern ids: 1 NoAttack, 2 OneHitImmediate, 3 TwoHitImmediate, 4 ImmediateSpecial, 5 DelaySpecial
+constexpr int kMovePatBytes = 408;
+constexpr int kAttPatBytes = 256;
+
+struct __align__(16) Tables {
+    uint4 rows[FT_NUM_ROWS];
+    uint4 hit[8];
+    uint2 hurt[16];
+    uint2 push[8];
+    uint32_t action_info[32];
+    uint32_t attack[8];
+    double term_reward[FT_NUM_CUM][4][2];
+    double step_reward[4];
+    uint8_t cum_next[16][4];
+    uint16_t move_off[8], move_len[8], att_off[8], att_len[8];
+    uint8_t move_pat[kMovePatBytes];
+    uint8_t att_pat[kAttPatBytes];
+};
+static_assert(sizeof(Tables) % 16 == 0, "Tables is copied as uint4");
+
+struct Params {
+    uint4 *pl_f1, *pl_f2, *pl_env, *pl_rng;
+    unsigned long long *stats;
+    const uint8_t *act1, *act2;
+    float4 *obs;
+    float *reward;
+    uint8_t *terminated;
+    int32_t *info_frame;
+    uchar4 *info_misc;
+    const Tables *tables;
+    const uint8_t *mask;   // reset / seed kernels
+    long long seed_base, first_env_index;
+    int n, frame_skip, autoreset, stale_intro;
+};
+
+// event bits of one simulated frame (one ballot each in the stats reduction)
+enum : uint32_t { EV_EPISODE = 1u << 0, EV_P1_WIN = 1u << 1, EV_P2_WIN = 1u << 2, EV_DOUBLE_KO = 1u << 3,
+                  EV_SPECIAL = 1u << 4, EV_SPECIAL_NEUTRAL = 1u << 5, EV_GUARD_BREAK_A = 1u << 6, EV_HIT_A = 1u << 7,
+                  EV_BLOCK_A = 1u << 8, EV_GUARD_BREAK_B = 1u << 9, EV_HIT_B = 1u << 10, EV_BLOCK_B = 1u << 11,
+                  EV_RESET = 1u << 12 };
+
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+
+struct Env {            // one battle, in registers
+    float pos1, vel1, pos2, vel2;
+    uint32_t pk1, hist1, pk2, hist2;
+    int32_t frame;
+    uint32_t misc, bq2, bq1;
+    uint32_t r0, r1, r2, r3;
+};
+
+// UnityEngine.Random restated as xorshift128 (closed source; see DESIGN.md "parity unpinned")
+__device__ __forceinline__ uint32_t rng_next(Env &e) {
+    uint32_t t = e.r0 ^ (e.r0 << 11);
+    e.r0 = e.r1; e.r1 = e.r2; e.r2 = e.r3;
+    e.r3 = e.r3 ^ (e.r3 >> 19) ^ t ^ (t >> 8);
+    return e.r3;
+}
+
+struct FrameOut {       // per-fighter products of the pre-collision phases
+    uint32_t flags;     // expanded row flags (boxes present, hurt ids, push id)
+    uint32_t kind;      // attack kind of the action the boxes were built from
+    float pos_b;        // position when the boxes were built (after movement, before push)
+};
+
+// Fighter.UpdateInput + IncrementActionFrame + UpdateActionRequest + UpdateMovement for one fighter.
+// SIDE 0 = P1 (faces right: forward = Right), 1 = P2 (faces left: forward = Left).
+template <int SIDE>
+__device__ __forceinline__ void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel, uint32_t &pk,
+                                               uint32_t &hist, uint32_t &arun, FrameOut &fo) {
+    // ---- UpdateInput (Fighter.cs:172-188) on the compact history ----
+    const uint32_t inA = (in >> 2) & 1u;
+    const uint32_t hl = ((hist & 0xffffu) << 1) | (in & 1u);          // bit i = Left held i frames ago, i = 0..16
+    const uint32_t hr = ((hist >> 16) << 1) | ((in >> 1) & 1u);
+    const bool prev_a = arun != 0u;
+    const bool atk_down = inA && !prev_a;                              // IsAttackInput(inputDown[0])
+    const bool special = !inA && arun >= 59u;                          // CheckSpecialAttackInput (Fighter.cs:569-583)
+    arun = inA ? min(arun + 1u, 59u) : 0u;
+    hist = (hl & 0xffffu) | (hr << 16);
+    const uint32_t fm = SIDE == 0 ? hr : hl;
+    const uint32_t bm = SIDE == 0 ? hl : hr;
+    const bool fwd = fm & 1u, back = bm & 1u;
+    // CheckForwardDashInput / CheckBackwardDashInput (Fighter.cs:585-635): first older frame (1..8) with a
+    // direction held decides; then any neutral frame among the 8 frames before it.
+    const uint32_t either = fm | bm;
+    const uint32_t scan = either & 0x1feu;
+    const int i = __ffs(scan | 0x200u) - 1;                            // 1..9 (9 = none)
+    const bool gap = ((~either >> (i + 1)) & 0xffu) != 0u;
+    const bool dash_f = (fm & 3u) == 1u && scan != 0u && !((bm >> i) & 1u) && gap;
+    const bool dash_b = (bm & 3u) == 1u && scan != 0u && !((fm >> i) & 1u) && gap;
+
+    // ---- IncrementActionFrame (Fighter.cs:140-166) ----
+    uint32_t act = pk & 31u;
+    uint32_t frame = (pk >> FGP_FRAME_SHIFT) & 511u;
+    uint32_t stun = (pk >> FGP_STUN_SHIFT) & 31u;
+    uint32_t hitcnt = (pk >> FGP_HITCNT_SHIFT) & 1u;
+    uint32_t buf = (pk >> FGP_BUF_SHIFT) & 1u;
+    uint32_t rsv = (pk >> FGP_RSV_SHIFT) & 1u;
+    uint32_t inback = (pk >> FGP_INBACK_SHIFT) & 1u;
+    uint32_t rprox = (pk >> FGP_RPROX_SHIFT) & 1u;
+    int shake = ((int)(pk << 1)) >> 28;                                 // bits 27..30, sign-extended
+    if (shake != 0) { shake = -shake; shake += shake > 0 ? -1 : 1; }
+    if (stun > 0u) stun--; else frame++;
+
+    // ---- UpdateActionRequest (Fighter.cs:201-286) with the RequestAction chain (Fighter.cs:472-510) collapsed:
+    //      when the action ended or is alwaysCancelable the FIRST request of the chain wins, otherwise the only
+    //      effect a request can have is buffering N_SPECIAL inside a cancel window. ----
+    const uint32_t info0 = T.action_info[act];
+    const bool ended = frame >= (info0 & 511u);
+    bool want_buffer = false;
+    bool set = false;
+    uint32_t req = act;
+    if (rsv && stun == 0u) {                                            // reserved GUARD_BREAK (Fighter.cs:212-218)
+        req = GUARD_BREAK; set = true;
+    } else if (buf && hitcnt && stun == 0u) {                           // buffered cancel (Fighter.cs:222-229)
+        req = N_SPECIAL; set = true;
+    } else {
+        const bool dir = fwd || back;
+        const bool in_normal = (act == N_ATTACK || act == B_ATTACK) && !ended;
+        req = special ? (dir ? B_SPECIAL : N_SPECIAL)
+            : atk_down ? (in_normal ? N_SPECIAL : (dir ? B_ATTACK : N_ATTACK))
+            : dash_f ? DASH_FORWARD
+            : dash_b ? DASH_BACKWARD
+            : (fwd && back) ? STAND
+            : fwd ? FORWARD
+            : back ? (rprox ? GUARD_PROXIMITY : BACKWARD)
+            : STAND;
+        const bool free_to_switch = ended || ((info0 >> 9) & 1u);
+        set = free_to_switch && (ended || req != act);
+        want_buffer = !free_to_switch && req == N_SPECIAL;
+        inback = back;
+        rprox = 0u;
+    }
+    if (set) {                                                          // SetCurrentAction (Fighter.cs:546-563)
+        act = req; frame = 0u; hitcnt = 0u; buf = 0u; rsv = 0u; shake = 0;
+    }
+
+    // ---- frame data of the (action, frame) the fighter ends up in ----
+    const uint32_t info = T.action_info[act];
+    const uint32_t row_idx = ((info >> 14) & 1023u) + min(frame, (info >> 24) & 63u);
+    const uint4 row = T.rows[row_idx];
+    if (want_buffer && (row.z & 8u)) buf = 1u;                          // cancel window (Fighter.cs:492-505)
+
+    // ---- UpdateMovement (Fighter.cs:291-319) ----
+    if (stun == 0u) {
+        const float dx = u2f(row.x);
+        pos = pos + (SIDE == 0 ? dx : -dx);
+        if (row.z & 1u) vel = u2f(row.y);
+    }
+
+    pk = act | frame << FGP_FRAME_SHIFT | stun << FGP_STUN_SHIFT | (pk & (7u << FGP_GUARD_SHIFT))
+       | hitcnt << FGP_HITCNT_SHIFT | buf << FGP_BUF_SHIFT | rsv << FGP_RSV_SHIFT | inback << FGP_INBACK_SHIFT
+       | rprox << FGP_RPROX_SHIFT | ((uint32_t)shake & 15u) << FGP_SHAKE_SHIFT;
+    fo.flags = row.z;
+    fo.kind = (info >> 11) & 7u;
+    fo.pos_b = pos;
+}
+
+// Does the attacker's hitbox `hb` overlap any of the victim's (<= 2) hurtboxes?  BoxBase.Overlaps
+// (Fighter.cs:17-25, inclusive) with the y test pre-resolved into hb.z.  a_/v_ shift = push + wall
+// displacement applied to already-built boxes by ApplyPositionChange (Fighter.cs:331-350).
+template <int ASIDE>
+__device__ __forceinline__ bool hit_overlaps(const Tables &T, uint4 hb, float apos_b, float a_s, float a_t,
+                                             float vpos_b, float v_s, float v_t, uint32_t vflags) {
+    const float hcx = u2f(hb.x);
+    const float hx = ((apos_b + (ASIDE == 0 ? hcx : -hcx)) + a_s) + a_t;
+    const float hw = u2f(hb.y);
+    const float hmin = hx - hw, hmax = hx + hw;
+    bool r = false;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t id = (vflags >> (4 + 4 * j)) & 15u;
+        if ((hb.z >> id) & 1u) {
+            const uint2 hu = T.hurt[id];
+            const float vcx = u2f(hu.x);
+            const float vx = ((vpos_b + (ASIDE == 0 ? -vcx : vcx)) + v_s) + v_t;
+            const float vhw = u2f(hu.y);
+            r = r || ((vx + vhw >= hmin) && (vx - vhw <= hmax));
+        }
+    }
+    return r;
+}
+
+// One attacker -> victim pass of BattleCore.UpdateHitboxHurtboxCollision (BattleCore.cs:521-591) including
+// NotifyAttackHit / NotifyDamaged / GetHitStunFrame / SetHitStun / SetSpriteShakeFrame / NotifyInProximityGuardRange
+// (Fighter.cs:352-454).  Boxes are the pre-collision snapshot; hit counts and the victim's action are current.
+template <int ASIDE>
+__device__ __forceinline__ uint32_t attack_pass(const Tables &T, uint32_t &apk, uint32_t &vpk, const FrameOut &af,
+                                                const FrameOut &vf, float a_s, float a_t, float v_s, float v_t) {
+    if (af.kind == 0u || !(af.flags & 6u) || ((apk >> FGP_HITCNT_SHIFT) & 1u)) return 0u;   // CanAttackHit
+    bool hit = false, prox = false;
+    if (af.flags & 4u)
+        hit = hit_overlaps<ASIDE>(T, T.hit[(af.kind - 1u) * 2u + 1u], af.pos_b, a_s, a_t, vf.pos_b, v_s, v_t, vf.flags);
+    if (!hit && (af.flags & 2u))
+        prox = hit_overlaps<ASIDE>(T, T.hit[(af.kind - 1u) * 2u], af.pos_b, a_s, a_t, vf.pos_b, v_s, v_t, vf.flags);
+    if (hit) {
+        const uint32_t atk = T.attack[af.kind];
+        uint32_t guard = (vpk >> FGP_GUARD_SHIFT) & 3u;
+        const bool brk = guard == 0u;                                   // guardHealth < 0 after the decrement
+        guard = brk ? 0u : guard - 1u;
+        uint32_t vital = (vpk >> FGP_VITAL_SHIFT) & 1u;
+        const uint32_t vact = vpk & 31u;
+        const bool guarding = vact == BACKWARD || ((T.action_info[vact] >> 10) & 1u);
+        uint32_t nact, stun, rsv = 0u, res;
+        if (guarding) {
+            nact = (atk >> 5) & 31u;
+            rsv = brk ? 1u : 0u;
+            stun = brk ? (atk >> 21) & 31u : (atk >> 16) & 31u;
+            res = brk ? 3u : 2u;
+        } else {
+            if ((atk >> 10) & 1u) vital = 0u;
+            nact = atk & 31u;
+            stun = (atk >> 11) & 31u;
+            res = 1u;
+        }
+        const int sh = min((int)stun / 3, 6) * (ASIDE == 0 ? 1 : -1);   // victim of P1 faces left -> +
+        vpk = nact | stun << FGP_STUN_SHIFT | guard << FGP_GUARD_SHIFT | vital << FGP_VITAL_SHIFT
+            | rsv << FGP_RSV_SHIFT | (vpk & (3u << FGP_INBACK_SHIFT)) | ((uint32_t)sh & 15u) << FGP_SHAKE_SHIFT;
+        apk = (apk & ~(31u << FGP_STUN_SHIFT)) | stun << FGP_STUN_SHIFT | 1u << FGP_HITCNT_SHIFT;
+        return res;
+    }
+    if (prox && ((vpk >> FGP_INBACK_SHIFT) & 1u)) vpk |= 1u << FGP_RPROX_SHIFT;
+    return 0u;
+}
+
+// BattleAI.getNextAIInput (BattleAI.cs:41-66) on pattern-id + cursor queues.  `dist` and `opp_act` are the state
+// captured by the PREVIOUS call (the ascending shift loop at BattleAI.cs:358-361 makes fightStates[5] exactly that).
+template <int SIDE>
+__device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &q, float dist, uint32_t opp_act) {
+    uint32_t mp = q & 7u, mc = (q >> 3) & 127u, ap = (q >> 10) & 7u, ac = (q >> 13) & 127u;
+    uint32_t input = 0u;
+    const int bucket = dist > 4.0f ? 0 : dist > 3.0f ? 1 : dist > 2.5f ? 2 : dist > 2.0f ? 3 : 4;
+    if (mc < T.move_len[mp]) {
+        const uint32_t v = T.move_pat[T.move_off[mp] + mc];           // 0 none, 1 forward, 2 backward
+        mc++;
+        input |= SIDE == 1 ? v : ((v >> 1) | ((v & 1u) << 1));          // P2: forward = Left(1); P1: forward = Right(2)
+    } else {                                                            // SelectMovement (BattleAI.cs:68-126)
+        const uint32_t n = (0x34572u >> (4 * bucket)) & 15u;            // ranges 2,7,5,4,3
+        const uint32_t r = rng_next(e) % n;
+        // nibble r of the bucket's word = move pattern id
+        const uint32_t sel = bucket == 0 ? 0x32u : bucket == 1 ? 0x1325544u : bucket == 2 ? 0x17654u
+                           : bucket == 3 ? 0x1176u : 0x176u;
+        mp = (sel >> (4 * r)) & 15u;
+        mc = 0u;
+    }
+    if (ac < T.att_len[ap]) {
+        input |= T.att_pat[T.att_off[ap] + ac];
+        ac++;
+    } else {                                                            // SelectAttack (BattleAI.cs:128-190)
+        const bool opp_hurt = opp_act == DAMAGE || opp_act == GUARD_BREAK || opp_act == N_SPECIAL || opp_act == B_SPECIAL;
+        const bool opp_normal = opp_act == N_ATTACK || opp_act == B_ATTACK;
+        if (opp_hurt || (bucket == 1 && opp_normal)) {
+            ap = 3u;                                                    // AddTwoHitImmediateAttack, no draw
+        } else {
+            const uint32_t n = (0x36354u >> (4 * bucket)) & 15u;        // ranges 4,5,3,6,3
+            const uint32_t r = rng_next(e) % n;
+            const uint32_t sel = bucket == 0 ? 0x1111u : bucket == 1 ? 0x52211u : bucket == 2 ? 0x321u
+                               : bucket == 3 ? 0x543322u : 0x332u;
+            ap = (sel >> (4 * r)) & 15u;
+        }
+        ac = 0u;
+    }
+    q = mp | mc << 3 | ap << 10 | ac << 13;
+    return input;
+}
+
+// Stop -> Intro -> one Intro frame -> Fight (BattleCore.cs:176-200, 262-291, 329-345) for one env.
+// What survives from the previous round (SetupBattleStart, Fighter.cs:120-135, does not touch them): the actors'
+// held inputs (replayed by the Intro frame), hit stun, isInputBackward / isReserveProximityGuard.
+template <bool P1BOT, bool P2BOT>
+__device__ __forceinline__ void reset_env(const Tables &T, Env &e, bool stale_intro) {
+    const bool was_done = (e.misc >> FGM_DONE_SHIFT) & 1u;
+    uint32_t a1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u, a2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+    if (!stale_intro) { a1 = 0u; a2 = 0u; }
+    uint32_t pk[2] = { e.pk1, e.pk2 };
+    uint32_t npk[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        uint32_t stun = (pk[s] >> FGP_STUN_SHIFT) & 31u;
+        uint32_t keep = pk[s] & (3u << FGP_INBACK_SHIFT);
+        if (was_done) {
+            // the End-state frame (BattleCore.cs:371-381) ran once: hit stun ticks; a dead fighter went through the
+            // normal request path with cleared inputs (flags reset), a winner returned early (flags kept)
+            if (stun > 0u) stun--;
+            if (!((pk[s] >> FGP_VITAL_SHIFT) & 1u)) keep = 0u;
+        }
+        // Intro frame: IncrementActionFrame (frame 0 -> 1 unless in hit stun), RequestAction(STAND) is a no-op
+        uint32_t frame = 1u;
+        if (stun > 0u) { stun--; frame = 0u; }
+        npk[s] = STAND | frame << FGP_FRAME_SHIFT | stun << FGP_STUN_SHIFT | 3u << FGP_GUARD_SHIFT
+               | 1u << FGP_VITAL_SHIFT | keep;
+    }
+    e.pk1 = npk[0]; e.pk2 = npk[1];
+    e.pos1 = -2.0f; e.pos2 = 2.0f; e.vel1 = 0.0f; e.vel2 = 0.0f;
+    e.hist1 = (a1 & 1u) | ((a1 >> 1) & 1u) << 16;                       // UpdateInput(stale) after ClearInput
+    e.hist2 = (a2 & 1u) | ((a2 >> 1) & 1u) << 16;
+    e.frame = -1;
+    e.bq1 = 0u; e.bq2 = 0u;                                            // BattleAI.Reset (BattleAI.cs:393-403)
+    const uint32_t run1 = (a1 >> 2) & 1u, run2 = (a2 >> 2) & 1u;       // Attack run after the Intro frame's input
+    // first bot query at the Fight transition (BattleCore.cs:289): decision input = round-start state
+    if (P1BOT) a1 = bot_next<0>(T, e, e.bq1, 4.0f, STAND);
+    if (P2BOT) a2 = bot_next<1>(T, e, e.bq2, 4.0f, STAND);
+    e.misc = run1 << FGM_ARUN1_SHIFT | run2 << FGM_ARUN2_SHIFT
+           | a1 << FGM_ACTOR1_SHIFT | a2 << FGM_ACTOR2_SHIFT;           // recorded inputs 0, done 0, cum 0
+}
+
+// FootsiesEnv._extract_obs / _extract_info (footsies.py:336-380) incl. the DEAD/WIN -> STAND remap of step()
+// (footsies.py:538-549; a no-op on the reset observation, which is always STAND).
+__device__ __forceinline__ void write_outputs(const Params &p, int i, const Env &e, float reward, bool terminated) {
+    uint32_t m1 = e.pk1 & 31u, m2 = e.pk2 & 31u;
+    if (m1 >= DEAD) m1 = STAND;
+    if (m2 >= DEAD) m2 = STAND;
+    const uint32_t f1 = m1 <= BACKWARD ? 0u : (e.pk1 >> FGP_FRAME_SHIFT) & 511u;
+    const uint32_t f2 = m2 <= BACKWARD ? 0u : (e.pk2 >> FGP_FRAME_SHIFT) & 511u;
+    float4 o0, o1;
+    o0.x = (float)((e.pk1 >> FGP_GUARD_SHIFT) & 3u); o0.y = (float)((e.pk2 >> FGP_GUARD_SHIFT) & 3u);
+    o0.z = (float)m1; o0.w = (float)m2;
+    o1.x = (float)f1; o1.y = (float)f2; o1.z = e.pos1; o1.w = e.pos2;
+    p.obs[2 * (size_t)i] = o0;
+    p.obs[2 * (size_t)i + 1] = o1;
+    p.reward[i] = reward;
+    p.terminated[i] = terminated ? 1 : 0;
+    p.info_frame[i] = e.frame;
+    uchar4 im;
+    im.x = (e.misc >> FGM_REC1_SHIFT) & 7u; im.y = (e.misc >> FGM_REC2_SHIFT) & 7u;
+    im.z = (e.pk1 >> FGP_STUN_SHIFT) & 31u; im.w = (e.pk2 >> FGP_STUN_SHIFT) & 31u;
+    p.info_misc[i] = im;
+}
+
+__device__ __forceinline__ void load_tables(Tables *dst, const Tables *src) {
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+    for (int k = threadIdx.x; k < (int)(sizeof(Tables) / 16); k += blockDim.x) d[k] = s[k];
+    __syncthreads();
+}
+
+template <bool WITH_RNG>
+__device__ __forceinline__ void load_env(const Params &p, int i, Env &e) {
+    const uint4 a = p.pl_f1[i], b = p.pl_f2[i], c = p.pl_env[i];
+    e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
+    e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
+    e.frame = (int32_t)c.x; e.misc = c.y; e.bq2 = c.z; e.bq1 = c.w;
+    if (WITH_RNG) { const uint4 r = p.pl_rng[i]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
+}
+template <bool WITH_RNG>
+__device__ __forceinline__ void store_env(const Params &p, int i, const Env &e) {
+    p.pl_f1[i] = make_uint4(f2u(e.pos1), f2u(e.vel1), e.pk1, e.hist1);
+    p.pl_f2[i] = make_uint4(f2u(e.pos2), f2u(e.vel2), e.pk2, e.hist2);
+    p.pl_env[i] = make_uint4((uint32_t)e.frame, e.misc, e.bq2, e.bq1);
+    if (WITH_RNG) p.pl_rng[i] = make_uint4(e.r0, e.r1, e.r2, e.r3);
+}
+
+// Warp-cooperative statistics: lane b of every warp owns counter b; one ballot + popc per event bit.
+struct StatAcc {
+    unsigned long long mine;   // lane-specialised accumulator
+    __device__ __forceinline__ void add_frame(uint32_t ev, int32_t ep_frames, int lane) {
+        if (!__any_sync(kFull, ev != 0u)) return;
+        // counters: 0 episodes 1 p1 wins 2 p2 wins 3 double ko 4 episode frames 5 specials 6 specials-from-neutral
+        //           7 guard breaks 8 hits 9 blocks 11 resets
+        const uint32_t b_ep = __ballot_sync(kFull, ev & EV_EPISODE), b_w1 = __ballot_sync(kFull, ev & EV_P1_WIN);
+        const uint32_t b_w2 = __ballot_sync(kFull, ev & EV_P2_WIN), b_dk = __ballot_sync(kFull, ev & EV_DOUBLE_KO);
+        const uint32_t b_sp = __ballot_sync(kFull, ev & EV_SPECIAL), b_sn = __ballot_sync(kFull, ev & EV_SPECIAL_NEUTRAL);
+        const uint32_t gb = __popc(__ballot_sync(kFull, ev & EV_GUARD_BREAK_A)) + __popc(__ballot_sync(kFull, ev & EV_GUARD_BREAK_B));
+        const uint32_t hi = __popc(__ballot_sync(kFull, ev & EV_HIT_A)) + __popc(__ballot_sync(kFull, ev & EV_HIT_B));
+        const uint32_t bl = __popc(__ballot_sync(kFull, ev & EV_BLOCK_A)) + __popc(__ballot_sync(kFull, ev & EV_BLOCK_B));
+        const uint32_t b_rs = __ballot_sync(kFull, ev & EV_RESET);
+        const uint32_t fr = __reduce_add_sync(kFull, (uint32_t)ep_frames);
+        uint32_t v = 0u;
+        v = lane == FG_STAT_EPISODES ? __popc(b_ep) : v;
+        v = lane == FG_STAT_P1_WINS ? __popc(b_w1) : v;
+        v = lane == FG_STAT_P2_WINS ? __popc(b_w2) : v;
+        v = lane == FG_STAT_DOUBLE_KO ? __popc(b_dk) : v;
+        v = lane == FG_STAT_EPISODE_FRAMES ? fr : v;
+        v = lane == FG_STAT_P1_SPECIALS ? __popc(b_sp) : v;
+        v = lane == FG_STAT_P1_SPECIALS_NEUTRAL ? __popc(b_sn) : v;
+        v = lane == FG_STAT_GUARD_BREAKS ? gb : v;
+        v = lane == FG_STAT_HITS ? hi : v;
+        v = lane == FG_STAT_BLOCKS ? bl : v;
+        v = lane == FG_STAT_RESETS ? __popc(b_rs) : v;
+        mine += v;
+    }
+};
+
+// One fight frame for one env (everything between "inputs known" and "state after the frame").
+// Returns event bits; sets `terminal`, accumulates the Python float64 reward into `reward`.
+template <bool P1BOT, bool P2BOT, bool DENSE>
+__device__ __forceinline__ uint32_t simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, double &reward,
+                                                   bool &terminal, int32_t &ep_frames) {
+    // state the bots will be shown after this frame (previous call's capture == state before this frame)
+    const float pre_dist = fabsf(e.pos2 - e.pos1);
+    const uint32_t pre_a1 = e.pk1 & 31u, pre_a2 = e.pk2 & 31u;
+    const uint32_t g1_before = (e.pk1 >> FGP_GUARD_SHIFT) & 3u, g2_before = (e.pk2 >> FGP_GUARD_SHIFT) & 3u;
+
+    e.frame++;
+    // BattleCore.RecordInput (BattleCore.cs:593-607): recording stops after maxRecordingInputFrame frames
+    if (e.frame < FG_MAX_RECORDING_INPUT_FRAME)
+        e.misc = (e.misc & ~(63u << FGM_REC1_SHIFT)) | in1 << FGM_REC1_SHIFT | in2 << FGM_REC2_SHIFT;
+
+    uint32_t arun1 = (e.misc >> FGM_ARUN1_SHIFT) & 63u, arun2 = (e.misc >> FGM_ARUN2_SHIFT) & 63u;
+    FrameOut f1, f2;
+    update_fighter<0>(T, in1, e.pos1, e.vel1, e.pk1, e.hist1, arun1, f1);
+    update_fighter<1>(T, in2, e.pos2, e.vel2, e.pk2, e.hist2, arun2, f2);
+
+    // ---- UpdatePushCharacterVsCharacter (BattleCore.cs:483-501), UnityEngine.Rect semantics: x = left edge, strict ----
+    const uint2 pb1 = T.push[(f1.flags >> 12) & 7u], pb2 = T.push[(f2.flags >> 12) & 7u];
+    const float px1 = e.pos1 + u2f(pb1.x), w1 = u2f(pb1.y);
+    const float px2 = e.pos2 - u2f(pb2.x), w2 = u2f(pb2.y);
+    const float xmax1 = w1 + px1, xmax2 = w2 + px2;
+    float s1 = 0.0f, s2 = 0.0f;
+    if (xmax2 > px1 && px2 < xmax1) {
+        if (e.pos1 < e.pos2) { const float d = xmax1 - px2; s1 = -0.5f * d; s2 = 0.5f * d; }
+        else if (e.pos1 > e.pos2) { const float d = xmax2 - px1; s1 = 0.5f * d; s2 = -0.5f * d; }
+    }
+    // ---- UpdatePushCharacterVsBackground (BattleCore.cs:503-519), BoxBase semantics: x = centre ----
+    float t1 = 0.0f, t2 = 0.0f;
+    {
+        const float c = px1 + s1, hw = 0.5f * w1, mn = c - hw, mx = c + hw;
+        if (mn < -5.0f) t1 = -5.0f - mn; else if (mx > 5.0f) t1 = 5.0f - mx;
+    }
+    {
+        const float c = px2 + s2, hw = 0.5f * w2, mn = c - hw, mx = c + hw;
+        if (mn < -5.0f) t2 = -5.0f - mn; else if (mx > 5.0f) t2 = 5.0f - mx;
+    }
+    e.pos1 = (e.pos1 + s1) + t1;
+    e.pos2 = (e.pos2 + s2) + t2;
+
+    // ---- UpdateHitboxHurtboxCollision (BattleCore.cs:521-591): P1 attacks first, then P2 with snapshot boxes ----
+    const uint32_t res_a = attack_pass<0>(T, e.pk1, e.pk2, f1, f2, s1, t1, s2, t2);   // result on P2
+    const uint32_t res_b = attack_pass<1>(T, e.pk2, e.pk1, f2, f1, s2, t2, s1, t1);   // result on P1
+
+    uint32_t ev = 0u;
+    ev |= res_a == 3u ? EV_GUARD_BREAK_A : res_a == 2u ? EV_BLOCK_A : res_a == 1u ? EV_HIT_A : 0u;
+    ev |= res_b == 3u ? EV_GUARD_BREAK_B : res_b == 2u ? EV_BLOCK_B : res_b == 1u ? EV_HIT_B : 0u;
+    const uint32_t a1 = e.pk1 & 31u;
+    if (a1 != pre_a1 && (a1 == N_SPECIAL || a1 == B_SPECIAL)) {         // wrappers/statistics.py:36-46
+        ev |= EV_SPECIAL;
+        if (pre_a1 != N_ATTACK && pre_a1 != B_ATTACK) ev |= EV_SPECIAL_NEUTRAL;
+    }
+
+    // ---- KO (BattleCore.cs:212-217), termination (footsies.py:555) ----
+    const bool dead1 = !((e.pk1 >> FGP_VITAL_SHIFT) & 1u), dead2 = !((e.pk2 >> FGP_VITAL_SHIFT) & 1u);
+    terminal = dead1 || dead2;
+
+    // ---- reward (footsies.py:382-405); Python floats are doubles ----
+    if (DENSE) {
+        const uint32_t code = (((e.pk1 >> FGP_GUARD_SHIFT) & 3u) < g1_before ? 1u : 0u)
+                            | (((e.pk2 >> FGP_GUARD_SHIFT) & 3u) < g2_before ? 2u : 0u);
+        uint32_t cum = (e.misc >> FGM_CUM_SHIFT) & 15u;
+        if (code | (terminal ? 1u : 0u)) {
+            cum = T.cum_next[cum][code];
+            e.misc = (e.misc & ~(15u << FGM_CUM_SHIFT)) | cum << FGM_CUM_SHIFT;
+            reward += terminal ? T.term_reward[cum][code][dead2 ? 1 : 0] : T.step_reward[code];
+        }
+    } else if (terminal) {
+        reward += dead2 ? 1.0 : -1.0;
+    }
+
+    if (terminal) {
+        // ChangeRoundState(KO): ClearInput on both fighters (BattleCore.cs:292-299); actors keep their inputs
+        e.hist1 = 0u; e.hist2 = 0u; arun1 = 0u; arun2 = 0u;
+        ev |= EV_EPISODE | (dead1 && dead2 ? EV_DOUBLE_KO : dead2 ? EV_P1_WIN : EV_P2_WIN);
+        ep_frames = e.frame + 1;
+        e.misc |= 1u << FGM_DONE_SHIFT;
+    }
+    // ---- TrainingManager.Step (TrainingManager.cs:59-77): actors' inputs for the next frame; bots are asked
+    //      after the frame, P1 first, and not on the terminal frame ----
+    uint32_t n1 = in1, n2 = in2;
+    if (!terminal) {
+        if (P1BOT) n1 = bot_next<0>(T, e, e.bq1, pre_dist, pre_a2);
+        if (P2BOT) n2 = bot_next<1>(T, e, e.bq2, pre_dist, pre_a1);
+    }
+    e.misc = (e.misc & ~((63u << FGM_ARUN1_SHIFT) | (63u << FGM_ARUN2_SHIFT) | (63u << FGM_ACTOR1_SHIFT)))
+           | arun1 << FGM_ARUN1_SHIFT | arun2 << FGM_ARUN2_SHIFT | n1 << FGM_ACTOR1_SHIFT | n2 << FGM_ACTOR2_SHIFT;
+    return ev;
+}
+
+// FootsiesEnv.step for every env: up to K fused fight frames, or the reset of a finished env (autoreset).
+template <bool KFUSED, bool P1BOT, bool P2BOT, bool DENSE>
+__global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
+    __shared__ Tables T;
+    __shared__ unsigned long long s_stats[FG_STAT_COUNT];
+    load_tables(&T, p.tables);
+    if (threadIdx.x < FG_STAT_COUNT) s_stats[threadIdx.x] = 0ull;
+    __syncthreads();
+    constexpr bool kRng = P1BOT || P2BOT;
+    const int lane = threadIdx.x & 31;
+    StatAcc acc; acc.mine = 0ull;
+    uint32_t frames_done = 0u;
+    const int n_round = (p.n + 31) & ~31;                               // keep warps converged for the ballots
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < p.n;
+        Env e;
+        bool run = false;
+        uint32_t ev0 = 0u, in1 = 0u, in2 = 0u;
+        if (valid) {
+            load_env<kRng>(p, i, e);
+            if ((e.misc >> FGM_DONE_SHIFT) & 1u) {
+                if (p.autoreset) {                                      // next-step autoreset: this call only resets
+                    reset_env<P1BOT, P2BOT>(T, e, p.stale_intro != 0);
+                    store_env<kRng>(p, i, e);
+                    write_outputs(p, i, e, 0.0f, false);
+                    ev0 = EV_RESET;
+                } else {
+                    p.reward[i] = 0.0f;                                 // frozen until fg_reset
+                }
+            } else {
+                run = true;
+                in1 = P1BOT ? (e.misc >> FGM_ACTOR1_SHIFT) & 7u : p.act1[i] & 7u;
+                in2 = P2BOT ? (e.misc >> FGM_ACTOR2_SHIFT) & 7u : p.act2[i] & 7u;
+            }
+        }
+        double reward = 0.0;
+        bool terminal = false;
+        const int K = KFUSED ? p.frame_skip : 1;
+        for (int k = 0; k < K; k++) {                                   // uniform trip count: the ballots stay converged
+            uint32_t ev = k == 0 ? ev0 : 0u;
+            int32_t ep_frames = 0;
+            if (run && !terminal) {
+                ev |= simulate_frame<P1BOT, P2BOT, DENSE>(T, e, in1, in2, reward, terminal, ep_frames);
+                frames_done++;
+                if (KFUSED) {
+                    if (P1BOT) in1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u;
+                    if (P2BOT) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                }
+            }
+            acc.add_frame(ev, ep_frames, lane);
+        }
+        if (run) {
+            store_env<kRng>(p, i, e);
+            write_outputs(p, i, e, (float)reward, terminal);
+        }
+    }
+    // block-level fold of the lane-specialised counters, then one atomic per counter per CTA
+    const uint32_t fsum = __reduce_add_sync(kFull, frames_done);
+    if (lane == FG_STAT_ENV_FRAMES) acc.mine += fsum;
+    if (lane < FG_STAT_COUNT && acc.mine) atomicAdd(&s_stats[lane], acc.mine);
+    __syncthreads();
+    if (threadIdx.x < FG_STAT_COUNT && s_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// FootsiesEnv.reset / RESET command for the envs selected by mask (NULL = all).
+template <bool P1BOT, bool P2BOT>
+__global__ void __launch_bounds__(kThreads) reset_kernel(const Params p) {
+    __shared__ Tables T;
+    load_tables(&T, p.tables);
+    constexpr bool kRng = P1BOT || P2BOT;
+    unsigned long long resets = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+        if (p.mask && !p.mask[i]) continue;
+        Env e;
+        load_env<kRng>(p, i, e);
+        reset_env<P1BOT, P2BOT>(T, e, p.stale_intro != 0);
+        store_env<kRng>(p, i, e);
+        write_outputs(p, i, e, 0.0f, false);
+        resets++;
+    }
+    if (resets) atomicAdd(&p.stats[FG_STAT_RESETS], resets);
+}
+
+// Random.InitState(seed_base + global env index) (BattleCore.cs:170-173)
+__global__ void __launch_bounds__(kThreads) seed_kernel(const Params p) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+        if (p.mask && !p.mask[i]) continue;
+        uint32_t s0 = (uint32_t)(int32_t)(p.seed_base + p.first_env_index + i);
+        uint32_t s1 = s0 * 1812433253u + 1u, s2 = s1 * 1812433253u + 1u, s3 = s2 * 1812433253u + 1u;
+        p.pl_rng[i] = make_uint4(s0, s1, s2, s3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof g_err, fmt, detail);
+    return code;
+}
+#define CUDA_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) \
+    return fail(FG_ERR_CUDA, #expr ": %s", cudaGetErrorString(_e)); } while (0)
+
+void build_tables(Tables &t) {
+    memset(&t, 0, sizeof t);
+    static const uint32_t rows[FT_NUM_ROWS][4] = FT_ROWS_INIT;
+    static const uint32_t hit[8][4] = FT_HIT_INIT;
+    static const uint32_t hurt[FT_NUM_HURT][2] = FT_HURT_INIT;
+    static const uint32_t push[FT_NUM_PUSH][2] = FT_PUSH_INIT;
+    static const uint32_t info[FT_NUM_ACTIONS] = FT_ACTION_INFO_INIT;
+    static const uint32_t attack[5] = FT_ATTACK_INIT;
+    static const uint8_t cum_next[FT_NUM_CUM][4] = FT_CUM_NEXT_INIT;
+    static const double step_reward[4] = FT_STEP_REWARD_INIT;
+    static const double term[FT_NUM_CUM][4][2] = FT_TERM_REWARD_INIT;
+    for (int i = 0; i < FT_NUM_ROWS; i++) t.rows[i] = make_uint4(rows[i][0], rows[i][1], rows[i][2], rows[i][3]);
+    for (int i = 0; i < 8; i++) t.hit[i] = make_uint4(hit[i][0], hit[i][1], hit[i][2], hit[i][3]);
+    for (int i = 0; i < FT_NUM_HURT; i++) t.hurt[i] = make_uint2(hurt[i][0], hurt[i][1]);
+    for (int i = 0; i < FT_NUM_PUSH; i++) t.push[i] = make_uint2(push[i][0], push[i][1]);
+    for (int i = 0; i < FT_NUM_ACTIONS; i++) t.action_info[i] = info[i];
+    for (int i = 0; i < 5; i++) t.attack[i] = attack[i];
+    memcpy(t.term_reward, term, sizeof term);
+    memcpy(t.step_reward, step_reward, sizeof step_reward);
+    for (int i = 0; i < FT_NUM_CUM; i++) for (int k = 0; k < 4; k++) t.cum_next[i][k] = cum_next[i][k];
+    // ---- BattleAI input sequences (BattleAI.cs:192-342): F = forward, B = backward, N = none ----
+    enum { N = 0, F = 1, B = 2 };
+    std::vector<uint8_t> mp;
+    auto rep = [&](std::vector<uint8_t> &v, int val, int n) { for (int i = 0; i < n; i++) v.push_back((uint8_t)val); };
+    auto dash = [&](std::vector<uint8_t> &v) { v.push_back(F); v.push_back(N); v.push_back(F); };  // :330-342 (both dashes tap FORWARD)
+    int id = 1;
+    auto begin = [&](std::vector<uint8_t> &v, uint16_t *off) { off[id] = (uint16_t)v.size(); };
+    auto end = [&](std::vector<uint8_t> &v, uint16_t *off, uint16_t *len) { len[id] = (uint16_t)(v.size() - off[id]); id++; };
+    begin(mp, t.move_off); rep(mp, N, 30); end(mp, t.move_off, t.move_len);                                   // 1 AddNeutralMovement
+    begin(mp, t.move_off); rep(mp, F, 40); rep(mp, B, 10); rep(mp, F, 30); rep(mp, B, 10); end(mp, t.move_off, t.move_len); // 2 FarApproach1
+    begin(mp, t.move_off); dash(mp); rep(mp, B, 25); dash(mp); rep(mp, B, 25); end(mp, t.move_off, t.move_len);             // 3 FarApproach2
+    begin(mp, t.move_off); rep(mp, F, 30); rep(mp, B, 10); rep(mp, F, 20); rep(mp, B, 10); end(mp, t.move_off, t.move_len); // 4 MidApproach1
+    begin(mp, t.move_off); dash(mp); rep(mp, B, 30); end(mp, t.move_off, t.move_len);                         // 5 MidApproach2
+    begin(mp, t.move_off); rep(mp, B, 60); end(mp, t.move_off, t.move_len);                                   // 6 FallBack1
+    begin(mp, t.move_off); dash(mp); rep(mp, B, 60); end(mp, t.move_off, t.move_len);                         // 7 FallBack2
+    memcpy(t.move_pat, mp.data(), mp.size());
+    std::vector<uint8_t> apv;
+    const int A = 4;
+    id = 1;
+    begin(apv, t.att_off); rep(apv, 0, 30); end(apv, t.att_off, t.att_len);                                   // 1 AddNoAttack
+    begin(apv, t.att_off); rep(apv, A, 1); rep(apv, 0, 18); end(apv, t.att_off, t.att_len);                   // 2 OneHitImmediate
+    begin(apv, t.att_off); rep(apv, A, 1); rep(apv, 0, 3); rep(apv, A, 1); rep(apv, 0, 18); end(apv, t.att_off, t.att_len); // 3 TwoHitImmediate
+    begin(apv, t.att_off); rep(apv, A, 60); rep(apv, 0, 1); end(apv, t.att_off, t.att_len);                   // 4 ImmediateSpecial
+    begin(apv, t.att_off); rep(apv, A, 120); rep(apv, 0, 1); end(apv, t.att_off, t.att_len);                  // 5 DelaySpecial
+    memcpy(t.att_pat, apv.data(), apv.size());
+}
+
+}  // namespace
+
+struct fg_handle {
+    fg_config cfg;
+    fg_buffers buf;
+    bool bound;
+    Tables *d_tables;
+    int sm_count;
+    int64_t launches;
+    uint8_t *d_mask;       // staging for fg_reset_host
+};
+
+namespace {
+
+int grid_for(const fg_handle *h, int blocks_per_sm) {
+    int want = (h->cfg.num_envs + kThreads - 1) / kThreads;
+    int cap = h->sm_count * blocks_per_sm;
+    return want < cap ? (want > 0 ? want : 1) : cap;
+}
+
+Params make_params(const fg_handle *h) {
+    Params p;
+    memset(&p, 0, sizeof p);
+    p.pl_f1 = (uint4 *)h->buf.state[FG_PLANE_F1]; p.pl_f2 = (uint4 *)h->buf.state[FG_PLANE_F2];
+    p.pl_env = (uint4 *)h->buf.state[FG_PLANE_ENV]; p.pl_rng = (uint4 *)h->buf.state[FG_PLANE_RNG];
+    p.stats = (unsigned long long *)h->buf.stats;
+    p.act1 = h->buf.actions_p1; p.act2 = h->buf.actions_p2;
+    p.obs = (float4 *)h->buf.obs; p.reward = h->buf.reward; p.terminated = h->buf.terminated;
+    p.info_frame = h->buf.info_frame; p.info_misc = (uchar4 *)h->buf.info_misc;
+    p.tables = h->d_tables;
+    p.first_env_index = h->cfg.first_env_index;
+    p.n = h->cfg.num_envs; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
+    p.stale_intro = h->cfg.stale_intro_input;
+    return p;
+}
+
+template <bool KF, bool B1, bool B2>
+void launch_step_d(bool dense, int grid, cudaStream_t s, const Params &p) {
+    if (dense) step_kernel<KF, B1, B2, true><<<grid, kThreads, 0, s>>>(p);
+    else step_kernel<KF, B1, B2, false><<<grid, kThreads, 0, s>>>(p);
+}
+template <bool KF>
+void launch_step_k(const fg_config &c, int grid, cudaStream_t s, const Params &p) {
+    const bool d = c.dense_reward != 0;
+    if (c.p1_bot && c.p2_bot) launch_step_d<KF, true, true>(d, grid, s, p);
+    else if (c.p1_bot) launch_step_d<KF, true, false>(d, grid, s, p);
+    else if (c.p2_bot) launch_step_d<KF, false, true>(d, grid, s, p);
+    else launch_step_d<KF, false, false>(d, grid, s, p);
+}
+
+int check_bound(const fg_handle *h) {
+    if (!h) return fail(FG_ERR_INVALID_ARGUMENT, "null handle%s");
+    if (!h->bound) return fail(FG_ERR_NOT_BOUND, "fg_bind has not been called%s");
+    return FG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t fg_abi_version(void) { return FG_ABI_VERSION; }
+const char *fg_last_error(void) { return g_err; }
+
+int32_t fg_algorithmic_bytes_per_env_step(const fg_config *cfg) {
+    if (!cfg) return 0;
+    const bool rng = cfg->p1_bot || cfg->p2_bot;
+    int state = 2 * 16 * (rng ? 4 : 3);                 // planes read + written
+    int actions = (cfg->p1_bot ? 0 : 1) + (cfg->p2_bot ? 0 : 1);
+    return state + actions + 32 /*obs*/ + 4 /*reward*/ + 1 /*terminated*/ + 4 /*info frame*/ + 4 /*info misc*/;
+}
+
+int32_t fg_create(const fg_config *cfg, fg_handle **out) {
+    if (!cfg || !out) return fail(FG_ERR_INVALID_ARGUMENT, "null argument%s");
+    if (cfg->struct_size != (int32_t)sizeof(fg_config)) return fail(FG_ERR_INVALID_ARGUMENT, "fg_config.struct_size mismatch%s");
+    if (cfg->num_envs <= 0) return fail(FG_ERR_INVALID_ARGUMENT, "num_envs must be positive%s");
+    if (cfg->frame_skip < 1 || cfg->frame_skip > 64) return fail(FG_ERR_INVALID_ARGUMENT, "frame_skip must be in [1, 64]%s");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FG_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback%s");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(FG_ERR_INVALID_ARGUMENT, "device ordinal out of range%s");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    fg_handle *h = new (std::nothrow) fg_handle();
+    if (!h) return fail(FG_ERR_INVALID_STATE, "out of host memory%s");
+    h->cfg = *cfg;
+    h->bound = false;
+    h->launches = 0;
+    h->d_mask = nullptr;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    Tables *host = new Tables();
+    build_tables(*host);
+    cudaError_t e = cudaMalloc(&h->d_tables, sizeof(Tables));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_tables, host, sizeof(Tables), cudaMemcpyHostToDevice);
+    delete host;
+    if (e != cudaSuccess) { delete h; return fail(FG_ERR_CUDA, "table upload: %s", cudaGetErrorString(e)); }
+    *out = h;
+    return FG_OK;
+}
+
+void fg_destroy(fg_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_tables);
+    if (h->d_mask) cudaFree(h->d_mask);
+    delete h;
+}
+
+int32_t fg_bind(fg_handle *h, const fg_buffers *b) {
+    if (!h || !b) return fail(FG_ERR_INVALID_ARGUMENT, "null argument%s");
+    if (b->struct_size != (int32_t)sizeof(fg_buffers)) return fail(FG_ERR_INVALID_ARGUMENT, "fg_buffers.struct_size mismatch%s");
+    for (int k = 0; k < FG_STATE_PLANES; k++)
+        if (!b->state[k] || ((uintptr_t)b->state[k] & 15u)) return fail(FG_ERR_INVALID_ARGUMENT, "state planes must be non-null and 16-byte aligned%s");
+    if (!b->stats || !b->obs || !b->reward || !b->terminated || !b->info_frame || !b->info_misc)
+        return fail(FG_ERR_INVALID_ARGUMENT, "output buffers must be non-null%s");
+    if (((uintptr_t)b->obs & 15u) || ((uintptr_t)b->info_misc & 3u) || ((uintptr_t)b->stats & 7u))
+        return fail(FG_ERR_INVALID_ARGUMENT, "obs must be 16-byte, info_misc 4-byte, stats 8-byte aligned%s");
+    if (!h->cfg.p1_bot && !b->actions_p1) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p1 is required unless p1_bot%s");
+    if (!h->cfg.p2_bot && !b->actions_p2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
+    h->buf = *b;
+    h->bound = true;
+    return FG_OK;
+}
+
+int32_t fg_seed(fg_handle *h, int64_t seed_base, const uint8_t *mask, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    Params p = make_params(h);
+    p.mask = mask; p.seed_base = seed_base;
+    seed_kernel<<<grid_for(h, 8), kThreads, 0, (cudaStream_t)stream>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+int32_t fg_reset(fg_handle *h, const uint8_t *mask, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    Params p = make_params(h);
+    p.mask = mask;
+    const int grid = grid_for(h, 4);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->cfg.p1_bot && h->cfg.p2_bot) reset_kernel<true, true><<<grid, kThreads, 0, s>>>(p);
+    else if (h->cfg.p1_bot) reset_kernel<true, false><<<grid, kThreads, 0, s>>>(p);
+    else if (h->cfg.p2_bot) reset_kernel<false, true><<<grid, kThreads, 0, s>>>(p);
+    else reset_kernel<false, false><<<grid, kThreads, 0, s>>>(p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+int32_t fg_step(fg_handle *h, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const Params p = make_params(h);
+    const int grid = grid_for(h, 4);
+    if (h->cfg.frame_skip == 1) launch_step_k<false>(h->cfg, grid, (cudaStream_t)stream, p);
+    else launch_step_k<true>(h->cfg, grid, (cudaStream_t)stream, p);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+int32_t fg_step_host(fg_handle *h, const uint8_t *a1, const uint8_t *a2, float *obs, float *reward,
+                     uint8_t *terminated, int32_t *info_frame, uint8_t *info_misc, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.num_envs;
+    if (!h->cfg.p1_bot) {
+        if (!a1) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p1 is required unless p1_bot%s");
+        CUDA_TRY(cudaMemcpyAsync((void *)h->buf.actions_p1, a1, n, cudaMemcpyHostToDevice, s));
+    }
+    if (!h->cfg.p2_bot) {
+        if (!a2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
+        CUDA_TRY(cudaMemcpyAsync((void *)h->buf.actions_p2, a2, n, cudaMemcpyHostToDevice, s));
+    }
+    if (int rc = fg_step(h, stream)) return rc;
+    if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->buf.obs, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, h->buf.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (terminated) CUDA_TRY(cudaMemcpyAsync(terminated, h->buf.terminated, n, cudaMemcpyDeviceToHost, s));
+    if (info_frame) CUDA_TRY(cudaMemcpyAsync(info_frame, h->buf.info_frame, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (info_misc) CUDA_TRY(cudaMemcpyAsync(info_misc, h->buf.info_misc, n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return FG_OK;
+}
+
+int32_t fg_reset_host(fg_handle *h, const uint8_t *mask, float *obs, int32_t *info_frame, uint8_t *info_misc, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->cfg.num_envs;
+    const uint8_t *dmask = nullptr;
+    if (mask) {
+        if (!h->d_mask) CUDA_TRY(cudaMalloc(&h->d_mask, n));
+        CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s));
+        dmask = h->d_mask;
+    }
+    if (int rc = fg_reset(h, dmask, stream)) return rc;
+    if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->buf.obs, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (info_frame) CUDA_TRY(cudaMemcpyAsync(info_frame, h->buf.info_frame, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (info_misc) CUDA_TRY(cudaMemcpyAsync(info_misc, h->buf.info_misc, n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return FG_OK;
+}
+
+int32_t fg_get_state(fg_handle *h, int32_t first, int32_t count, fg_env_state *out) {
+    if (int rc = check_bound(h)) return rc;
+    if (!out || first < 0 || count < 0 || (int64_t)first + count > h->cfg.num_envs)
+        return fail(FG_ERR_INVALID_ARGUMENT, "env range out of bounds%s");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<FgVec4> pl[FG_STATE_PLANES];
+    for (int k = 0; k < FG_STATE_PLANES; k++) {
+        pl[k].resize((size_t)count);
+        CUDA_TRY(cudaMemcpy(pl[k].data(), (const FgVec4 *)h->buf.state[k] + first, sizeof(FgVec4) * (size_t)count, cudaMemcpyDeviceToHost));
+    }
+    for (int i = 0; i < count; i++)
+        fg_decode_env(pl[FG_PLANE_F1][i], pl[FG_PLANE_F2][i], pl[FG_PLANE_ENV][i], pl[FG_PLANE_RNG][i], &out[i]);
+    return FG_OK;
+}
+
+int32_t fg_set_state(fg_handle *h, int32_t first, int32_t count, const fg_env_state *in) {
+    if (int rc = check_bound(h)) return rc;
+    if (!in || first < 0 || count < 0 || (int64_t)first + count > h->cfg.num_envs)
+        return fail(FG_ERR_INVALID_ARGUMENT, "env range out of bounds%s");
+    std::vector<FgVec4> pl[FG_STATE_PLANES];
+    for (int k = 0; k < FG_STATE_PLANES; k++) pl[k].resize((size_t)count);
+    for (int i = 0; i < count; i++)
+        if (fg_encode_env(&in[i], &pl[FG_PLANE_F1][i], &pl[FG_PLANE_F2][i], &pl[FG_PLANE_ENV][i], &pl[FG_PLANE_RNG][i]))
+            return fail(FG_ERR_INVALID_STATE, "state not representable (unknown action id, WIN/has_won, or field out of range)%s");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int k = 0; k < FG_STATE_PLANES; k++)
+        CUDA_TRY(cudaMemcpy((FgVec4 *)h->buf.state[k] + first, pl[k].data(), sizeof(FgVec4) * (size_t)count, cudaMemcpyHostToDevice));
+    return FG_OK;
+}
+
+int32_t fg_read_stats(fg_handle *h, uint64_t *out, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    if (!out) return fail(FG_ERR_INVALID_ARGUMENT, "null output%s");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(out, h->buf.stats, sizeof(uint64_t) * FG_STAT_COUNT, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return FG_OK;
+}
+
+int64_t fg_launch_count(fg_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+// state_codec.h -- compact per-env battle state (64 B/env in four 16-byte SoA planes) and its
+// expanded form.  Shared by the CUDA kernels and the host-side fg_get_state / fg_set_state.
+//
+// Why this is enough (vs. the reference's 3 x 180 ints of input history per fighter, Fighter.cs:98-101):
+//   * dash detection reads Left/Right of input[0..16] only (Fighter.cs:585-635 with dashAllowFrame 9:
+//     i <= 8, j <= i + 8)                                   -> 16 stored frames + the new one = 17
+//   * the hold-release special reads "Attack held on input[1..59]" (Fighter.cs:569-583) -> a run length
+//     saturating at 59
+//   * inputDown / inputUp are functions of input[0], input[1] (Fighter.cs:184-185).
+#ifndef FOOTSIES_B200_STATE_CODEC_H
+#define FOOTSIES_B200_STATE_CODEC_H
+
+#include <stdint.h>
+#include "../../include/footsies_b200.h"
+#include "frame_tables.h"
+
+#if defined(__CUDACC__)
+#define FG_HD __host__ __device__ __forceinline__
+#else
+#define FG_HD static inline
+#endif
+
+// plane indices
+#define FG_PLANE_F1 0   // {pos_x bits, velocity_x bits, packed, hist}
+#define FG_PLANE_F2 1
+#define FG_PLANE_ENV 2  // {frame, misc, bot queue P2, bot queue P1}
+#define FG_PLANE_RNG 3  // xorshift128 state
+
+// packed fighter word
+#define FGP_ACT_SHIFT 0      // 5 bits: action index (moves.py order)
+#define FGP_FRAME_SHIFT 5    // 9 bits
+#define FGP_STUN_SHIFT 14    // 5 bits
+#define FGP_GUARD_SHIFT 19   // 2 bits
+#define FGP_VITAL_SHIFT 21   // 1 bit
+#define FGP_HITCNT_SHIFT 22  // 1 bit (numberOfHit == 1 for every attack)
+#define FGP_BUF_SHIFT 23     // 1 bit: bufferActionID == 110
+#define FGP_RSV_SHIFT 24     // 1 bit: reserveDamageActionID == 310
+#define FGP_INBACK_SHIFT 25  // 1 bit: isInputBackward
+#define FGP_RPROX_SHIFT 26   // 1 bit: isReserveProximityGuard
+#define FGP_SHAKE_SHIFT 27   // 4 bits two's complement: spriteShakePosition in [-6, 6]
+
+// misc env word
+#define FGM_ARUN1_SHIFT 0    // 6 bits: attack run length P1 (saturates at 59)
+#define FGM_ARUN2_SHIFT 6
+#define FGM_REC1_SHIFT 12    // 3 bits: last recorded input P1 (BattleCore.cs:593-607 stops recording after 18000 frames)
+#define FGM_REC2_SHIFT 15
+#define FGM_DONE_SHIFT 18    // battle over, waiting for reset
+#define FGM_CUM_SHIFT 19     // 4 bits: dense-reward automaton index
+#define FGM_ACTOR1_SHIFT 23  // 3 bits: input the P1 actor holds (TrainingRemoteActor.input / TrainingBattleAIActor.input)
+#define FGM_ACTOR2_SHIFT 26
+
+#define FG_MAX_RECORDING_INPUT_FRAME 18000  // BattleCore.cs:67
+
+struct FgVec4 { uint32_t x, y, z, w; };
+
+FG_HD uint32_t fg_bits(uint32_t v, int shift, int n) { return (v >> shift) & ((1u << n) - 1u); }
+
+FG_HD uint32_t fg_f2u(float f) { union { float f; uint32_t u; } c; c.f = f; return c.u; }
+FG_HD float fg_u2f(uint32_t u) { union { float f; uint32_t u; } c; c.u = u; return c.f; }
+
+// ---- host-side expansion (fg_get_state / fg_set_state) ----
+static const int FG_ACTION_IDS[FT_NUM_ACTIONS] = FT_ACTION_IDS_INIT;
+static const uint32_t FG_ACTION_INFO_H[FT_NUM_ACTIONS] = FT_ACTION_INFO_INIT;
+
+static inline int fg_action_index(int id) {
+    for (int i = 0; i < FT_NUM_ACTIONS; i++) if (FG_ACTION_IDS[i] == id) return i;
+    return -1;
+}
+
+static inline void fg_decode_fighter(const FgVec4 &v, uint32_t arun, fg_fighter_state *o) {
+    o->pos_x = fg_u2f(v.x);
+    o->velocity_x = fg_u2f(v.y);
+    uint32_t p = v.z;
+    o->action_id = FG_ACTION_IDS[fg_bits(p, FGP_ACT_SHIFT, 5) % FT_NUM_ACTIONS];
+    o->action_frame = (int)fg_bits(p, FGP_FRAME_SHIFT, 9);
+    o->hitstun = (int)fg_bits(p, FGP_STUN_SHIFT, 5);
+    o->guard = (int)fg_bits(p, FGP_GUARD_SHIFT, 2);
+    o->vital = (int)fg_bits(p, FGP_VITAL_SHIFT, 1);
+    o->hit_count = (int)fg_bits(p, FGP_HITCNT_SHIFT, 1);
+    o->buffer_id = fg_bits(p, FGP_BUF_SHIFT, 1) ? 110 : -1;
+    o->reserve_id = fg_bits(p, FGP_RSV_SHIFT, 1) ? 310 : -1;
+    o->is_input_backward = (int)fg_bits(p, FGP_INBACK_SHIFT, 1);
+    o->is_reserve_prox = (int)fg_bits(p, FGP_RPROX_SHIFT, 1);
+    o->shake = ((int32_t)(fg_bits(p, FGP_SHAKE_SHIFT, 4) << 28)) >> 28;
+    o->has_won = 0;
+    o->hist_left = v.w & 0xffffu;
+    o->hist_right = v.w >> 16;
+    o->attack_run = (int)arun;
+    o->input0 = (int)((o->hist_left & 1u) | (o->hist_right & 1u) << 1 | (arun > 0 ? 4u : 0u));
+}
+
+// returns 0 on success, -1 if the state cannot be represented
+static inline int fg_encode_fighter(const fg_fighter_state *s, FgVec4 *v, uint32_t *arun) {
+    int idx = fg_action_index(s->action_id);
+    if (idx < 0 || idx == FT_IDX_WIN || s->has_won) return -1;
+    int frame_count = (int)(FG_ACTION_INFO_H[idx] & 0x1ffu);
+    if (s->action_frame < 0 || s->action_frame > frame_count || s->action_frame > 511) return -1;
+    if (s->hitstun < 0 || s->hitstun > 31 || s->guard < 0 || s->guard > 3 || s->vital < 0 || s->vital > 1) return -1;
+    if (s->hit_count < 0 || s->hit_count > 1) return -1;
+    if (!(s->buffer_id == -1 || s->buffer_id == 110) || !(s->reserve_id == -1 || s->reserve_id == 310)) return -1;
+    if (s->shake < -6 || s->shake > 6 || s->attack_run < 0 || s->attack_run > 59) return -1;
+    if ((s->hist_left | s->hist_right) >> 16) return -1;
+    uint32_t p = (uint32_t)idx << FGP_ACT_SHIFT | (uint32_t)s->action_frame << FGP_FRAME_SHIFT
+               | (uint32_t)s->hitstun << FGP_STUN_SHIFT | (uint32_t)s->guard << FGP_GUARD_SHIFT
+               | (uint32_t)s->vital << FGP_VITAL_SHIFT | (uint32_t)s->hit_count << FGP_HITCNT_SHIFT
+               | (uint32_t)(s->buffer_id == 110) << FGP_BUF_SHIFT | (uint32_t)(s->reserve_id == 310) << FGP_RSV_SHIFT
+               | (uint32_t)(s->is_input_backward != 0) << FGP_INBACK_SHIFT
+               | (uint32_t)(s->is_reserve_prox != 0) << FGP_RPROX_SHIFT
+               | ((uint32_t)s->shake & 0xfu) << FGP_SHAKE_SHIFT;
+    v->x = fg_f2u(s->pos_x);
+    v->y = fg_f2u(s->velocity_x);
+    v->z = p;
+    v->w = (s->hist_left & 0xffffu) | (s->hist_right & 0xffffu) << 16;
+    *arun = (uint32_t)s->attack_run;
+    return 0;
+}
+
+static inline void fg_decode_env(const FgVec4 &f1, const FgVec4 &f2, const FgVec4 &e, const FgVec4 &r, fg_env_state *o) {
+    uint32_t m = e.y;
+    fg_decode_fighter(f1, fg_bits(m, FGM_ARUN1_SHIFT, 6), &o->f[0]);
+    fg_decode_fighter(f2, fg_bits(m, FGM_ARUN2_SHIFT, 6), &o->f[1]);
+    o->frame = (int32_t)e.x;
+    o->recorded_input[0] = (int)fg_bits(m, FGM_REC1_SHIFT, 3);
+    o->recorded_input[1] = (int)fg_bits(m, FGM_REC2_SHIFT, 3);
+    o->done = (int)fg_bits(m, FGM_DONE_SHIFT, 1);
+    o->cum_reward_index = (int)fg_bits(m, FGM_CUM_SHIFT, 4);
+    o->actor_input[0] = (int)fg_bits(m, FGM_ACTOR1_SHIFT, 3);
+    o->actor_input[1] = (int)fg_bits(m, FGM_ACTOR2_SHIFT, 3);
+    o->rng_state[0] = r.x; o->rng_state[1] = r.y; o->rng_state[2] = r.z; o->rng_state[3] = r.w;
+    o->bot_queue[0] = e.w; o->bot_queue[1] = e.z;
+}
+
+static inline int fg_encode_env(const fg_env_state *s, FgVec4 *f1, FgVec4 *f2, FgVec4 *e, FgVec4 *r) {
+    uint32_t a1 = 0, a2 = 0;
+    if (fg_encode_fighter(&s->f[0], f1, &a1) || fg_encode_fighter(&s->f[1], f2, &a2)) return -1;
+    if (s->cum_reward_index < 0 || s->cum_reward_index >= FT_NUM_CUM) return -1;
+    uint32_t m = a1 << FGM_ARUN1_SHIFT | a2 << FGM_ARUN2_SHIFT
+               | ((uint32_t)s->recorded_input[0] & 7u) << FGM_REC1_SHIFT | ((uint32_t)s->recorded_input[1] & 7u) << FGM_REC2_SHIFT
+               | (uint32_t)(s->done != 0) << FGM_DONE_SHIFT | (uint32_t)s->cum_reward_index << FGM_CUM_SHIFT
+               | ((uint32_t)s->actor_input[0] & 7u) << FGM_ACTOR1_SHIFT | ((uint32_t)s->actor_input[1] & 7u) << FGM_ACTOR2_SHIFT;
+    e->x = (uint32_t)s->frame; e->y = m; e->z = s->bot_queue[1]; e->w = s->bot_queue[0];
+    r->x = s->rng_state[0]; r->y = s->rng_state[1]; r->z = s->rng_state[2]; r->w = s->rng_state[3];
+    return 0;
+}
+#endif

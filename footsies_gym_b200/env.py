@@ -1,0 +1,412 @@
+"""Batched, B200-native drop-in for the reference's FootsiesEnv (footsies-gym/footsies_gym/envs/footsies.py).
+
+Same API surface -- reset / step / hard_reset / close / set_opponent / observation_space / action_space /
+reward_range / most_recent_observation / most_recent_info -- with a leading `num_envs` dimension: every
+call steps N independent battles on one GPU through libfootsies_b200.so (include/footsies_b200.h).  No game
+binary, no sockets, no CPU fallback.
+
+Differences from the single-process reference that a caller must know:
+  * observations / rewards / flags are torch tensors on the device, written IN PLACE by the kernel: the
+    tensors returned by step() are the same objects every call (clone what you need to keep);
+  * obs["guard"], obs["move"], obs["move_frame"], obs["position"] are float32 views [N, 2] of one [N, 8]
+    tensor (`env.obs`), which a policy network can consume directly;
+  * actions are a uint8 bitmask per env (Left=1, Right=2, Attack=4: the game's InputDefine,
+    InputData.cs:8-14, i.e. what wrappers/action_comb_disc.py produces) or an [N, 3] 0/1 tensor in the
+    reference's MultiBinary(3) order (left, right, attack);
+  * finished battles restart by themselves like the game does (BattleCore.cs:176-180): with
+    autoreset=True the step() after a terminal one returns the first observation of the next battle
+    (frame -1, reward 0, terminated False) and ignores the action, exactly the state the reference's
+    reset() would have read from the socket.
+"""
+import ctypes as C
+from typing import Callable, Optional, Union
+
+import numpy as np
+import torch
+
+from . import _capi
+from . import frame_data as _fd
+from .moves import FootsiesMove
+from .spaces import footsies_action_space, footsies_observation_space
+
+
+class FootsiesGameClosedError(RuntimeError):
+    """Kept for API compatibility with footsies_gym.envs.exceptions (never raised: there is no game process)."""
+
+
+def _as_bitmask(action, n, device):
+    """Accepts a uint8 bitmask [N], an [N, 3] (left, right, attack) array, or one 3-tuple for N == 1."""
+    if isinstance(action, torch.Tensor):
+        t = action
+    else:
+        t = torch.as_tensor(np.asarray(action))
+    if t.dim() == 1 and t.shape[0] == 3 and n == 1 and t.dtype in (torch.bool,):
+        t = t.reshape(1, 3)
+    if t.dim() == 2:
+        if t.shape != (n, 3):
+            raise ValueError(f"action must have shape ({n},) or ({n}, 3), got {tuple(t.shape)}")
+        t = t.to(torch.uint8)
+        t = t[:, 0] | (t[:, 1] << 1) | (t[:, 2] << 2)
+    elif t.dim() == 1:
+        if t.shape[0] == 3 and n == 1:
+            t = t.to(torch.uint8)
+            t = (t[0] | (t[1] << 1) | (t[2] << 2)).reshape(1)
+        elif t.shape[0] != n:
+            raise ValueError(f"action must have shape ({n},) or ({n}, 3), got {tuple(t.shape)}")
+    elif t.dim() == 0 and n == 1:
+        t = t.reshape(1)
+    else:
+        raise ValueError(f"unsupported action shape {tuple(t.shape)}")
+    return t.to(device=device, dtype=torch.uint8, non_blocking=True)
+
+
+class FootsiesEnv:
+    metadata = {"render_modes": [], "render_fps": 50}
+
+    def __init__(
+        self,
+        num_envs: int = 1,
+        device: Union[str, torch.device, None] = None,
+        frame_delay: int = 0,
+        render_mode: Optional[str] = None,
+        by_example: bool = False,
+        opponent: Union[Callable, str, None] = None,
+        vs_player: bool = False,
+        dense_reward: bool = True,
+        frame_skip: int = 1,
+        autoreset: bool = True,
+        seed: Optional[int] = 0,
+        first_env_index: int = 0,
+        stale_intro_input: bool = True,
+        **reference_kwargs,
+    ):
+        """
+        Parameters (reference names keep their meaning, footsies.py:34-97)
+        ----------
+        num_envs: battles stepped per call on this GPU
+        device: CUDA device (default: current device)
+        frame_delay: observations / info are delayed by this many frames (reward and termination are not)
+        by_example: P1 is driven by the in-game bot, actions passed to step() are ignored
+        opponent: None or "bot" -> in-game BattleAI (reference default); a callable `(obs, info) -> actions`
+            -> custom policy queried every step like the reference's `opponent`; "self_play" / "remote"
+            -> P2 actions are passed to step(action, opponent_action)
+        dense_reward: +-0.3 per guard point with terminal compensation, else sparse +-1
+        frame_skip: K >= 1 frames fused per step() with the action repeated; rewards are summed
+        autoreset: see module docstring
+        seed: per-env bot RNG = InitState(seed + first_env_index + i); None leaves the RNG planes zeroed
+        first_env_index: global index of env 0 (multi-GPU sharding keeps results independent of the split)
+        reference_kwargs: game_path, game_address, game_port, fast_forward, sync_mode, ... are accepted
+            and ignored (there is no game process to configure)
+        """
+        if render_mode is not None:
+            raise ValueError("render_mode is not supported: this simulator is headless")
+        if vs_player:
+            raise ValueError("vs_player is not supported: there is no human input device")
+        if opponent is not None and not callable(opponent) and opponent not in ("bot", "self_play", "remote"):
+            raise ValueError("opponent must be None, 'bot', 'self_play', 'remote' or a callable")
+        unknown = set(reference_kwargs) - {
+            "game_path", "game_address", "game_port", "skip_instancing", "fast_forward", "fast_forward_speed",
+            "sync_mode", "remote_control_port", "opponent_port", "log_file", "log_file_overwrite"}
+        if unknown:
+            raise TypeError(f"unexpected keyword arguments: {sorted(unknown)}")
+        if num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        if frame_delay < 0:
+            raise ValueError("frame_delay must be >= 0")
+        if not torch.cuda.is_available():
+            raise RuntimeError("footsies_gym_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if self.device.type != "cuda":
+            raise RuntimeError("footsies_gym_b200 runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.frame_delay = int(frame_delay)
+        self.by_example = bool(by_example)
+        self.opponent = opponent if callable(opponent) else None
+        self._opponent_mode = "bot" if opponent in (None, "bot") else "remote"
+        self.dense_reward = bool(dense_reward)
+        self.frame_skip = int(frame_skip)
+        self.autoreset = bool(autoreset)
+        self.first_env_index = int(first_env_index)
+        self.stale_intro_input = bool(stale_intro_input)
+        self.render_mode = None
+
+        relevant = [m for m in FootsiesMove if m.name not in ("WIN", "DEAD")]
+        self.observation_space = footsies_observation_space(len(relevant), max(m.value.duration for m in relevant))
+        self.action_space = footsies_action_space()
+        self.reward_range = (-1, 1)
+
+        self._lib = _capi.load()
+        self._handle = None
+        self._allocate()
+        self._create_handle()
+        self._seed_value = seed
+        if seed is not None:
+            self.seed(seed)
+        self.has_reset = False
+        self._most_recent_observation = None
+        self._most_recent_info = None
+
+    # ------------------------------------------------------------------ buffers / handle
+    def _allocate(self):
+        n, dev = self.num_envs, self.device
+        self.state = torch.zeros((_capi.FG_STATE_PLANES, n, 4), dtype=torch.int32, device=dev)
+        self.stats = torch.zeros(_capi.FG_STAT_COUNT, dtype=torch.int64, device=dev)
+        self.actions_p1 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.actions_p2 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.obs = torch.zeros((n, 8), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.terminated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)   # the reference never truncates (footsies.py:570)
+        self.info_frame = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.info_misc = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
+        self._obs_dict = self._make_obs_dict(self.obs)
+        self._info_dict = self._make_info_dict(self.info_frame, self.info_misc, self._obs_dict)
+        if self.frame_delay > 0:
+            d = self.frame_delay + 1
+            self._ring_obs = torch.zeros((d, n, 8), dtype=torch.float32, device=dev)
+            self._ring_frame = torch.zeros((d, n), dtype=torch.int32, device=dev)
+            self._ring_misc = torch.zeros((d, n, 4), dtype=torch.uint8, device=dev)
+            self._ring_pos = 0
+            self._delayed_obs = torch.zeros((n, 8), dtype=torch.float32, device=dev)
+            self._delayed_frame = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._delayed_misc = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
+            self._delayed_obs_dict = self._make_obs_dict(self._delayed_obs)
+            self._delayed_info_dict = self._make_info_dict(self._delayed_frame, self._delayed_misc, self._delayed_obs_dict)
+        # pinned host mirrors for the host-buffer (reference-facing) path, created on first use
+        self._host = None
+
+    @staticmethod
+    def _make_obs_dict(obs):
+        return {"guard": obs[:, 0:2], "move": obs[:, 2:4], "move_frame": obs[:, 4:6], "position": obs[:, 6:8]}
+
+    @staticmethod
+    def _make_info_dict(frame, misc, obs_dict):
+        d = {"frame": frame, "p1_action": misc[:, 0], "p2_action": misc[:, 1],
+             "p1_hitstun": misc[:, 2], "p2_hitstun": misc[:, 3]}
+        d.update(obs_dict)   # the reference copies the observation into info (footsies.py:378-379)
+        return d
+
+    def _config(self):
+        return _capi.FgConfig(
+            struct_size=C.sizeof(_capi.FgConfig), num_envs=self.num_envs, device=self.device.index,
+            p1_bot=int(self.by_example), p2_bot=int(self._opponent_mode == "bot"),
+            dense_reward=int(self.dense_reward), frame_skip=self.frame_skip, autoreset=int(self.autoreset),
+            stale_intro_input=int(self.stale_intro_input), reserved0=0, first_env_index=self.first_env_index)
+
+    def _create_handle(self):
+        if self._handle is not None:
+            self._lib.fg_destroy(self._handle)
+            self._handle = None
+        h = C.c_void_p()
+        cfg = self._config()
+        _capi.check(self._lib.fg_create(C.byref(cfg), C.byref(h)))
+        self._handle = h
+        b = _capi.FgBuffers()
+        b.struct_size = C.sizeof(_capi.FgBuffers)
+        for k in range(_capi.FG_STATE_PLANES):
+            b.state[k] = self.state[k].data_ptr()
+        b.stats = self.stats.data_ptr()
+        b.actions_p1 = self.actions_p1.data_ptr()
+        b.actions_p2 = self.actions_p2.data_ptr()
+        b.obs = self.obs.data_ptr()
+        b.reward = self.reward.data_ptr()
+        b.terminated = self.terminated.data_ptr()
+        b.info_frame = self.info_frame.data_ptr()
+        b.info_misc = self.info_misc.data_ptr()
+        _capi.check(self._lib.fg_bind(self._handle, C.byref(b)))
+        self.algorithmic_bytes_per_env_step = int(self._lib.fg_algorithmic_bytes_per_env_step(C.byref(cfg)))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ reference API
+    def seed(self, seed: int, mask: Optional[torch.Tensor] = None):
+        """Remote-control SEED (footsies.py:454-456): env i gets Random.InitState(seed + first_env_index + i)."""
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._lib.fg_seed(self._handle, int(seed), None if m is None else C.c_void_p(m.data_ptr()),
+                                      self._stream()))
+
+    def reset(self, *, seed: Optional[int] = None, options: Optional[dict] = None):
+        """Reset every env (or options={'mask': bool tensor [N]}); returns (obs, info) of frame -1 (footsies.py:482-515)."""
+        mask = None if not options else options.get("mask")
+        if seed is not None:
+            self.seed(seed, mask)
+        return self.hard_reset(mask)
+
+    def hard_reset(self, mask: Optional[torch.Tensor] = None):
+        """Force the selected envs (default all) back to the start of a battle (README.md:87, RESET command)."""
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        _capi.check(self._lib.fg_reset(self._handle, None if m is None else C.c_void_p(m.data_ptr()), self._stream()))
+        self.has_reset = True
+        if self.frame_delay > 0:
+            sel = slice(None) if m is None else m.bool()
+            self._ring_obs[:, sel] = self.obs[sel]          # queue pre-filled with the first state (footsies.py:502-504)
+            self._ring_frame[:, sel] = self.info_frame[sel]
+            self._ring_misc[:, sel] = self.info_misc[sel]
+            self._delayed_obs[sel] = self.obs[sel]
+            self._delayed_frame[sel] = self.info_frame[sel]
+            self._delayed_misc[sel] = self.info_misc[sel]
+        return self._finish_obs()
+
+    def step(self, action=None, opponent_action=None):
+        """One FootsiesEnv.step for all envs: returns (obs, reward, terminated, truncated, info) (footsies.py:518-570)."""
+        if not self.has_reset:
+            raise RuntimeError("call reset() before step()")
+        if not self.by_example:
+            if action is None:
+                raise ValueError("action is required unless by_example=True")
+            self.actions_p1.copy_(_as_bitmask(action, self.num_envs, self.device), non_blocking=True)
+        if self._opponent_mode != "bot":
+            if opponent_action is None:
+                if self.opponent is None:
+                    raise ValueError("opponent_action is required when the opponent is not the in-game bot")
+                opponent_action = self.opponent(self._most_recent_observation, self._most_recent_info)
+            self.actions_p2.copy_(_as_bitmask(opponent_action, self.num_envs, self.device), non_blocking=True)
+        _capi.check(self._lib.fg_step(self._handle, self._stream()))
+        if self.frame_delay > 0:
+            self._advance_delay_ring()
+        obs, info = self._finish_obs()
+        return obs, self.reward, self.terminated, self.truncated, info
+
+    def _advance_delay_ring(self):
+        # footsies.py:533-535: append the newest state, pop the oldest (queue length frame_delay + 1);
+        # an env that was just auto-reset restarts with a queue full of its first state (footsies.py:502-504)
+        d = self.frame_delay + 1
+        was_reset = self.info_frame == -1
+        if bool(was_reset.any()):
+            self._ring_obs[:, was_reset] = self.obs[was_reset]
+            self._ring_frame[:, was_reset] = self.info_frame[was_reset]
+            self._ring_misc[:, was_reset] = self.info_misc[was_reset]
+        p = self._ring_pos
+        self._ring_obs[p].copy_(self.obs)
+        self._ring_frame[p].copy_(self.info_frame)
+        self._ring_misc[p].copy_(self.info_misc)
+        self._ring_pos = (p + 1) % d
+        o = self._ring_pos                      # oldest entry
+        self._delayed_obs.copy_(self._ring_obs[o])
+        self._delayed_frame.copy_(self._ring_frame[o])
+        self._delayed_misc.copy_(self._ring_misc[o])
+        # the DEAD -> STAND remap is applied to the delayed state when it is emitted (footsies.py:538-552);
+        # the kernel already applied it to the undelayed observation it wrote, so nothing more to do here.
+
+    def _finish_obs(self):
+        if self.frame_delay > 0:
+            obs, info = self._delayed_obs_dict, self._delayed_info_dict
+        else:
+            obs, info = self._obs_dict, self._info_dict
+        self._most_recent_observation, self._most_recent_info = obs, info
+        return obs, info
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None:
+            self._lib.fg_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def set_opponent(self, opponent: Optional[Callable]):
+        """Switch P2 between a custom policy and the in-game bot (footsies.py:458-480, P2_BOT command).
+        Returns True: like the reference recommends, call reset() afterwards."""
+        self.opponent = opponent
+        mode = "bot" if opponent is None else "remote"
+        if mode != self._opponent_mode:
+            self._opponent_mode = mode
+            torch.cuda.synchronize(self.device)
+            self._create_handle()
+        return True
+
+    @property
+    def most_recent_observation(self):
+        return self._most_recent_observation
+
+    @property
+    def most_recent_info(self):
+        return self._most_recent_info
+
+    # ------------------------------------------------------------------ host-buffer (reference-facing) path
+    def _host_buffers(self):
+        if self._host is None:
+            n = self.num_envs
+            pin = dict(pin_memory=True)
+            self._host = dict(
+                a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
+                obs=torch.zeros((n, 8), dtype=torch.float32, **pin), reward=torch.zeros(n, dtype=torch.float32, **pin),
+                terminated=torch.zeros(n, dtype=torch.bool, **pin), info_frame=torch.zeros(n, dtype=torch.int32, **pin),
+                info_misc=torch.zeros((n, 4), dtype=torch.uint8, **pin))
+        return self._host
+
+    def step_host(self, action=None, opponent_action=None):
+        """step() for callers that live on the CPU like the reference's agents: actions are read from host
+        memory and obs / reward / terminated / info are delivered to pinned host tensors (one C call:
+        H2D copy, kernel, D2H copies, sync).  Returns host tensors (reused between calls)."""
+        if not self.has_reset:
+            raise RuntimeError("call reset() before step()")
+        hb = self._host_buffers()
+        p1 = p2 = None
+        if not self.by_example:
+            a = _as_bitmask(action, self.num_envs, "cpu")
+            if a.data_ptr() != hb["a1"].data_ptr():
+                hb["a1"].copy_(a)
+            p1 = C.c_void_p(hb["a1"].data_ptr())
+        if self._opponent_mode != "bot":
+            if opponent_action is None:
+                raise ValueError("opponent_action is required when the opponent is not the in-game bot")
+            a = _as_bitmask(opponent_action, self.num_envs, "cpu")
+            if a.data_ptr() != hb["a2"].data_ptr():
+                hb["a2"].copy_(a)
+            p2 = C.c_void_p(hb["a2"].data_ptr())
+        _capi.check(self._lib.fg_step_host(
+            self._handle, p1, p2, C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["reward"].data_ptr()),
+            C.c_void_p(hb["terminated"].data_ptr()), C.c_void_p(hb["info_frame"].data_ptr()),
+            C.c_void_p(hb["info_misc"].data_ptr()), self._stream()))
+        obs = self._make_obs_dict(hb["obs"])
+        info = self._make_info_dict(hb["info_frame"], hb["info_misc"], obs)
+        return obs, hb["reward"], hb["terminated"], torch.zeros_like(hb["terminated"]), info
+
+    def host_io_bytes_per_step(self):
+        """(host->device, device->host) bytes moved by one step_host call."""
+        n = self.num_envs
+        h2d = n * ((0 if self.by_example else 1) + (0 if self._opponent_mode == "bot" else 1))
+        d2h = n * (32 + 4 + 1 + 4 + 4)
+        return h2d, d2h
+
+    # ------------------------------------------------------------------ state access, statistics
+    def get_state(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
+        """Expanded per-env state as a numpy structured array (fg_env_state)."""
+        count = self.num_envs - first if count is None else count
+        out = np.zeros(count, dtype=_capi.env_state_dtype())
+        _capi.check(self._lib.fg_get_state(self._handle, int(first), int(count), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def set_state(self, states: np.ndarray, first: int = 0):
+        states = np.ascontiguousarray(states, dtype=_capi.env_state_dtype())
+        _capi.check(self._lib.fg_set_state(self._handle, int(first), len(states), C.c_void_p(states.ctypes.data)))
+
+    def episode_stats(self) -> dict:
+        """Episode statistics accumulated on the device by the step kernel's warp reductions."""
+        out = np.zeros(_capi.FG_STAT_COUNT, dtype=np.uint64)
+        _capi.check(self._lib.fg_read_stats(self._handle, C.c_void_p(out.ctypes.data), self._stream()))
+        return {k: int(v) for k, v in zip(_capi.STAT_NAMES, out)}
+
+    def all_reduce_stats(self) -> dict:
+        """End-of-rollout statistics summed over all ranks (the only collective on this path)."""
+        from .distributed import all_reduce_stats
+        return all_reduce_stats(self.stats)
+
+    def launch_count(self) -> int:
+        return int(self._lib.fg_launch_count(self._handle))
+
+    # reference helper kept for completeness (footsies.py:590-614): there are no ports to find
+    @staticmethod
+    def find_ports(start: int, step: int = 1, stop=None):
+        raise RuntimeError("find_ports is meaningless here: the simulator uses no sockets")
+
+
+MOVE_DURATIONS = list(_fd.MOVE_DURATIONS)

@@ -1,0 +1,159 @@
+/*
+ * footsies_b200.h -- C ABI of the B200-native batched FOOTSIES simulator (libfootsies_b200.so).
+ *
+ * The reference (martinhoT/Footsies-Gym) has no FFI: its de-facto boundary is the Gymnasium API of
+ * FootsiesEnv (footsies-gym/footsies_gym/envs/footsies.py:20-588) on top of a TCP protocol to the Unity
+ * game (footsies.py:261-334, Assets/Script/SocketHelper.cs:48-82, TrainingRemoteControl.cs:18-107).
+ * This library replaces everything below that API -- process, sockets, JSON and the C# battle engine --
+ * for N independent battles per call.  Each entry point names the reference interface it stands in for.
+ *
+ * Conventions: plain pointers and sizes only; every function returns FG_OK (0) or a negative fg_status;
+ * fg_last_error() returns a thread-local message for the last failure; nothing throws.  The library never
+ * allocates or frees the buffers passed to fg_bind (the host language owns them, e.g. torch tensors).
+ * `stream` arguments are a cudaStream_t passed as void* (NULL = default stream); device-buffer entry
+ * points only enqueue work and return.  One handle per GPU / host thread; handles share no mutable state.
+ */
+#ifndef FOOTSIES_B200_H
+#define FOOTSIES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FG_ABI_VERSION 1
+
+typedef enum {
+    FG_OK = 0,
+    FG_ERR_INVALID_ARGUMENT = -1,
+    FG_ERR_NOT_BOUND = -2,
+    FG_ERR_CUDA = -3,
+    FG_ERR_NO_DEVICE = -4,
+    FG_ERR_INVALID_STATE = -5
+} fg_status;
+
+/* Opponent / actor wiring (GameManager.cs:184-205 flags --p1-bot / --p2-bot, footsies.py:230-247). */
+typedef struct {
+    int32_t struct_size;        /* sizeof(fg_config), for ABI evolution                                   */
+    int32_t num_envs;           /* battles stepped per call on this device                                */
+    int32_t device;             /* CUDA device ordinal                                                    */
+    int32_t p1_bot;             /* 1: P1 is the in-game BattleAI (FootsiesEnv by_example)                 */
+    int32_t p2_bot;             /* 1: P2 is the in-game BattleAI (opponent=None); 0: P2 from actions_p2   */
+    int32_t dense_reward;       /* FootsiesEnv dense_reward (footsies.py:388-405), else sparse (:382-386) */
+    int32_t frame_skip;         /* K >= 1 frames fused per fg_step with the same action; stops at KO      */
+    int32_t autoreset;          /* 0: finished battles freeze until fg_reset; 1: the step after a terminal
+                                   one performs the reset and returns the frame -1 state                  */
+    int32_t stale_intro_input;  /* 1 = reference behaviour: the Intro frame replays the actors' last input */
+    int32_t reserved0;
+    int64_t first_env_index;    /* global index of env 0 (multi-GPU sharding; seeds use global indices)   */
+} fg_config;
+
+/* Compact battle state: 4 planes of 16 bytes per env (64 B/env), structure-of-arrays, 16-byte aligned.
+ * Layout of the words is private to the library (see csrc/state_codec.h); use fg_get_state/fg_set_state. */
+#define FG_STATE_PLANES 4
+#define FG_STATE_PLANE_BYTES_PER_ENV 16
+
+enum { FG_STAT_EPISODES = 0, FG_STAT_P1_WINS, FG_STAT_P2_WINS, FG_STAT_DOUBLE_KO, FG_STAT_EPISODE_FRAMES,
+       FG_STAT_P1_SPECIALS, FG_STAT_P1_SPECIALS_NEUTRAL, FG_STAT_GUARD_BREAKS, FG_STAT_HITS, FG_STAT_BLOCKS,
+       FG_STAT_ENV_FRAMES,      /* fight frames simulated: the env-frames counter of the throughput metric */
+       FG_STAT_RESETS, FG_STAT_COUNT = 16 };
+
+/* All pointers are DEVICE pointers owned by the caller and must stay valid while bound. */
+typedef struct {
+    int32_t struct_size;
+    int32_t reserved0;
+    void *state[FG_STATE_PLANES];   /* each: 16 * num_envs bytes, 16-byte aligned                         */
+    uint64_t *stats;                /* [FG_STAT_COUNT] episode statistics (wrappers/statistics.py:26-50 and
+                                       the win-rate loop footsies.py:657-661), accumulated by warp reductions */
+    const uint8_t *actions_p1;      /* [num_envs] bitmask Left=1 Right=2 Attack=4 (InputData.cs:8-14; the
+                                       3 bytes FootsiesEnv._send_action sends, footsies.py:323-334, packed) */
+    const uint8_t *actions_p2;      /* [num_envs] same for P2; may be NULL when p2_bot                     */
+    float *obs;                     /* [num_envs][8]: guard p1,p2 | move index p1,p2 | move_frame p1,p2 |
+                                       position p1,p2  (FootsiesEnv._extract_obs, footsies.py:336-368)     */
+    float *reward;                  /* [num_envs] (footsies.py:382-405)                                    */
+    uint8_t *terminated;            /* [num_envs] p1Vital == 0 or p2Vital == 0 (footsies.py:555)           */
+    int32_t *info_frame;            /* [num_envs] info["frame"] (footsies.py:370-380)                      */
+    uint8_t *info_misc;             /* [num_envs][4]: p1_action mask, p2_action mask, p1_hitstun, p2_hitstun */
+} fg_buffers;
+
+/* Expanded, readable per-env state (superset of EnvironmentState.cs:12-26; the fields of
+ * FighterState.cs:26-56 that survive compaction).  Same field order as the test oracle's trace. */
+typedef struct {
+    float pos_x;
+    float velocity_x;
+    int32_t action_id;          /* CommonActionID value (Fighter.cs:42-61), e.g. 110                      */
+    int32_t action_frame;
+    int32_t hitstun;
+    int32_t guard;
+    int32_t vital;
+    int32_t hit_count;
+    int32_t buffer_id;          /* -1 or 110                                                              */
+    int32_t reserve_id;         /* -1 or 310                                                              */
+    int32_t is_input_backward;
+    int32_t is_reserve_prox;
+    int32_t shake;              /* spriteShakePosition                                                    */
+    int32_t has_won;            /* always 0: WIN is unreachable in training            */
+    int32_t input0;             /* input applied on the most recent frame                                 */
+    uint32_t hist_left;         /* bit i: Left held i frames ago, i < 16                                  */
+    uint32_t hist_right;
+    int32_t attack_run;         /* consecutive most-recent frames with Attack held, saturating at 59      */
+} fg_fighter_state;
+
+typedef struct {
+    fg_fighter_state f[2];
+    int32_t frame;              /* BattleCore.frameCount                                                  */
+    int32_t recorded_input[2];  /* p{1,2}MostRecentAction (BattleCore.cs:463-464)                         */
+    int32_t done;               /* battle is over and waiting for a reset                                 */
+    int32_t cum_reward_index;   /* index into the dense-reward automaton                                  */
+    int32_t actor_input[2];     /* input each actor holds for the next frame (bots: already decided)      */
+    uint32_t rng_state[4];      /* per-env xorshift128 standing in for UnityEngine.Random                 */
+    uint32_t bot_queue[2];      /* per bot: move pattern[0:3) cursor[3:10) attack pattern[10:13) cursor[13:20) */
+} fg_env_state;
+
+typedef struct fg_handle fg_handle;
+
+/* Library / build identification. */
+int32_t fg_abi_version(void);
+const char *fg_last_error(void);
+/* Bytes of algorithmic HBM traffic of ONE single-frame fg_step for one env (state read + write, actions,
+ * obs, reward, terminated, info) under the given config -- the numerator of the roofline in bench.py. */
+int32_t fg_algorithmic_bytes_per_env_step(const fg_config *cfg);
+
+/* Replaces: FootsiesEnv.__init__ + _instantiate_game + _connect_to_game (footsies.py:34-290). */
+int32_t fg_create(const fg_config *cfg, fg_handle **out);
+/* Replaces: FootsiesEnv.close (footsies.py:572-578). */
+void fg_destroy(fg_handle *h);
+int32_t fg_bind(fg_handle *h, const fg_buffers *buffers);
+
+/* Replaces: remote-control SEED (footsies.py:454-456, BattleCore.cs:170-173): per env
+ * Random.InitState(seed_base + global env index).  mask: device uint8[num_envs] or NULL = all. */
+int32_t fg_seed(fg_handle *h, int64_t seed_base, const uint8_t *mask, void *stream);
+/* Replaces: FootsiesEnv.reset / remote-control RESET (footsies.py:482-515, BattleCore.cs:143-146, 262-291):
+ * Stop -> Intro -> one Intro frame -> Fight; writes the frame -1 observation.  mask as above. */
+int32_t fg_reset(fg_handle *h, const uint8_t *mask, void *stream);
+/* Replaces: FootsiesEnv.step (footsies.py:518-570) for all envs: frame_skip fused BattleCore fight frames
+ * (BattleCore.cs:201-220, 347-364) + bot query (TrainingManager.cs:59-77) + obs / reward / termination. */
+int32_t fg_step(fg_handle *h, void *stream);
+/* Same as fg_step but with HOST buffers (the reference-facing call: actions come from and results go to
+ * host memory like the reference's socket messages): H2D actions, step, D2H results, synchronises.
+ * Any output pointer may be NULL to skip that copy.  actions_p2 may be NULL when p2_bot. */
+int32_t fg_step_host(fg_handle *h, const uint8_t *actions_p1, const uint8_t *actions_p2, float *obs,
+                     float *reward, uint8_t *terminated, int32_t *info_frame, uint8_t *info_misc, void *stream);
+/* Host-buffer variant of fg_reset: mask is a HOST uint8[num_envs] or NULL; copies back obs / info. */
+int32_t fg_reset_host(fg_handle *h, const uint8_t *mask, float *obs, int32_t *info_frame, uint8_t *info_misc,
+                      void *stream);
+
+/* Replaces: remote-control STATE_SAVE / STATE_LOAD (footsies.py:432-444, BattleCore.cs:667-683) at the level
+ * of the compact state.  out / in are HOST arrays of `count` entries starting at env `first`. Synchronous. */
+int32_t fg_get_state(fg_handle *h, int32_t first, int32_t count, fg_env_state *out);
+int32_t fg_set_state(fg_handle *h, int32_t first, int32_t count, const fg_env_state *in);
+/* Copies the statistics vector to the host (synchronises `stream`). */
+int32_t fg_read_stats(fg_handle *h, uint64_t *out /* FG_STAT_COUNT */, void *stream);
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
+int64_t fg_launch_count(fg_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
