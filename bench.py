@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""Throughput benchmark of the batched FOOTSIES frame update (BASELINE.json metric: env-frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs-per-gpu E]
+
+One "step" = one FootsiesEnv.step over every env of the rank (frame-skip 1: one BattleCore fight frame per
+env).  Workload (config D of SURVEY.md §8, weak-scaled so that each GPU's working set exceeds the 126 MB L2):
+random-action P1 (iid uniform over the 8 input bitmasks) vs the in-game BattleAI, auto-reset on KO.
+Env-frames are counted by the kernel's own simulated-frame counter, not as N x K.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over ranks);
+`e2e` = the same metric through the host-buffer C-ABI call (pinned host actions in, results out);
+`roofline` = algorithmic HBM bytes per launch / measured launch time vs MEASURED_PEAKS.json;
+`cpu_baseline` = the CPU oracle port on this box's host cores (rank 0, N = 1 only).
+`--impl reference` times that CPU port alone on the same workload definition.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "env_frames_per_sec"
+UNIT = "env-frames/s"
+DEFAULT_ENVS_PER_GPU = 4 * 1024 * 1024
+WORKLOAD = ("D-weak: random-action P1 vs in-game BattleAI, frame-skip 1, auto-reset, "
+            "{n} envs per GPU (BASELINE configs[3] weak-scaled so the per-GPU working set exceeds L2)")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=DEFAULT_ENVS_PER_GPU)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        rows = []
+        for ts, ln in self.lines:
+            if t0 <= ts <= t1 + 0.06:
+                parts = [x.strip() for x in ln.split(",")]
+                if len(parts) >= 9:
+                    rows.append(parts)
+        if not rows:
+            return None
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def cpu_oracle_throughput(n_envs, seconds, threads, seed=1234):
+    """The CPU port (oracle) on the same workload definition; returns (frames/s, frames, elapsed, steps)."""
+    import numpy as np
+    import oracle_binding as ob
+    orc = ob.OracleBatch(n_envs, p2_bot=True, seed=0, threads=threads)
+    orc.trace = None  # no per-env trace copies in the timed loop
+    ob.lib().fo_reset(orc.h, None, None)
+    rng = np.random.default_rng(seed)
+    tapes = [rng.integers(0, 8, size=n_envs, dtype=np.uint8) for _ in range(16)]
+    for i in range(3):
+        ob.lib().fo_step(orc.h, tapes[i].ctypes.data, None, 1, None, threads)
+    f0 = orc.frames_simulated()
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        ob.lib().fo_step(orc.h, tapes[steps % 16].ctypes.data, None, 1, None, threads)
+        steps += 1
+        if time.perf_counter() - t0 >= seconds:
+            break
+    dt = time.perf_counter() - t0
+    frames = orc.frames_simulated() - f0
+    return frames / dt, frames, dt, steps
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  The game binary / C# engine cannot run offline, so this is
+    the oracle port (kind "port") on all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_envs = 32768
+    import numpy as np
+    import oracle_binding as ob
+    orc = ob.OracleBatch(n_envs, p2_bot=True, seed=0, threads=threads)
+    ob.lib().fo_reset(orc.h, None, None)
+    rng = np.random.default_rng(1234)
+    tapes = [rng.integers(0, 8, size=n_envs, dtype=np.uint8) for _ in range(16)]
+    for i in range(args.warmup):
+        ob.lib().fo_step(orc.h, tapes[i % 16].ctypes.data, None, 1, None, threads)
+    f0 = orc.frames_simulated()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ob.lib().fo_step(orc.h, tapes[i % 16].ctypes.data, None, 1, None, threads)
+    dt = time.perf_counter() - t0
+    frames = orc.frames_simulated() - f0
+    value = frames / dt
+    sample = f"{n_envs} envs x {args.steps} steps on {threads} host threads (bounded sample of the workload)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(args.steps, 1) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(n=args.envs_per_gpu), "reference_sample": sample,
+                   "note": "reference game binary + FootsiesEnv not runnable offline (no Unity/mono, no binary); "
+                           "this is the scalar C restatement of its battle logic (oracle/)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from footsies_gym_b200 import FootsiesEnv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.envs_per_gpu
+    env = FootsiesEnv(num_envs=n, device=dev, opponent=None, seed=0, first_env_index=rank * n)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    n_tapes = 8
+    tapes = [torch.randint(0, 8, (n,), generator=gen, device=dev, dtype=torch.uint8) for _ in range(n_tapes)]
+
+    def device_step(i):
+        env.bind_actions(tapes[i % n_tapes])     # zero-copy: the kernel reads the resident tape directly
+        env.step_bound()
+
+    for i in range(max(args.warmup, 3)):
+        device_step(i)
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+
+    # ---------------- timed region: K device-resident steps ----------------
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    frames_before = env.episode_stats()["env_frames"]
+    launches_before = env.launch_count()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        device_step(i)
+    ev1.record()
+    barrier()
+    wall1 = time.time()
+    ms_local = ev0.elapsed_time(ev1)
+    frames_local = env.episode_stats()["env_frames"] - frames_before
+    launches = env.launch_count() - launches_before
+
+    clocks = None
+    if rank == 0:
+        clocks = sampler.summary(wall0, wall1)
+        if clocks is None or clocks["samples"] < 3:
+            # region too short to sample: repeat the identical load for ~1.2 s just to read the clocks
+            w0 = time.time()
+            i = 0
+            while time.time() - w0 < 1.2:
+                for _ in range(20):
+                    device_step(i)
+                    i += 1
+                torch.cuda.synchronize(dev)
+            w1 = time.time()
+            clocks = sampler.summary(w0, w1) or {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            clocks["sampled"] = "identical launch loop right after the timed region (region shorter than the sampler period)"
+        sampler.stop()
+
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    f = torch.tensor([frames_local], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    ms_total = float(t.item())
+    frames_total = int(f.item())
+    value = frames_total / (ms_total * 1e-3)
+
+    # ---------------- e2e: the host-buffer C-ABI call (pinned host actions in, results out) ----------------
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    host_tapes = [tp.cpu().pin_memory() for tp in tapes[:4]]
+    env.bind_actions(torch.zeros(n, dtype=torch.uint8, device=dev))   # staging buffer for the host actions
+    for i in range(2):
+        env.step_host(host_tapes[i % 4])
+    fb = env.episode_stats()["env_frames"]
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        obs_h, rew_h, term_h, _, info_h = env.step_host(host_tapes[i % 4])
+    torch.cuda.synchronize(dev)
+    e2e_dt = time.perf_counter() - t0
+    e2e_frames = env.episode_stats()["env_frames"] - fb
+    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
+    fe = torch.tensor([e2e_frames], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fe, op=dist.ReduceOp.SUM)
+    e2e_value = int(fe.item()) / float(te.item())
+    h2d, d2h = env.host_io_bytes_per_step()
+
+    # ---------------- end-of-rollout statistics all-reduce (the only collective on the path) ----------------
+    stats = env.all_reduce_stats()
+
+    # ---------------- extra single-GPU workloads (parity-gate configs, informational) ----------------
+    extra = {}
+    if rank == 0 and not args.no_extra:
+        def quick(n_envs, frame_skip, self_play, steps=200):
+            e = FootsiesEnv(num_envs=n_envs, device=dev, opponent="self_play" if self_play else None,
+                            frame_skip=frame_skip, seed=0)
+            e.reset()
+            a1 = [torch.randint(0, 8, (n_envs,), generator=gen, device=dev, dtype=torch.uint8) for _ in range(4)]
+            a2 = [torch.randint(0, 8, (n_envs,), generator=gen, device=dev, dtype=torch.uint8) for _ in range(4)]
+            for i in range(10):
+                e.bind_actions(a1[i % 4], a2[i % 4] if self_play else None)
+                e.step_bound()
+            torch.cuda.synchronize(dev)
+            f0 = e.episode_stats()["env_frames"]
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(steps):
+                e.bind_actions(a1[i % 4], a2[i % 4] if self_play else None)
+                e.step_bound()
+            s1.record()
+            torch.cuda.synchronize(dev)
+            ms = s0.elapsed_time(s1)
+            fr = e.episode_stats()["env_frames"] - f0
+            e.close()
+            return {"env_frames_per_sec": fr / (ms * 1e-3), "ms_per_step": ms / steps, "envs": n_envs,
+                    "frame_skip": frame_skip, "opponent": "self_play" if self_play else "bot",
+                    "note": "working set fits L2 (launch/latency-bound regime)"}
+        extra["B_4096_bot_k1"] = quick(4096, 1, False)
+        extra["C_65536_selfplay_k4"] = quick(65536, 4, True)
+        extra["1Mi_bot_k1"] = quick(1 << 20, 1, False)
+        extra["1Mi_bot_k4"] = quick(1 << 20, 4, False, steps=100)
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, frames, dt, steps = cpu_oracle_throughput(32768, args.cpu_seconds, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"32768 envs x {steps} steps ({frames} env-frames, {dt:.1f} s) of the same "
+                                  f"random-vs-bot workload on {threads} host threads; oracle/ C restatement "
+                                  f"(reference game binary not runnable offline)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        bytes_per_env = env.algorithmic_bytes_per_env_step
+        ms_per_launch = ms_total / max(args.steps, 1)
+        achieved = bytes_per_env * n / (ms_per_launch * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_launch, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(n=n), "envs_per_gpu": n, "frame_skip": 1, "opponent": "bot",
+                       "actions": "iid uniform over 8 bitmasks, torch.Generator(device).manual_seed(1234 + rank)",
+                       "l2": f"inputs larger than L2: {2 * 64 * n / 1e6:.0f} MB of state traffic + "
+                             f"{46 * n / 1e6:.0f} MB of outputs per step vs 126 MB L2; no flush",
+                       "frames_counted": "kernel simulated-frame counter (FG_STAT_ENV_FRAMES)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_env_frame": bytes_per_env, "peak_source": peak_src,
+                         "kernel": "step_kernel<K=1, P2 bot, dense>"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "FootsiesEnv.step_host -> fg_step_host (pinned host buffers)"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "episode_stats_all_ranks": stats,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -204,6 +204,11 @@ class FootsiesEnv:
         cfg = self._config()
         _capi.check(self._lib.fg_create(C.byref(cfg), C.byref(h)))
         self._handle = h
+        cfg2 = self._config()
+        self._bind()
+        self.algorithmic_bytes_per_env_step = int(self._lib.fg_algorithmic_bytes_per_env_step(C.byref(cfg2)))
+
+    def _bind(self):
         b = _capi.FgBuffers()
         b.struct_size = C.sizeof(_capi.FgBuffers)
         for k in range(_capi.FG_STATE_PLANES):
@@ -217,7 +222,6 @@ class FootsiesEnv:
         b.info_frame = self.info_frame.data_ptr()
         b.info_misc = self.info_misc.data_ptr()
         _capi.check(self._lib.fg_bind(self._handle, C.byref(b)))
-        self.algorithmic_bytes_per_env_step = int(self._lib.fg_algorithmic_bytes_per_env_step(C.byref(cfg)))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -265,6 +269,29 @@ class FootsiesEnv:
                     raise ValueError("opponent_action is required when the opponent is not the in-game bot")
                 opponent_action = self.opponent(self._most_recent_observation, self._most_recent_info)
             self.actions_p2.copy_(_as_bitmask(opponent_action, self.num_envs, self.device), non_blocking=True)
+        _capi.check(self._lib.fg_step(self._handle, self._stream()))
+        if self.frame_delay > 0:
+            self._advance_delay_ring()
+        obs, info = self._finish_obs()
+        return obs, self.reward, self.terminated, self.truncated, info
+
+    def bind_actions(self, actions_p1: Optional[torch.Tensor] = None, actions_p2: Optional[torch.Tensor] = None):
+        """Zero-copy action input: make the kernel read its actions straight from the given device tensors
+        (uint8 [N] bitmasks, e.g. a policy's output buffer) from now on; then call step_bound()."""
+        for t in (actions_p1, actions_p2):
+            if t is not None and (t.dtype != torch.uint8 or t.shape != (self.num_envs,) or t.device != self.device
+                                  or not t.is_contiguous()):
+                raise ValueError("bound action tensors must be contiguous uint8 [num_envs] on the env's device")
+        if actions_p1 is not None:
+            self.actions_p1 = actions_p1
+        if actions_p2 is not None:
+            self.actions_p2 = actions_p2
+        self._bind()
+
+    def step_bound(self):
+        """step() without any action copy: the kernel reads the tensors given to bind_actions()."""
+        if not self.has_reset:
+            raise RuntimeError("call reset() before step()")
         _capi.check(self._lib.fg_step(self._handle, self._stream()))
         if self.frame_delay > 0:
             self._advance_delay_ring()
