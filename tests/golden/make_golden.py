@@ -1,0 +1,295 @@
+#!/usr/bin/env python3
+"""Generate golden vectors with the REFERENCE's own, unmodified Python code.
+
+Runs only in the authoring container (needs /root/reference).  It imports the reference's
+`footsies_gym.envs.footsies.FootsiesEnv` (gymnasium is not installed, so a minimal stand-in module is put in
+sys.modules first -- the reference code itself is untouched) and lets it talk over its real TCP protocol
+(footsies.py:261-334, 407-456; SocketHelper.cs:48-82; TrainingRemoteControl.cs:18-107) to a small game server
+whose battle engine is the CPU oracle.  Everything the reference computes in Python -- observation dict,
+move-index mapping, DEAD->STAND remap, move_frame simplification, info, dense / sparse reward, termination,
+frame_delay queue, reset semantics -- is recorded as the expected answer.
+
+What this pins: the Python half of the path and the EnvironmentState field mapping
+(a15).  What it cannot pin: the C# engine itself (the oracle plays the game's part here).
+
+Output: tests/golden/ref_python_<name>.npz, one per scenario:
+  ops        int32 [M, 4]  what the game did, in order: (kind, a, b, expect_index)
+                           kind 0 = fight frame with P1 action a, P2 action b; 1 = round start (reset);
+                           2 = Random.InitState(a)
+  exp_*      the reference's outputs for every reset() / step() call, indexed by expect_index
+"""
+import json
+import os
+import socket
+import struct
+import sys
+import threading
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF_PY = "/root/reference/footsies-gym"
+
+
+def install_gymnasium_stub():
+    from footsies_gym_b200 import spaces as sp
+    gym = types.ModuleType("gymnasium")
+
+    class Env:
+        def reset(self, *, seed=None, options=None):
+            return None
+
+    class Wrapper:
+        def __init__(self, env):
+            self.env = env
+
+    gym.Env = Env
+    gym.Wrapper = gym.ObservationWrapper = gym.ActionWrapper = Wrapper
+    spaces = types.ModuleType("gymnasium.spaces")
+    spaces.Dict, spaces.MultiDiscrete, spaces.Box = sp.Dict, sp.MultiDiscrete, sp.Box
+    spaces.MultiBinary, spaces.Discrete = sp.MultiBinary, sp.Discrete
+    utils = types.ModuleType("gymnasium.spaces.utils")
+    utils.unflatten = lambda space, x: x
+    spaces.utils = utils
+    spaces.Space = object
+    envs = types.ModuleType("gymnasium.envs")
+    reg = types.ModuleType("gymnasium.envs.registration")
+    reg.register = lambda **kw: None
+    envs.registration = reg
+    gym.spaces, gym.envs = spaces, envs
+    for name, mod in (("gymnasium", gym), ("gymnasium.spaces", spaces), ("gymnasium.spaces.utils", utils),
+                      ("gymnasium.envs", envs), ("gymnasium.envs.registration", reg)):
+        sys.modules[name] = mod
+
+
+def free_ports(k):
+    socks, ports = [], []
+    for _ in range(k):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        ports.append(s.getsockname()[1])
+        socks.append(s)
+    for s in socks:
+        s.close()
+    return ports
+
+
+class OracleGameServer(threading.Thread):
+    """Plays the Unity game's role on the wire; the battle engine behind it is the CPU oracle."""
+
+    def __init__(self, ports, p2_remote, seed0=0):
+        super().__init__(daemon=True)
+        import oracle_binding as ob
+        self.ob = ob
+        self.ports = ports
+        self.p2_remote = p2_remote
+        # game side only: the oracle's own python half is irrelevant here (autoreset off, delay 0)
+        self.orc = ob.OracleBatch(1, p2_bot=not p2_remote, autoreset=False, seed=seed0)
+        self.ops = []
+        self.listeners = []
+        for p in ports[: 3 if p2_remote else 2]:
+            ls = socket.socket()
+            ls.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            ls.bind(("127.0.0.1", p))
+            ls.listen(1)
+            self.listeners.append(ls)
+        self.stop_flag = False
+
+    def state_json(self):
+        t = self.orc.trace[0]
+        f1, f2 = t["f"][0], t["f"][1]
+        d = {
+            "p1Vital": int(f1["vital"]), "p2Vital": int(f2["vital"]), "p1Guard": int(f1["guard"]),
+            "p2Guard": int(f2["guard"]), "p1Move": int(f1["action_id"]), "p1MoveFrame": int(f1["action_frame"]),
+            "p2Move": int(f2["action_id"]), "p2MoveFrame": int(f2["action_frame"]),
+            "p1Position": float(f1["pos_x"]), "p2Position": float(f2["pos_x"]), "globalFrame": int(t["frame"]),
+            "p1MostRecentAction": int(t["recorded_input"][0]), "p2MostRecentAction": int(t["recorded_input"][1]),
+            "p1Hitstun": int(f1["hitstun"]), "p2Hitstun": int(f2["hitstun"]),
+        }
+        return json.dumps(d).encode("utf-8")
+
+    @staticmethod
+    def send_msg(sock, payload):
+        sock.sendall(struct.pack("!I", len(payload)) + payload)       # SocketHelper.cs:70-82
+
+    @staticmethod
+    def recv_exact(sock, n):
+        buf = b""
+        while len(buf) < n:
+            chunk = sock.recv(n - len(buf))
+            if not chunk:
+                raise ConnectionError("peer closed")
+            buf += chunk
+        return buf
+
+    def round_start(self):
+        self.orc.reset()
+        self.ops.append((1, 0, 0))
+        self.send_msg(self.p1, self.state_json())
+
+    def run(self):
+        import select
+        # accept order mirrors FootsiesEnv._connect_to_game: P1, remote control, then the opponent
+        self.p1, _ = self.listeners[0].accept()
+        self.rc, _ = self.listeners[1].accept()
+        self.p2 = None
+        if self.p2_remote:
+            self.p2, _ = self.listeners[2].accept()
+        try:
+            self.round_start()
+            while not self.stop_flag:
+                r, _, _ = select.select([self.p1, self.rc], [], [], 0.2)
+                if self.rc in r:                                       # TrainingRemoteControl.ProcessCommand
+                    size = struct.unpack("!I", self.recv_exact(self.rc, 4))[0]
+                    msg = json.loads(self.recv_exact(self.rc, size).decode("utf-8"))
+                    if msg["command"] == 1:                            # RESET
+                        self.round_start()
+                    elif msg["command"] == 5:                          # SEED
+                        self.orc.seed(int(msg["value"]))
+                        self.ops.append((2, int(msg["value"]), 0))
+                    continue
+                if self.p1 in r:
+                    a = self.recv_exact(self.p1, 3)                    # TrainingRemoteActor.cs:93-116
+                    a1 = (1 if a[0] else 0) | (2 if a[1] else 0) | (4 if a[2] else 0)
+                    a2 = 0
+                    if self.p2 is not None:
+                        b = self.recv_exact(self.p2, 3)
+                        a2 = (1 if b[0] else 0) | (2 if b[1] else 0) | (4 if b[2] else 0)
+                    self.orc.step([a1], [a2])
+                    self.ops.append((0, a1, a2))
+                    self.send_msg(self.p1, self.state_json())
+                    if self.orc.trace[0]["battle_over"]:               # the game restarts by itself
+                        self.round_start()
+        except (ConnectionError, OSError):
+            pass
+
+
+def flat_obs(obs):
+    return [obs["guard"][0], obs["guard"][1], obs["move"][0], obs["move"][1],
+            obs["move_frame"][0], obs["move_frame"][1], obs["position"][0], obs["position"][1]]
+
+
+def mask3(t):
+    return int(t[0]) | int(t[1]) << 1 | int(t[2]) << 2
+
+
+def run_scenario(name, *, dense, frame_delay, p2_remote, n_calls, rng_seed, seeds_at_reset=True):
+    from footsies_gym.envs.footsies import FootsiesEnv   # the reference class, unmodified
+    ports = free_ports(3)
+    server = OracleGameServer(ports, p2_remote)
+    server.start()
+    rng = np.random.default_rng(rng_seed)
+    p2_tape = []
+
+    def opponent(obs, info):
+        a = int(rng.integers(0, 8))
+        p2_tape.append(a)
+        return (a & 1 != 0, a & 2 != 0, a & 4 != 0)
+
+    env = FootsiesEnv(frame_delay=frame_delay, game_address="127.0.0.1", game_port=ports[0],
+                      remote_control_port=ports[1], opponent_port=ports[2], skip_instancing=True,
+                      sync_mode="synced_non_blocking", dense_reward=dense,
+                      opponent=opponent if p2_remote else None)
+    exp = {k: [] for k in ("kind", "obs", "reward", "terminated", "truncated", "frame", "action", "hitstun")}
+
+    def record(kind, obs, reward, terminated, truncated, info):
+        exp["kind"].append(kind)
+        exp["obs"].append(flat_obs(obs))
+        exp["reward"].append(float(reward))
+        exp["terminated"].append(int(terminated))
+        exp["truncated"].append(int(truncated))
+        exp["frame"].append(int(info["frame"]))
+        exp["action"].append([mask3(info["p1_action"]), mask3(info["p2_action"])])
+        exp["hitstun"].append([int(info["p1_hitstun"]), int(info["p2_hitstun"])])
+        for k in ("guard", "move", "move_frame", "position"):   # info carries a copy of obs (footsies.py:378-379)
+            assert tuple(info[k]) == tuple(obs[k])
+
+    # client-side log of which expectation belongs to which game op
+    call_ops = []
+    episode = 0
+    obs, info = env.reset(seed=1000)
+    record(1, obs, 0.0, False, False, info)
+    call_ops.append("reset")
+    steps_in_episode = 0
+    sticky = 0
+    for _ in range(n_calls):
+        if rng.random() < 0.15:
+            sticky = int(rng.integers(0, 8))
+        a = sticky if rng.random() < 0.7 else int(rng.integers(0, 8))
+        obs, reward, terminated, truncated, info = env.step((a & 1 != 0, a & 2 != 0, a & 4 != 0))
+        record(0, obs, reward, terminated, truncated, info)
+        call_ops.append("step")
+        steps_in_episode += 1
+        force = (not terminated) and steps_in_episode > 40 and rng.random() < 0.004
+        if terminated or force:
+            episode += 1
+            seed = 2000 + episode if (seeds_at_reset and episode % 3 == 0) else None
+            obs, info = env.reset(seed=seed)
+            record(1, obs, 0.0, False, False, info)
+            call_ops.append("reset")
+            steps_in_episode = 0
+    server.stop_flag = True
+    env.close()
+    server.join(timeout=5)
+
+    # attach expectation indices to the game ops: every step op <-> one step() call in order; every reset()
+    # call <-> the LAST round start before the next fight frame (earlier ones were never observed)
+    ops = server.ops
+    step_calls = [i for i, k in enumerate(call_ops) if k == "step"]
+    reset_calls = [i for i, k in enumerate(call_ops) if k == "reset"]
+    out = np.full((len(ops), 4), -1, dtype=np.int32)
+    si = 0
+    for j, (kind, a, b) in enumerate(ops):
+        out[j, :3] = (kind, a, b)
+        if kind == 0:
+            out[j, 3] = step_calls[si]
+            si += 1
+    assert si == len(step_calls)
+    # walk the client calls and the ops together to place the reset expectations
+    j = 0
+    last_round_start = None
+    for i, k in enumerate(call_ops):
+        if k == "step":
+            while ops[j][0] != 0:
+                if ops[j][0] == 1:
+                    last_round_start = j
+                j += 1
+            j += 1
+        else:
+            # the observed round start is the last kind-1 op before the next kind-0 op (or the end)
+            jj = j
+            cand = None
+            while jj < len(ops) and ops[jj][0] != 0:
+                if ops[jj][0] == 1:
+                    cand = jj
+                jj += 1
+            if cand is None:
+                cand = last_round_start
+            out[cand, 3] = i
+    path = os.path.join(HERE, f"ref_python_{name}.npz")
+    np.savez_compressed(
+        path, ops=out, exp_kind=np.array(exp["kind"], np.int8), exp_obs=np.array(exp["obs"], np.float64),
+        exp_reward=np.array(exp["reward"], np.float64), exp_terminated=np.array(exp["terminated"], np.int8),
+        exp_truncated=np.array(exp["truncated"], np.int8), exp_frame=np.array(exp["frame"], np.int32),
+        exp_action=np.array(exp["action"], np.int8), exp_hitstun=np.array(exp["hitstun"], np.int8),
+        p2_tape=np.array(p2_tape, np.int8),
+        config=np.array([int(dense), frame_delay, int(p2_remote), 0], np.int32))
+    n_ep = int(np.sum(np.array(exp["terminated"])))
+    print(f"{name}: {len(ops)} game ops, {len(call_ops)} API calls, {n_ep} terminations -> {os.path.relpath(path, ROOT)}")
+
+
+def main():
+    install_gymnasium_stub()
+    sys.path.insert(0, REF_PY)
+    run_scenario("dense_bot", dense=True, frame_delay=0, p2_remote=False, n_calls=6000, rng_seed=1)
+    run_scenario("sparse_bot", dense=False, frame_delay=0, p2_remote=False, n_calls=3000, rng_seed=2)
+    run_scenario("dense_delay3_bot", dense=True, frame_delay=3, p2_remote=False, n_calls=3000, rng_seed=3)
+    run_scenario("dense_remote_p2", dense=True, frame_delay=0, p2_remote=True, n_calls=4000, rng_seed=4)
+
+
+if __name__ == "__main__":
+    main()
