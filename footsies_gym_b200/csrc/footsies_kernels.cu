@@ -72,11 +72,13 @@ struct Params {
     int n, frame_skip, autoreset, stale_intro;
 };
 
-// event bits of one simulated frame (one ballot each in the stats reduction)
-enum : uint32_t { EV_EPISODE = 1u << 0, EV_P1_WIN = 1u << 1, EV_P2_WIN = 1u << 2, EV_DOUBLE_KO = 1u << 3,
-                  EV_SPECIAL = 1u << 4, EV_SPECIAL_NEUTRAL = 1u << 5, EV_GUARD_BREAK_A = 1u << 6, EV_HIT_A = 1u << 7,
-                  EV_BLOCK_A = 1u << 8, EV_GUARD_BREAK_B = 1u << 9, EV_HIT_B = 1u << 10, EV_BLOCK_B = 1u << 11,
-                  EV_RESET = 1u << 12 };
+// Per-thread packed statistics: three 32-bit words of four 8-bit lanes each, bumped once per frame and folded
+// by a warp reduction when a thread has gone kStatFlushFrames frames without a flush (and at kernel end).
+//   A: episodes | P1 wins | P2 wins | double KOs      (1 << 8*w trick: w = winner code)
+//   R: (none)   | hits    | blocks  | guard breaks    (1 << 8*DamageResult for each of the two attack passes)
+//   S: specials | specials-from-neutral | resets | (unused)
+struct StatAcc { uint32_t a, r, s; };
+constexpr uint32_t kStatFlushFrames = 120u;   // <= 2 events per lane per frame -> a byte lane cannot overflow
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
@@ -390,42 +392,29 @@ __device__ __forceinline__ void store_env(const Params &p, int i, const Env &e) 
     if (WITH_RNG) p.pl_rng[i] = make_uint4(e.r0, e.r1, e.r2, e.r3);
 }
 
-// Warp-cooperative statistics: lane b of every warp owns counter b; one ballot + popc per event bit.
-struct StatAcc {
-    unsigned long long mine;   // lane-specialised accumulator
-    __device__ __forceinline__ void add_frame(uint32_t ev, int32_t ep_frames, int lane) {
-        if (!__any_sync(kFull, ev != 0u)) return;
-        // counters: 0 episodes 1 p1 wins 2 p2 wins 3 double ko 4 episode frames 5 specials 6 specials-from-neutral
-        //           7 guard breaks 8 hits 9 blocks 11 resets
-        const uint32_t b_ep = __ballot_sync(kFull, ev & EV_EPISODE), b_w1 = __ballot_sync(kFull, ev & EV_P1_WIN);
-        const uint32_t b_w2 = __ballot_sync(kFull, ev & EV_P2_WIN), b_dk = __ballot_sync(kFull, ev & EV_DOUBLE_KO);
-        const uint32_t b_sp = __ballot_sync(kFull, ev & EV_SPECIAL), b_sn = __ballot_sync(kFull, ev & EV_SPECIAL_NEUTRAL);
-        const uint32_t gb = __popc(__ballot_sync(kFull, ev & EV_GUARD_BREAK_A)) + __popc(__ballot_sync(kFull, ev & EV_GUARD_BREAK_B));
-        const uint32_t hi = __popc(__ballot_sync(kFull, ev & EV_HIT_A)) + __popc(__ballot_sync(kFull, ev & EV_HIT_B));
-        const uint32_t bl = __popc(__ballot_sync(kFull, ev & EV_BLOCK_A)) + __popc(__ballot_sync(kFull, ev & EV_BLOCK_B));
-        const uint32_t b_rs = __ballot_sync(kFull, ev & EV_RESET);
-        const uint32_t fr = __reduce_add_sync(kFull, (uint32_t)ep_frames);
-        uint32_t v = 0u;
-        v = lane == FG_STAT_EPISODES ? __popc(b_ep) : v;
-        v = lane == FG_STAT_P1_WINS ? __popc(b_w1) : v;
-        v = lane == FG_STAT_P2_WINS ? __popc(b_w2) : v;
-        v = lane == FG_STAT_DOUBLE_KO ? __popc(b_dk) : v;
-        v = lane == FG_STAT_EPISODE_FRAMES ? fr : v;
-        v = lane == FG_STAT_P1_SPECIALS ? __popc(b_sp) : v;
-        v = lane == FG_STAT_P1_SPECIALS_NEUTRAL ? __popc(b_sn) : v;
-        v = lane == FG_STAT_GUARD_BREAKS ? gb : v;
-        v = lane == FG_STAT_HITS ? hi : v;
-        v = lane == FG_STAT_BLOCKS ? bl : v;
-        v = lane == FG_STAT_RESETS ? __popc(b_rs) : v;
-        mine += v;
-    }
-};
+// Warp-cooperative fold of the packed per-thread counters into the CTA's shared-memory vector.
+__device__ __forceinline__ void flush_stats(StatAcc &acc, unsigned long long *s_stats, int lane) {
+    const uint32_t w[3] = { acc.a, acc.r, acc.s };
+    // (word, byte lane) -> statistic index; -1 = unused
+    const int map[3][4] = { { FG_STAT_EPISODES, FG_STAT_P1_WINS, FG_STAT_P2_WINS, FG_STAT_DOUBLE_KO },
+                            { -1, FG_STAT_HITS, FG_STAT_BLOCKS, FG_STAT_GUARD_BREAKS },
+                            { FG_STAT_P1_SPECIALS, FG_STAT_P1_SPECIALS_NEUTRAL, FG_STAT_RESETS, -1 } };
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            if (map[k][b] < 0) continue;
+            const uint32_t tot = __reduce_add_sync(kFull, (w[k] >> (8 * b)) & 255u);
+            if (lane == 0 && tot) atomicAdd(&s_stats[map[k][b]], (unsigned long long)tot);
+        }
+    acc.a = 0u; acc.r = 0u; acc.s = 0u;
+}
 
 // One fight frame for one env (everything between "inputs known" and "state after the frame").
-// Returns event bits; sets `terminal`, accumulates the Python float64 reward into `reward`.
+// Sets `terminal`, accumulates the Python float64 reward into `reward`, bumps the packed statistics.
 template <bool P1BOT, bool P2BOT, bool DENSE>
-__device__ __forceinline__ uint32_t simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, double &reward,
-                                                   bool &terminal, int32_t &ep_frames) {
+__device__ __forceinline__ void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, double &reward,
+                                               bool &terminal, StatAcc &acc, unsigned long long *s_stats) {
     // state the bots will be shown after this frame (previous call's capture == state before this frame)
     const float pre_dist = fabsf(e.pos2 - e.pos1);
     const uint32_t pre_a1 = e.pk1 & 31u, pre_a2 = e.pk2 & 31u;
@@ -468,14 +457,10 @@ __device__ __forceinline__ uint32_t simulate_frame(const Tables &T, Env &e, uint
     const uint32_t res_a = attack_pass<0>(T, e.pk1, e.pk2, f1, f2, s1, t1, s2, t2);   // result on P2
     const uint32_t res_b = attack_pass<1>(T, e.pk2, e.pk1, f2, f1, s2, t2, s1, t1);   // result on P1
 
-    uint32_t ev = 0u;
-    ev |= res_a == 3u ? EV_GUARD_BREAK_A : res_a == 2u ? EV_BLOCK_A : res_a == 1u ? EV_HIT_A : 0u;
-    ev |= res_b == 3u ? EV_GUARD_BREAK_B : res_b == 2u ? EV_BLOCK_B : res_b == 1u ? EV_HIT_B : 0u;
+    acc.r += (1u << (8u * res_a)) + (1u << (8u * res_b));                // byte lane = DamageResult of each pass
     const uint32_t a1 = e.pk1 & 31u;
-    if (a1 != pre_a1 && (a1 == N_SPECIAL || a1 == B_SPECIAL)) {         // wrappers/statistics.py:36-46
-        ev |= EV_SPECIAL;
-        if (pre_a1 != N_ATTACK && pre_a1 != B_ATTACK) ev |= EV_SPECIAL_NEUTRAL;
-    }
+    if (a1 != pre_a1 && (a1 == N_SPECIAL || a1 == B_SPECIAL))           // wrappers/statistics.py:36-46
+        acc.s += (pre_a1 != N_ATTACK && pre_a1 != B_ATTACK) ? 0x101u : 1u;
 
     // ---- KO (BattleCore.cs:212-217), termination (footsies.py:555) ----
     const bool dead1 = !((e.pk1 >> FGP_VITAL_SHIFT) & 1u), dead2 = !((e.pk2 >> FGP_VITAL_SHIFT) & 1u);
@@ -498,8 +483,8 @@ __device__ __forceinline__ uint32_t simulate_frame(const Tables &T, Env &e, uint
     if (terminal) {
         // ChangeRoundState(KO): ClearInput on both fighters (BattleCore.cs:292-299); actors keep their inputs
         e.hist1 = 0u; e.hist2 = 0u; arun1 = 0u; arun2 = 0u;
-        ev |= EV_EPISODE | (dead1 && dead2 ? EV_DOUBLE_KO : dead2 ? EV_P1_WIN : EV_P2_WIN);
-        ep_frames = e.frame + 1;
+        acc.a += 1u + (1u << (8u * (dead1 && dead2 ? 3u : dead2 ? 1u : 2u)));
+        atomicAdd(&s_stats[FG_STAT_EPISODE_FRAMES], (unsigned long long)(e.frame + 1));   // rare: once per episode
         e.misc |= 1u << FGM_DONE_SHIFT;
     }
     // ---- TrainingManager.Step (TrainingManager.cs:59-77): actors' inputs for the next frame; bots are asked
@@ -511,69 +496,149 @@ __device__ __forceinline__ uint32_t simulate_frame(const Tables &T, Env &e, uint
     }
     e.misc = (e.misc & ~((63u << FGM_ARUN1_SHIFT) | (63u << FGM_ARUN2_SHIFT) | (63u << FGM_ACTOR1_SHIFT)))
            | arun1 << FGM_ARUN1_SHIFT | arun2 << FGM_ARUN2_SHIFT | n1 << FGM_ACTOR1_SHIFT | n2 << FGM_ACTOR2_SHIFT;
-    return ev;
 }
 
+// ---- TMA (1-D bulk async copy) + mbarrier helpers: the state planes of the NEXT chunk of 256 envs stream into
+//      shared memory while the current chunk is being simulated ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kStages = 2;
+template <int PLANES> struct __align__(128) StageBuf { uint4 pl[PLANES][kThreads]; };
+
 // FootsiesEnv.step for every env: up to K fused fight frames, or the reset of a finished env (autoreset).
+// Persistent CTAs walk chunks of 256 consecutive envs; chunk c+grid is prefetched by one elected thread with
+// 3-4 bulk copies of 4 KB (one per state plane) while chunk c is simulated out of registers.
 template <bool KFUSED, bool P1BOT, bool P2BOT, bool DENSE>
 __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
+    constexpr bool kRng = P1BOT || P2BOT;
+    constexpr int kPlanes = kRng ? 4 : 3;
     __shared__ Tables T;
+    __shared__ StageBuf<kPlanes> stage[kStages];
+    __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
     __shared__ unsigned long long s_stats[FG_STAT_COUNT];
     load_tables(&T, p.tables);
     if (threadIdx.x < FG_STAT_COUNT) s_stats[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full_bar[s], 1u); mbar_init(&empty_bar[s], kThreads / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    constexpr bool kRng = P1BOT || P2BOT;
     const int lane = threadIdx.x & 31;
-    StatAcc acc; acc.mine = 0ull;
-    uint32_t frames_done = 0u;
-    const int n_round = (p.n + 31) & ~31;                               // keep warps converged for the ballots
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const int num_chunks = (p.n + kThreads - 1) / kThreads;
+    const int full_chunks = p.n / kThreads;                             // chunks that can be bulk-copied whole
+    const uint4 *const planes[4] = { p.pl_f1, p.pl_f2, p.pl_env, p.pl_rng };
+    auto issue = [&](int chunk, int s) {                                // elected thread only
+        mbar_expect_tx(&full_bar[s], (uint32_t)(kPlanes * kThreads * sizeof(uint4)));
+#pragma unroll
+        for (int k = 0; k < kPlanes; k++)
+            tma_load_1d(stage[s].pl[k], planes[k] + (size_t)chunk * kThreads, (uint32_t)(kThreads * sizeof(uint4)), &full_bar[s]);
+    };
+    if (threadIdx.x == 0 && (int)blockIdx.x < full_chunks) issue(blockIdx.x, 0);
+
+    StatAcc acc = { 0u, 0u, 0u };
+    uint32_t frames_done = 0u, frames_since_flush = 0u;
+    // actions are prefetched one chunk ahead into registers
+    uint32_t nin1 = 0u, nin2 = 0u;
+    {
+        const int i0 = blockIdx.x * kThreads + threadIdx.x;
+        if (i0 < p.n) { if (!P1BOT) nin1 = p.act1[i0]; if (!P2BOT) nin2 = p.act2[i0]; }
+    }
+    int k = 0;
+    for (int c = blockIdx.x; c < num_chunks; c += gridDim.x, k++) {
+        const int s = k & 1;
+        const int i = c * kThreads + threadIdx.x;
         const bool valid = i < p.n;
+        const bool staged = c < full_chunks;
+        if (threadIdx.x == 0) {                                         // producer: next chunk -> the other stage
+            const int cn = c + gridDim.x;
+            if (cn < full_chunks) {
+                if (k >= 1) mbar_wait(&empty_bar[s ^ 1], ((k - 1) >> 1) & 1);   // every warp has read chunk k-1
+                issue(cn, s ^ 1);
+            }
+        }
+        const uint32_t act1 = nin1, act2 = nin2;
+        {
+            const int in = i + gridDim.x * kThreads;
+            if (in < p.n) { if (!P1BOT) nin1 = p.act1[in]; if (!P2BOT) nin2 = p.act2[in]; }
+        }
         Env e;
         bool run = false;
-        uint32_t ev0 = 0u, in1 = 0u, in2 = 0u;
+        uint32_t in1 = 0u, in2 = 0u;
+        if (staged) {
+            mbar_wait(&full_bar[s], (k >> 1) & 1);
+            const uint4 a = stage[s].pl[0][threadIdx.x], b = stage[s].pl[1][threadIdx.x], cc = stage[s].pl[2][threadIdx.x];
+            e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
+            e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
+            e.frame = (int32_t)cc.x; e.misc = cc.y; e.bq2 = cc.z; e.bq1 = cc.w;
+            if (kRng) { const uint4 r = stage[s].pl[kPlanes - 1][threadIdx.x]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        } else if (valid) {
+            load_env<kRng>(p, i, e);                                    // ragged tail chunk: plain loads
+        }
         if (valid) {
-            load_env<kRng>(p, i, e);
             if ((e.misc >> FGM_DONE_SHIFT) & 1u) {
                 if (p.autoreset) {                                      // next-step autoreset: this call only resets
                     reset_env<P1BOT, P2BOT>(T, e, p.stale_intro != 0);
                     store_env<kRng>(p, i, e);
                     write_outputs(p, i, e, 0.0f, false);
-                    ev0 = EV_RESET;
+                    acc.s += 0x10000u;
                 } else {
                     p.reward[i] = 0.0f;                                 // frozen until fg_reset
                 }
             } else {
                 run = true;
-                in1 = P1BOT ? (e.misc >> FGM_ACTOR1_SHIFT) & 7u : p.act1[i] & 7u;
-                in2 = P2BOT ? (e.misc >> FGM_ACTOR2_SHIFT) & 7u : p.act2[i] & 7u;
+                in1 = P1BOT ? (e.misc >> FGM_ACTOR1_SHIFT) & 7u : act1 & 7u;
+                in2 = P2BOT ? (e.misc >> FGM_ACTOR2_SHIFT) & 7u : act2 & 7u;
             }
         }
         double reward = 0.0;
         bool terminal = false;
         const int K = KFUSED ? p.frame_skip : 1;
-        for (int k = 0; k < K; k++) {                                   // uniform trip count: the ballots stay converged
-            uint32_t ev = k == 0 ? ev0 : 0u;
-            int32_t ep_frames = 0;
+        for (int kk = 0; kk < K; kk++) {
             if (run && !terminal) {
-                ev |= simulate_frame<P1BOT, P2BOT, DENSE>(T, e, in1, in2, reward, terminal, ep_frames);
+                simulate_frame<P1BOT, P2BOT, DENSE>(T, e, in1, in2, reward, terminal, acc, s_stats);
                 frames_done++;
                 if (KFUSED) {
                     if (P1BOT) in1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u;
                     if (P2BOT) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
                 }
             }
-            acc.add_frame(ev, ep_frames, lane);
         }
         if (run) {
             store_env<kRng>(p, i, e);
             write_outputs(p, i, e, (float)reward, terminal);
         }
+        frames_since_flush += (uint32_t)K;                              // uniform across the CTA
+        if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, s_stats, lane); frames_since_flush = 0u; }
     }
-    // block-level fold of the lane-specialised counters, then one atomic per counter per CTA
+    flush_stats(acc, s_stats, lane);
     const uint32_t fsum = __reduce_add_sync(kFull, frames_done);
-    if (lane == FG_STAT_ENV_FRAMES) acc.mine += fsum;
-    if (lane < FG_STAT_COUNT && acc.mine) atomicAdd(&s_stats[lane], acc.mine);
+    if (lane == 0 && fsum) atomicAdd(&s_stats[FG_STAT_ENV_FRAMES], (unsigned long long)fsum);
     __syncthreads();
     if (threadIdx.x < FG_STAT_COUNT && s_stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
