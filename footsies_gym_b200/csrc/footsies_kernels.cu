@@ -51,7 +51,7 @@ struct __align__(16) Tables {
     double term_reward[FT_NUM_CUM][4][2];
     double step_reward[4];
     uint8_t cum_next[16][4];
-    uint16_t move_off[8], move_len[8], att_off[8], att_len[8];
+    uint32_t move_meta[8], att_meta[8];   // pattern offset | length << 16
     uint8_t move_pat[kMovePatBytes];
     uint8_t att_pat[kAttPatBytes];
 };
@@ -121,7 +121,7 @@ __device__ __forceinline__ void update_fighter(const Tables &T, uint32_t in, flo
     hist = (hl & 0xffffu) | (hr << 16);
     const uint32_t fm = SIDE == 0 ? hr : hl;
     const uint32_t bm = SIDE == 0 ? hl : hr;
-    const bool fwd = fm & 1u, back = bm & 1u;
+    const bool back = bm & 1u;
     // CheckForwardDashInput / CheckBackwardDashInput (Fighter.cs:585-635): first older frame (1..8) with a
     // direction held decides; then any neutral frame among the 8 frames before it.
     const uint32_t either = fm | bm;
@@ -131,18 +131,20 @@ __device__ __forceinline__ void update_fighter(const Tables &T, uint32_t in, flo
     const bool dash_f = (fm & 3u) == 1u && scan != 0u && !((bm >> i) & 1u) && gap;
     const bool dash_b = (bm & 3u) == 1u && scan != 0u && !((fm >> i) & 1u) && gap;
 
+    // All fields are updated in place in the packed word (no unpack / repack).
+    constexpr uint32_t M_STUN = 31u << FGP_STUN_SHIFT, M_GV = 7u << FGP_GUARD_SHIFT, M_HIT = 1u << FGP_HITCNT_SHIFT,
+                       M_BUF = 1u << FGP_BUF_SHIFT, M_RSV = 1u << FGP_RSV_SHIFT, M_INBACK = 1u << FGP_INBACK_SHIFT,
+                       M_RPROX = 1u << FGP_RPROX_SHIFT, M_SHAKE = 15u << FGP_SHAKE_SHIFT;
     // ---- IncrementActionFrame (Fighter.cs:140-166) ----
-    uint32_t act = pk & 31u;
-    uint32_t frame = (pk >> FGP_FRAME_SHIFT) & 511u;
-    uint32_t stun = (pk >> FGP_STUN_SHIFT) & 31u;
-    uint32_t hitcnt = (pk >> FGP_HITCNT_SHIFT) & 1u;
-    uint32_t buf = (pk >> FGP_BUF_SHIFT) & 1u;
-    uint32_t rsv = (pk >> FGP_RSV_SHIFT) & 1u;
-    uint32_t inback = (pk >> FGP_INBACK_SHIFT) & 1u;
-    uint32_t rprox = (pk >> FGP_RPROX_SHIFT) & 1u;
-    int shake = ((int)(pk << 1)) >> 28;                                 // bits 27..30, sign-extended
-    if (shake != 0) { shake = -shake; shake += shake > 0 ? -1 : 1; }
-    if (stun > 0u) stun--; else frame++;
+    if (pk & M_SHAKE) {                                                 // sprite shake decay (only after a hit)
+        int shake = ((int)(pk << 1)) >> 28;
+        shake = -shake; shake += shake > 0 ? -1 : 1;
+        pk = (pk & ~M_SHAKE) | ((uint32_t)shake & 15u) << FGP_SHAKE_SHIFT;
+    }
+    pk = (pk & M_STUN) ? pk - (1u << FGP_STUN_SHIFT) : pk + (1u << FGP_FRAME_SHIFT);   // stun-- else frame++
+    const bool stun0 = !(pk & M_STUN);
+    const uint32_t act = pk & 31u;
+    const uint32_t frame = (pk >> FGP_FRAME_SHIFT) & 511u;
 
     // ---- UpdateActionRequest (Fighter.cs:201-286) with the RequestAction chain (Fighter.cs:472-510) collapsed:
     //      when the action ended or is alwaysCancelable the FIRST request of the chain wins, otherwise the only
@@ -150,49 +152,39 @@ __device__ __forceinline__ void update_fighter(const Tables &T, uint32_t in, flo
     const uint32_t info0 = T.action_info[act];
     const bool ended = frame >= (info0 & 511u);
     bool want_buffer = false;
-    bool set = false;
-    uint32_t req = act;
-    if (rsv && stun == 0u) {                                            // reserved GUARD_BREAK (Fighter.cs:212-218)
+    bool set;
+    uint32_t req;
+    if ((pk & (M_RSV | M_STUN)) == M_RSV) {                             // reserved GUARD_BREAK (Fighter.cs:212-218)
         req = GUARD_BREAK; set = true;
-    } else if (buf && hitcnt && stun == 0u) {                           // buffered cancel (Fighter.cs:222-229)
+    } else if ((pk & (M_BUF | M_HIT | M_STUN)) == (M_BUF | M_HIT)) {    // buffered cancel (Fighter.cs:222-229)
         req = N_SPECIAL; set = true;
     } else {
-        const bool dir = fwd || back;
+        const uint32_t dir = (fm | bm) & 1u;
         const bool in_normal = (act == N_ATTACK || act == B_ATTACK) && !ended;
-        req = special ? (dir ? B_SPECIAL : N_SPECIAL)
-            : atk_down ? (in_normal ? N_SPECIAL : (dir ? B_ATTACK : N_ATTACK))
-            : dash_f ? DASH_FORWARD
-            : dash_b ? DASH_BACKWARD
-            : (fwd && back) ? STAND
-            : fwd ? FORWARD
-            : back ? (rprox ? GUARD_PROXIMITY : BACKWARD)
-            : STAND;
-        const bool free_to_switch = ended || ((info0 >> 9) & 1u);
+        // attack request: N_ATTACK 5 / B_ATTACK 6 / N_SPECIAL 7 / B_SPECIAL 8 (the B_ variant when a direction is held)
+        const uint32_t areq = special ? N_SPECIAL + dir : in_normal ? (uint32_t)N_SPECIAL : N_ATTACK + dir;
+        // movement request by (fwd, back, isReserveProximityGuard): STAND / FORWARD / BACKWARD / GUARD_PROXIMITY
+        const uint32_t mv = (0x0E100210u >> (4u * ((fm & 1u) | (bm & 1u) << 1 | ((pk >> FGP_RPROX_SHIFT) & 1u) << 2))) & 15u;
+        req = (special || atk_down) ? areq : dash_f ? (uint32_t)DASH_FORWARD : dash_b ? (uint32_t)DASH_BACKWARD : mv;
+        const bool free_to_switch = ended || (info0 & 512u);
         set = free_to_switch && (ended || req != act);
         want_buffer = !free_to_switch && req == N_SPECIAL;
-        inback = back;
-        rprox = 0u;
+        pk = (pk & ~(M_INBACK | M_RPROX)) | (back ? M_INBACK : 0u);     // isInputBackward = back; reserve flag consumed
     }
-    if (set) {                                                          // SetCurrentAction (Fighter.cs:546-563)
-        act = req; frame = 0u; hitcnt = 0u; buf = 0u; rsv = 0u; shake = 0;
-    }
+    if (set) pk = (pk & (M_STUN | M_GV | M_INBACK | M_RPROX)) | req;    // SetCurrentAction (Fighter.cs:546-563)
 
     // ---- frame data of the (action, frame) the fighter ends up in ----
-    const uint32_t info = T.action_info[act];
-    const uint32_t row_idx = ((info >> 14) & 1023u) + min(frame, (info >> 24) & 63u);
+    const uint32_t info = T.action_info[pk & 31u];
+    const uint32_t row_idx = ((info >> 14) & 1023u) + min((pk >> FGP_FRAME_SHIFT) & 511u, (info >> 24) & 63u);
     const uint4 row = T.rows[row_idx];
-    if (want_buffer && (row.z & 8u)) buf = 1u;                          // cancel window (Fighter.cs:492-505)
+    if (want_buffer && (row.z & 8u)) pk |= M_BUF;                       // cancel window (Fighter.cs:492-505)
 
     // ---- UpdateMovement (Fighter.cs:291-319) ----
-    if (stun == 0u) {
+    if (stun0) {
         const float dx = u2f(row.x);
         pos = pos + (SIDE == 0 ? dx : -dx);
         if (row.z & 1u) vel = u2f(row.y);
     }
-
-    pk = act | frame << FGP_FRAME_SHIFT | stun << FGP_STUN_SHIFT | (pk & (7u << FGP_GUARD_SHIFT))
-       | hitcnt << FGP_HITCNT_SHIFT | buf << FGP_BUF_SHIFT | rsv << FGP_RSV_SHIFT | inback << FGP_INBACK_SHIFT
-       | rprox << FGP_RPROX_SHIFT | ((uint32_t)shake & 15u) << FGP_SHAKE_SHIFT;
     fo.flags = row.z;
     fo.kind = (info >> 11) & 7u;
     fo.pos_b = pos;
@@ -229,7 +221,7 @@ __device__ __forceinline__ bool hit_overlaps(const Tables &T, uint4 hb, float ap
 template <int ASIDE>
 __device__ __forceinline__ uint32_t attack_pass(const Tables &T, uint32_t &apk, uint32_t &vpk, const FrameOut &af,
                                                 const FrameOut &vf, float a_s, float a_t, float v_s, float v_t) {
-    if (af.kind == 0u || !(af.flags & 6u) || ((apk >> FGP_HITCNT_SHIFT) & 1u)) return 0u;   // CanAttackHit
+    if (!(af.flags & 6u) || ((apk >> FGP_HITCNT_SHIFT) & 1u)) return 0u;   // no hitbox out, or CanAttackHit false
     bool hit = false, prox = false;
     if (af.flags & 4u)
         hit = hit_overlaps<ASIDE>(T, T.hit[(af.kind - 1u) * 2u + 1u], af.pos_b, a_s, a_t, vf.pos_b, v_s, v_t, vf.flags);
@@ -272,8 +264,9 @@ __device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &
     uint32_t mp = q & 7u, mc = (q >> 3) & 127u, ap = (q >> 10) & 7u, ac = (q >> 13) & 127u;
     uint32_t input = 0u;
     const int bucket = dist > 4.0f ? 0 : dist > 3.0f ? 1 : dist > 2.5f ? 2 : dist > 2.0f ? 3 : 4;
-    if (mc < T.move_len[mp]) {
-        const uint32_t v = T.move_pat[T.move_off[mp] + mc];           // 0 none, 1 forward, 2 backward
+    const uint32_t mmeta = T.move_meta[mp], ameta = T.att_meta[ap];
+    if (mc < (mmeta >> 16)) {
+        const uint32_t v = T.move_pat[(mmeta & 0xffffu) + mc];           // 0 none, 1 forward, 2 backward
         mc++;
         input |= SIDE == 1 ? v : ((v >> 1) | ((v & 1u) << 1));          // P2: forward = Left(1); P1: forward = Right(2)
     } else {                                                            // SelectMovement (BattleAI.cs:68-126)
@@ -285,8 +278,8 @@ __device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &
         mp = (sel >> (4 * r)) & 15u;
         mc = 0u;
     }
-    if (ac < T.att_len[ap]) {
-        input |= T.att_pat[T.att_off[ap] + ac];
+    if (ac < (ameta >> 16)) {
+        input |= T.att_pat[(ameta & 0xffffu) + ac];
         ac++;
     } else {                                                            // SelectAttack (BattleAI.cs:128-190)
         const bool opp_hurt = opp_act == DAMAGE || opp_act == GUARD_BREAK || opp_act == N_SPECIAL || opp_act == B_SPECIAL;
@@ -709,25 +702,30 @@ void build_tables(Tables &t) {
     auto rep = [&](std::vector<uint8_t> &v, int val, int n) { for (int i = 0; i < n; i++) v.push_back((uint8_t)val); };
     auto dash = [&](std::vector<uint8_t> &v) { v.push_back(F); v.push_back(N); v.push_back(F); };  // :330-342 (both dashes tap FORWARD)
     int id = 1;
+    uint16_t move_off[8] = {0}, move_len[8] = {0}, att_off[8] = {0}, att_len[8] = {0};
     auto begin = [&](std::vector<uint8_t> &v, uint16_t *off) { off[id] = (uint16_t)v.size(); };
     auto end = [&](std::vector<uint8_t> &v, uint16_t *off, uint16_t *len) { len[id] = (uint16_t)(v.size() - off[id]); id++; };
-    begin(mp, t.move_off); rep(mp, N, 30); end(mp, t.move_off, t.move_len);                                   // 1 AddNeutralMovement
-    begin(mp, t.move_off); rep(mp, F, 40); rep(mp, B, 10); rep(mp, F, 30); rep(mp, B, 10); end(mp, t.move_off, t.move_len); // 2 FarApproach1
-    begin(mp, t.move_off); dash(mp); rep(mp, B, 25); dash(mp); rep(mp, B, 25); end(mp, t.move_off, t.move_len);             // 3 FarApproach2
-    begin(mp, t.move_off); rep(mp, F, 30); rep(mp, B, 10); rep(mp, F, 20); rep(mp, B, 10); end(mp, t.move_off, t.move_len); // 4 MidApproach1
-    begin(mp, t.move_off); dash(mp); rep(mp, B, 30); end(mp, t.move_off, t.move_len);                         // 5 MidApproach2
-    begin(mp, t.move_off); rep(mp, B, 60); end(mp, t.move_off, t.move_len);                                   // 6 FallBack1
-    begin(mp, t.move_off); dash(mp); rep(mp, B, 60); end(mp, t.move_off, t.move_len);                         // 7 FallBack2
+    begin(mp, move_off); rep(mp, N, 30); end(mp, move_off, move_len);                                   // 1 AddNeutralMovement
+    begin(mp, move_off); rep(mp, F, 40); rep(mp, B, 10); rep(mp, F, 30); rep(mp, B, 10); end(mp, move_off, move_len); // 2 FarApproach1
+    begin(mp, move_off); dash(mp); rep(mp, B, 25); dash(mp); rep(mp, B, 25); end(mp, move_off, move_len);             // 3 FarApproach2
+    begin(mp, move_off); rep(mp, F, 30); rep(mp, B, 10); rep(mp, F, 20); rep(mp, B, 10); end(mp, move_off, move_len); // 4 MidApproach1
+    begin(mp, move_off); dash(mp); rep(mp, B, 30); end(mp, move_off, move_len);                         // 5 MidApproach2
+    begin(mp, move_off); rep(mp, B, 60); end(mp, move_off, move_len);                                   // 6 FallBack1
+    begin(mp, move_off); dash(mp); rep(mp, B, 60); end(mp, move_off, move_len);                         // 7 FallBack2
     memcpy(t.move_pat, mp.data(), mp.size());
     std::vector<uint8_t> apv;
     const int A = 4;
     id = 1;
-    begin(apv, t.att_off); rep(apv, 0, 30); end(apv, t.att_off, t.att_len);                                   // 1 AddNoAttack
-    begin(apv, t.att_off); rep(apv, A, 1); rep(apv, 0, 18); end(apv, t.att_off, t.att_len);                   // 2 OneHitImmediate
-    begin(apv, t.att_off); rep(apv, A, 1); rep(apv, 0, 3); rep(apv, A, 1); rep(apv, 0, 18); end(apv, t.att_off, t.att_len); // 3 TwoHitImmediate
-    begin(apv, t.att_off); rep(apv, A, 60); rep(apv, 0, 1); end(apv, t.att_off, t.att_len);                   // 4 ImmediateSpecial
-    begin(apv, t.att_off); rep(apv, A, 120); rep(apv, 0, 1); end(apv, t.att_off, t.att_len);                  // 5 DelaySpecial
+    begin(apv, att_off); rep(apv, 0, 30); end(apv, att_off, att_len);                                   // 1 AddNoAttack
+    begin(apv, att_off); rep(apv, A, 1); rep(apv, 0, 18); end(apv, att_off, att_len);                   // 2 OneHitImmediate
+    begin(apv, att_off); rep(apv, A, 1); rep(apv, 0, 3); rep(apv, A, 1); rep(apv, 0, 18); end(apv, att_off, att_len); // 3 TwoHitImmediate
+    begin(apv, att_off); rep(apv, A, 60); rep(apv, 0, 1); end(apv, att_off, att_len);                   // 4 ImmediateSpecial
+    begin(apv, att_off); rep(apv, A, 120); rep(apv, 0, 1); end(apv, att_off, att_len);                  // 5 DelaySpecial
     memcpy(t.att_pat, apv.data(), apv.size());
+    for (int i = 0; i < 8; i++) {
+        t.move_meta[i] = move_off[i] | (uint32_t)move_len[i] << 16;
+        t.att_meta[i] = att_off[i] | (uint32_t)att_len[i] << 16;
+    }
 }
 
 }  // namespace
