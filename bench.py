@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=DEFAULT_ENVS_PER_GPU)
+    ap.add_argument("--burnin", type=int, default=600,
+                    help="untimed steps before the warm-up so that episodes are desynchronised (steady state)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -191,6 +193,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.envs_per_gpu
@@ -205,6 +209,10 @@ def main():
         env.bind_actions(tapes[i % n_tapes])     # zero-copy: the kernel reads the resident tape directly
         env.step_bound()
 
+    # burn-in: all envs start synchronised on frame -1 (low divergence, optimistic); run until episodes have
+    # desynchronised so that the timed region measures the steady state of a long rollout
+    for i in range(args.burnin):
+        device_step(i)
     for i in range(max(args.warmup, 3)):
         device_step(i)
     torch.cuda.synchronize(dev)
@@ -341,7 +349,8 @@ def main():
                        "actions": "iid uniform over 8 bitmasks, torch.Generator(device).manual_seed(1234 + rank)",
                        "l2": f"inputs larger than L2: {2 * 64 * n / 1e6:.0f} MB of state traffic + "
                              f"{46 * n / 1e6:.0f} MB of outputs per step vs 126 MB L2; no flush",
-                       "frames_counted": "kernel simulated-frame counter (FG_STAT_ENV_FRAMES)"},
+                       "frames_counted": "kernel simulated-frame counter (FG_STAT_ENV_FRAMES)",
+                       "burnin_steps": args.burnin},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_env_frame": bytes_per_env, "peak_source": peak_src,

@@ -190,44 +190,51 @@ __device__ __forceinline__ void update_fighter(const Tables &T, uint32_t in, flo
     fo.pos_b = pos;
 }
 
-// Does the attacker's hitbox `hb` overlap any of the victim's (<= 2) hurtboxes?  BoxBase.Overlaps
-// (Fighter.cs:17-25, inclusive) with the y test pre-resolved into hb.z.  a_/v_ shift = push + wall
-// displacement applied to already-built boxes by ApplyPositionChange (Fighter.cs:331-350).
-template <int ASIDE>
-__device__ __forceinline__ bool hit_overlaps(const Tables &T, uint4 hb, float apos_b, float a_s, float a_t,
-                                             float vpos_b, float v_s, float v_t, uint32_t vflags) {
-    const float hcx = u2f(hb.x);
-    const float hx = ((apos_b + (ASIDE == 0 ? hcx : -hcx)) + a_s) + a_t;
-    const float hw = u2f(hb.y);
-    const float hmin = hx - hw, hmax = hx + hw;
-    bool r = false;
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const uint32_t id = (vflags >> (4 + 4 * j)) & 15u;
-        if ((hb.z >> id) & 1u) {
-            const uint2 hu = T.hurt[id];
-            const float vcx = u2f(hu.x);
-            const float vx = ((vpos_b + (ASIDE == 0 ? -vcx : vcx)) + v_s) + v_t;
-            const float vhw = u2f(hu.y);
-            r = r || ((vx + vhw >= hmin) && (vx - vhw <= hmax));
-        }
-    }
-    return r;
+// World x-extent of a box built at position pos_b (Fighter.cs:706-719: x = pos + data.x * sign; BoxBase xMin/xMax,
+// Fighter.cs:12-13) and then displaced by the push (s) and the wall clamp (t) like ApplyPositionChange does to
+// already-built boxes (Fighter.cs:331-350).  Every operation rounds separately.
+template <int SIDE>
+__device__ __forceinline__ void box_extent(float pos_b, uint32_t cx_bits, uint32_t hw_bits, float s, float t,
+                                           float &lo, float &hi) {
+    const float cx = u2f(cx_bits), hw = u2f(hw_bits);
+    const float x = ((pos_b + (SIDE == 0 ? cx : -cx)) + s) + t;
+    lo = x - hw;
+    hi = x + hw;
 }
 
-// One attacker -> victim pass of BattleCore.UpdateHitboxHurtboxCollision (BattleCore.cs:521-591) including
-// NotifyAttackHit / NotifyDamaged / GetHitStunFrame / SetHitStun / SetSpriteShakeFrame / NotifyInProximityGuardRange
-// (Fighter.cs:352-454).  Boxes are the pre-collision snapshot; hit counts and the victim's action are current.
+// Geometry half of BattleCore.UpdateHitboxHurtboxCollision (BattleCore.cs:535-565) for one attacker: does its real /
+// proximity hitbox overlap any of the victim's (<= 2) hurtboxes?  BoxBase.Overlaps (Fighter.cs:17-25, inclusive); the
+// y half of each test is pre-resolved into the hitbox's mask over hurtbox ids.  Straight-line code: the boxes are a
+// snapshot, so both attackers' tests can be evaluated before either attack is applied.
 template <int ASIDE>
-__device__ __forceinline__ uint32_t attack_pass(const Tables &T, uint32_t &apk, uint32_t &vpk, const FrameOut &af,
-                                                const FrameOut &vf, float a_s, float a_t, float v_s, float v_t) {
-    if (!(af.flags & 6u) || ((apk >> FGP_HITCNT_SHIFT) & 1u)) return 0u;   // no hitbox out, or CanAttackHit false
-    bool hit = false, prox = false;
-    if (af.flags & 4u)
-        hit = hit_overlaps<ASIDE>(T, T.hit[(af.kind - 1u) * 2u + 1u], af.pos_b, a_s, a_t, vf.pos_b, v_s, v_t, vf.flags);
-    if (!hit && (af.flags & 2u))
-        prox = hit_overlaps<ASIDE>(T, T.hit[(af.kind - 1u) * 2u], af.pos_b, a_s, a_t, vf.pos_b, v_s, v_t, vf.flags);
-    if (hit) {
+__device__ __forceinline__ void attack_overlaps(const Tables &T, const FrameOut &af, const FrameOut &vf, float a_s, float a_t,
+                                                float v_s, float v_t, bool &real_hit, bool &prox_hit) {
+    const uint32_t kidx = (max(af.kind, 1u) - 1u) * 2u;
+    const uint4 hp = T.hit[kidx], hr = T.hit[kidx + 1u];               // proximity box, real box of this attack
+    const uint32_t id0 = (vf.flags >> 4) & 15u, id1 = (vf.flags >> 8) & 15u;
+    const uint2 v0 = T.hurt[id0], v1 = T.hurt[id1];
+    float plo, phi, rlo, rhi, v0lo, v0hi, v1lo, v1hi;
+    box_extent<ASIDE>(af.pos_b, hp.x, hp.y, a_s, a_t, plo, phi);
+    box_extent<ASIDE>(af.pos_b, hr.x, hr.y, a_s, a_t, rlo, rhi);
+    box_extent<1 - ASIDE>(vf.pos_b, v0.x, v0.y, v_s, v_t, v0lo, v0hi);
+    box_extent<1 - ASIDE>(vf.pos_b, v1.x, v1.y, v_s, v_t, v1lo, v1hi);
+    // otherBox.xMax >= xMin && otherBox.xMin <= xMax with self = hitbox, other = hurtbox; id 0 (no box) never has its bit set
+    const bool r0 = ((hr.z >> id0) & 1u) && v0hi >= rlo && v0lo <= rhi;
+    const bool r1 = ((hr.z >> id1) & 1u) && v1hi >= rlo && v1lo <= rhi;
+    const bool p0 = ((hp.z >> id0) & 1u) && v0hi >= plo && v0lo <= phi;
+    const bool p1 = ((hp.z >> id1) & 1u) && v1hi >= plo && v1lo <= phi;
+    real_hit = (af.flags & 4u) && (r0 || r1);
+    prox_hit = (af.flags & 2u) && (p0 || p1);
+}
+
+// Effect half of one attacker -> victim pass (BattleCore.cs:567-586): NotifyAttackHit / NotifyDamaged /
+// GetHitStunFrame / SetHitStun / SetSpriteShakeFrame / NotifyInProximityGuardRange (Fighter.cs:352-454).
+// Hit counts and the victim's action are the CURRENT ones (P1's hit may just have changed P2), boxes are the snapshot.
+template <int ASIDE>
+__device__ __forceinline__ uint32_t attack_apply(const Tables &T, uint32_t &apk, uint32_t &vpk, const FrameOut &af,
+                                                 bool real_hit, bool prox_hit) {
+    const bool can = (af.flags & 6u) && !((apk >> FGP_HITCNT_SHIFT) & 1u);   // a hitbox is out and CanAttackHit
+    if (can && real_hit) {
         const uint32_t atk = T.attack[af.kind];
         uint32_t guard = (vpk >> FGP_GUARD_SHIFT) & 3u;
         const bool brk = guard == 0u;                                   // guardHealth < 0 after the decrement
@@ -253,7 +260,8 @@ __device__ __forceinline__ uint32_t attack_pass(const Tables &T, uint32_t &apk, 
         apk = (apk & ~(31u << FGP_STUN_SHIFT)) | stun << FGP_STUN_SHIFT | 1u << FGP_HITCNT_SHIFT;
         return res;
     }
-    if (prox && ((vpk >> FGP_INBACK_SHIFT) & 1u)) vpk |= 1u << FGP_RPROX_SHIFT;
+    // NotifyInProximityGuardRange: latch only while the victim holds back (Fighter.cs:400-406)
+    if (can && prox_hit) vpk |= ((vpk >> FGP_INBACK_SHIFT) & 1u) << FGP_RPROX_SHIFT;
     return 0u;
 }
 
@@ -447,8 +455,14 @@ __device__ __forceinline__ void simulate_frame(const Tables &T, Env &e, uint32_t
     e.pos2 = (e.pos2 + s2) + t2;
 
     // ---- UpdateHitboxHurtboxCollision (BattleCore.cs:521-591): P1 attacks first, then P2 with snapshot boxes ----
-    const uint32_t res_a = attack_pass<0>(T, e.pk1, e.pk2, f1, f2, s1, t1, s2, t2);   // result on P2
-    const uint32_t res_b = attack_pass<1>(T, e.pk2, e.pk1, f2, f1, s2, t2, s1, t1);   // result on P1
+    uint32_t res_a = 0u, res_b = 0u;
+    if ((f1.flags | f2.flags) & 6u) {                                   // somebody has a hitbox out
+        bool real_a, prox_a, real_b, prox_b;
+        attack_overlaps<0>(T, f1, f2, s1, t1, s2, t2, real_a, prox_a);
+        attack_overlaps<1>(T, f2, f1, s2, t2, s1, t1, real_b, prox_b);
+        res_a = attack_apply<0>(T, e.pk1, e.pk2, f1, real_a, prox_a);  // result on P2
+        res_b = attack_apply<1>(T, e.pk2, e.pk1, f2, real_b, prox_b);  // result on P1
+    }
 
     acc.r += (1u << (8u * res_a)) + (1u << (8u * res_b));                // byte lane = DamageResult of each pass
     const uint32_t a1 = e.pk1 & 31u;
