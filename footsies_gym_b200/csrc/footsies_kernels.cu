@@ -52,6 +52,7 @@ struct __align__(16) Tables {
     double step_reward[4];
     uint8_t cum_next[16][4];
     uint32_t move_meta[8], att_meta[8];   // pattern offset | length << 16
+    unsigned long long mod_magic[8];      // floor(2^64 / n) + 1
     uint8_t move_pat[kMovePatBytes];
     uint8_t att_pat[kAttPatBytes];
 };
@@ -267,41 +268,52 @@ __device__ __forceinline__ uint32_t attack_apply(const Tables &T, uint32_t &apk,
 
 // BattleAI.getNextAIInput (BattleAI.cs:41-66) on pattern-id + cursor queues.  `dist` and `opp_act` are the state
 // captured by the PREVIOUS call (the ascending shift loop at BattleAI.cs:358-361 makes fightStates[5] exactly that).
+// r % n for 2 <= n <= 7 without a division: floor(r / n) == umul64hi(r, floor(2^64 / n) + 1) for every 32-bit r.
+__device__ __forceinline__ uint32_t mod_small(const Tables &T, uint32_t r, uint32_t n) {
+    const uint32_t q = (uint32_t)__umul64hi((unsigned long long)r, T.mod_magic[n]);
+    return r - q * n;
+}
+
 template <int SIDE>
 __device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &q, float dist, uint32_t opp_act) {
     uint32_t mp = q & 7u, mc = (q >> 3) & 127u, ap = (q >> 10) & 7u, ac = (q >> 13) & 127u;
     uint32_t input = 0u;
-    const int bucket = dist > 4.0f ? 0 : dist > 3.0f ? 1 : dist > 2.5f ? 2 : dist > 2.0f ? 3 : 4;
     const uint32_t mmeta = T.move_meta[mp], ameta = T.att_meta[ap];
-    if (mc < (mmeta >> 16)) {
-        const uint32_t v = T.move_pat[(mmeta & 0xffffu) + mc];           // 0 none, 1 forward, 2 backward
+    const bool have_m = mc < (mmeta >> 16), have_a = ac < (ameta >> 16);
+    if (have_m) {
+        const uint32_t v = T.move_pat[(mmeta & 0xffffu) + mc];         // 0 none, 1 forward, 2 backward
         mc++;
-        input |= SIDE == 1 ? v : ((v >> 1) | ((v & 1u) << 1));          // P2: forward = Left(1); P1: forward = Right(2)
-    } else {                                                            // SelectMovement (BattleAI.cs:68-126)
-        const uint32_t n = (0x34572u >> (4 * bucket)) & 15u;            // ranges 2,7,5,4,3
-        const uint32_t r = rng_next(e) % n;
-        // nibble r of the bucket's word = move pattern id
-        const uint32_t sel = bucket == 0 ? 0x32u : bucket == 1 ? 0x1325544u : bucket == 2 ? 0x17654u
-                           : bucket == 3 ? 0x1176u : 0x176u;
-        mp = (sel >> (4 * r)) & 15u;
-        mc = 0u;
+        input = SIDE == 1 ? v : ((v >> 1) | ((v & 1u) << 1));           // P2: forward = Left(1); P1: forward = Right(2)
     }
-    if (ac < (ameta >> 16)) {
+    if (have_a) {
         input |= T.att_pat[(ameta & 0xffffu) + ac];
         ac++;
-    } else {                                                            // SelectAttack (BattleAI.cs:128-190)
-        const bool opp_hurt = opp_act == DAMAGE || opp_act == GUARD_BREAK || opp_act == N_SPECIAL || opp_act == B_SPECIAL;
-        const bool opp_normal = opp_act == N_ATTACK || opp_act == B_ATTACK;
-        if (opp_hurt || (bucket == 1 && opp_normal)) {
-            ap = 3u;                                                    // AddTwoHitImmediateAttack, no draw
-        } else {
-            const uint32_t n = (0x36354u >> (4 * bucket)) & 15u;        // ranges 4,5,3,6,3
-            const uint32_t r = rng_next(e) % n;
-            const uint32_t sel = bucket == 0 ? 0x1111u : bucket == 1 ? 0x52211u : bucket == 2 ? 0x321u
-                               : bucket == 3 ? 0x543322u : 0x332u;
-            ap = (sel >> (4 * r)) & 15u;
+    }
+    if (!(have_m && have_a)) {                                          // an empty queue is refilled and contributes 0 (BattleAI.cs:50-62)
+        const int bucket = dist > 4.0f ? 0 : dist > 3.0f ? 1 : dist > 2.5f ? 2 : dist > 2.0f ? 3 : 4;
+        if (!have_m) {                                                  // SelectMovement (BattleAI.cs:68-126)
+            const uint32_t n = (0x34572u >> (4 * bucket)) & 15u;        // Random.Range(0, n): n = 2,7,5,4,3
+            const uint32_t r = mod_small(T, rng_next(e), n);
+            // nibble r of the bucket's word = move pattern id
+            const uint32_t sel = bucket == 0 ? 0x32u : bucket == 1 ? 0x1325544u : bucket == 2 ? 0x17654u
+                               : bucket == 3 ? 0x1176u : 0x176u;
+            mp = (sel >> (4 * r)) & 15u;
+            mc = 0u;
         }
-        ac = 0u;
+        if (!have_a) {                                                  // SelectAttack (BattleAI.cs:128-190)
+            const bool opp_hurt = opp_act == DAMAGE || opp_act == GUARD_BREAK || opp_act == N_SPECIAL || opp_act == B_SPECIAL;
+            const bool opp_normal = opp_act == N_ATTACK || opp_act == B_ATTACK;
+            if (opp_hurt || (bucket == 1 && opp_normal)) {
+                ap = 3u;                                                // AddTwoHitImmediateAttack, no draw
+            } else {
+                const uint32_t n = (0x36354u >> (4 * bucket)) & 15u;    // n = 4,5,3,6,3
+                const uint32_t r = mod_small(T, rng_next(e), n);
+                const uint32_t sel = bucket == 0 ? 0x1111u : bucket == 1 ? 0x52211u : bucket == 2 ? 0x321u
+                                   : bucket == 3 ? 0x543322u : 0x332u;
+                ap = (sel >> (4 * r)) & 15u;
+            }
+            ac = 0u;
+        }
     }
     q = mp | mc << 3 | ap << 10 | ac << 13;
     return input;
@@ -736,6 +748,7 @@ void build_tables(Tables &t) {
     begin(apv, att_off); rep(apv, A, 60); rep(apv, 0, 1); end(apv, att_off, att_len);                   // 4 ImmediateSpecial
     begin(apv, att_off); rep(apv, A, 120); rep(apv, 0, 1); end(apv, att_off, att_len);                  // 5 DelaySpecial
     memcpy(t.att_pat, apv.data(), apv.size());
+    for (int i = 1; i < 8; i++) t.mod_magic[i] = i == 1 ? 0ull : (~0ull) / (unsigned long long)i + 1ull;
     for (int i = 0; i < 8; i++) {
         t.move_meta[i] = move_off[i] | (uint32_t)move_len[i] << 16;
         t.att_meta[i] = att_off[i] | (uint32_t)att_len[i] << 16;
