@@ -6,7 +6,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_NAME = "libfootsies_b200.so"
-LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
+LIB_PATH = os.environ.get("FOOTSIES_B200_LIB") or os.path.join(PKG_DIR, LIB_NAME)   # override: developer experiments only
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -25,7 +25,16 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+#ifndef FG_THREADS
+#define FG_THREADS 256
+#endif
+#ifndef FG_STAGES
+#define FG_STAGES 2
+#endif
+#ifndef FG_BLOCKS_PER_SM
+#define FG_BLOCKS_PER_SM 4
+#endif
+constexpr int kThreads = FG_THREADS;
 constexpr uint32_t kFull = 0xffffffffu;
 
 // action indices (moves.py order)
@@ -165,7 +174,8 @@ __device__ __forceinline__ void update_fighter(const Tables &T, uint32_t in, flo
         // attack request: N_ATTACK 5 / B_ATTACK 6 / N_SPECIAL 7 / B_SPECIAL 8 (the B_ variant when a direction is held)
         const uint32_t areq = special ? N_SPECIAL + dir : in_normal ? (uint32_t)N_SPECIAL : N_ATTACK + dir;
         // movement request by (fwd, back, isReserveProximityGuard): STAND / FORWARD / BACKWARD / GUARD_PROXIMITY
-        const uint32_t mv = (0x0E100210u >> (4u * ((fm & 1u) | (bm & 1u) << 1 | ((pk >> FGP_RPROX_SHIFT) & 1u) << 2))) & 15u;
+        // nibble LUT indexed by the raw Left/Right bits (+4 when the proximity-guard flag is set)
+        const uint32_t mv = ((SIDE == 0 ? 0x01E00120u : 0x0E100210u) >> (4u * ((in & 3u) | ((pk >> (FGP_RPROX_SHIFT - 2)) & 4u)))) & 15u;
         req = (special || atk_down) ? areq : dash_f ? (uint32_t)DASH_FORWARD : dash_b ? (uint32_t)DASH_BACKWARD : mv;
         const bool free_to_switch = ended || (info0 & 512u);
         set = free_to_switch && (ended || req != act);
@@ -276,18 +286,18 @@ __device__ __forceinline__ uint32_t mod_small(const Tables &T, uint32_t r, uint3
 
 template <int SIDE>
 __device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &q, float dist, uint32_t opp_act) {
-    uint32_t mp = q & 7u, mc = (q >> 3) & 127u, ap = (q >> 10) & 7u, ac = (q >> 13) & 127u;
+    // queue word: move position in move_pat [0:9) | moves remaining [9:16) | attack position in att_pat [16:24) |
+    // attacks remaining [24:31): dequeuing is one add on the packed word
     uint32_t input = 0u;
-    const uint32_t mmeta = T.move_meta[mp], ameta = T.att_meta[ap];
-    const bool have_m = mc < (mmeta >> 16), have_a = ac < (ameta >> 16);
+    const bool have_m = (q & (127u << 9)) != 0u, have_a = (q & (127u << 24)) != 0u;
     if (have_m) {
-        const uint32_t v = T.move_pat[(mmeta & 0xffffu) + mc];         // 0 none, 1 forward, 2 backward
-        mc++;
+        const uint32_t v = T.move_pat[q & 511u];                        // 0 none, 1 forward, 2 backward
+        q += 1u - (1u << 9);
         input = SIDE == 1 ? v : ((v >> 1) | ((v & 1u) << 1));           // P2: forward = Left(1); P1: forward = Right(2)
     }
     if (have_a) {
-        input |= T.att_pat[(ameta & 0xffffu) + ac];
-        ac++;
+        input |= T.att_pat[(q >> 16) & 255u];
+        q += (1u << 16) - (1u << 24);
     }
     if (!(have_m && have_a)) {                                          // an empty queue is refilled and contributes 0 (BattleAI.cs:50-62)
         const int bucket = dist > 4.0f ? 0 : dist > 3.0f ? 1 : dist > 2.5f ? 2 : dist > 2.0f ? 3 : 4;
@@ -297,12 +307,13 @@ __device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &
             // nibble r of the bucket's word = move pattern id
             const uint32_t sel = bucket == 0 ? 0x32u : bucket == 1 ? 0x1325544u : bucket == 2 ? 0x17654u
                                : bucket == 3 ? 0x1176u : 0x176u;
-            mp = (sel >> (4 * r)) & 15u;
-            mc = 0u;
+            const uint32_t meta = T.move_meta[(sel >> (4 * r)) & 15u];  // offset | length << 16
+            q = (q & 0xffff0000u) | (meta & 0xffffu) | (meta >> 16) << 9;
         }
         if (!have_a) {                                                  // SelectAttack (BattleAI.cs:128-190)
             const bool opp_hurt = opp_act == DAMAGE || opp_act == GUARD_BREAK || opp_act == N_SPECIAL || opp_act == B_SPECIAL;
             const bool opp_normal = opp_act == N_ATTACK || opp_act == B_ATTACK;
+            uint32_t ap;
             if (opp_hurt || (bucket == 1 && opp_normal)) {
                 ap = 3u;                                                // AddTwoHitImmediateAttack, no draw
             } else {
@@ -312,10 +323,10 @@ __device__ __forceinline__ uint32_t bot_next(const Tables &T, Env &e, uint32_t &
                                    : bucket == 3 ? 0x543322u : 0x332u;
                 ap = (sel >> (4 * r)) & 15u;
             }
-            ac = 0u;
+            const uint32_t meta = T.att_meta[ap];
+            q = (q & 0x0000ffffu) | (meta & 0xffffu) << 16 | (meta >> 16) << 24;
         }
     }
-    q = mp | mc << 3 | ap << 10 | ac << 13;
     return input;
 }
 
@@ -478,7 +489,7 @@ __device__ __forceinline__ void simulate_frame(const Tables &T, Env &e, uint32_t
 
     acc.r += (1u << (8u * res_a)) + (1u << (8u * res_b));                // byte lane = DamageResult of each pass
     const uint32_t a1 = e.pk1 & 31u;
-    if (a1 != pre_a1 && (a1 == N_SPECIAL || a1 == B_SPECIAL))           // wrappers/statistics.py:36-46
+    if (a1 != pre_a1 && (a1 - N_SPECIAL) < 2u)                          // became N_SPECIAL / B_SPECIAL (wrappers/statistics.py:36-46)
         acc.s += (pre_a1 != N_ATTACK && pre_a1 != B_ATTACK) ? 0x101u : 1u;
 
     // ---- KO (BattleCore.cs:212-217), termination (footsies.py:555) ----
@@ -545,7 +556,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int kStages = 2;
+constexpr int kStages = FG_STAGES;
 template <int PLANES> struct __align__(128) StageBuf { uint4 pl[PLANES][kThreads]; };
 
 // FootsiesEnv.step for every env: up to K fused fight frames, or the reset of a finished env (autoreset).
@@ -576,8 +587,12 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
         for (int k = 0; k < kPlanes; k++)
             tma_load_1d(stage[s].pl[k], planes[k] + (size_t)chunk * kThreads, (uint32_t)(kThreads * sizeof(uint4)), &full_bar[s]);
     };
-    if (threadIdx.x == 0 && (int)blockIdx.x < full_chunks) issue(blockIdx.x, 0);
-
+    // prologue: chunks 0 .. kStages-2 of this CTA are in flight before the loop starts
+    if (threadIdx.x == 0)
+        for (int j = 0; j < kStages - 1; j++) {
+            const int cj = blockIdx.x + j * gridDim.x;
+            if (cj < full_chunks) issue(cj, j);
+        }
     StatAcc acc = { 0u, 0u, 0u };
     uint32_t frames_done = 0u, frames_since_flush = 0u;
     // actions are prefetched one chunk ahead into registers
@@ -588,15 +603,16 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
     }
     int k = 0;
     for (int c = blockIdx.x; c < num_chunks; c += gridDim.x, k++) {
-        const int s = k & 1;
+        const int s = k % kStages;
         const int i = c * kThreads + threadIdx.x;
         const bool valid = i < p.n;
         const bool staged = c < full_chunks;
-        if (threadIdx.x == 0) {                                         // producer: next chunk -> the other stage
-            const int cn = c + gridDim.x;
+        if (threadIdx.x == 0) {                                         // producer: chunk k + kStages - 1 -> the stage read at k - 1
+            const int cn = c + (kStages - 1) * gridDim.x;
             if (cn < full_chunks) {
-                if (k >= 1) mbar_wait(&empty_bar[s ^ 1], ((k - 1) >> 1) & 1);   // every warp has read chunk k-1
-                issue(cn, s ^ 1);
+                const int sn = (k + kStages - 1) % kStages;
+                if (k >= 1) mbar_wait(&empty_bar[sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
+                issue(cn, sn);
             }
         }
         const uint32_t act1 = nin1, act2 = nin2;
@@ -608,7 +624,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
         bool run = false;
         uint32_t in1 = 0u, in2 = 0u;
         if (staged) {
-            mbar_wait(&full_bar[s], (k >> 1) & 1);
+            mbar_wait(&full_bar[s], (k / kStages) & 1);
             const uint4 a = stage[s].pl[0][threadIdx.x], b = stage[s].pl[1][threadIdx.x], cc = stage[s].pl[2][threadIdx.x];
             e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
             e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
@@ -912,7 +928,7 @@ int32_t fg_step(fg_handle *h, void *stream) {
     if (int rc = check_bound(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const Params p = make_params(h);
-    const int grid = grid_for(h, 4);
+    const int grid = grid_for(h, FG_BLOCKS_PER_SM);
     if (h->cfg.frame_skip == 1) launch_step_k<false>(h->cfg, grid, (cudaStream_t)stream, p);
     else launch_step_k<true>(h->cfg, grid, (cudaStream_t)stream, p);
     h->launches++;

@@ -108,7 +108,7 @@ typedef struct {
     int32_t cum_reward_index;   /* index into the dense-reward automaton                                  */
     int32_t actor_input[2];     /* input each actor holds for the next frame (bots: already decided)      */
     uint32_t rng_state[4];      /* per-env xorshift128 standing in for UnityEngine.Random                 */
-    uint32_t bot_queue[2];      /* per bot: move pattern[0:3) cursor[3:10) attack pattern[10:13) cursor[13:20) */
+    uint32_t bot_queue[2];      /* per bot: move position[0:9) remaining[9:16) attack position[16:24) remaining[24:31) */
 } fg_env_state;
 
 typedef struct fg_handle fg_handle;
