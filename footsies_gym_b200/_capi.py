@@ -26,7 +26,7 @@ class FgBuffers(C.Structure):
                 ("state", C.c_void_p * FG_STATE_PLANES), ("stats", C.c_void_p),
                 ("actions_p1", C.c_void_p), ("actions_p2", C.c_void_p), ("obs", C.c_void_p),
                 ("reward", C.c_void_p), ("terminated", C.c_void_p), ("info_frame", C.c_void_p),
-                ("info_misc", C.c_void_p)]
+                ("info_misc", C.c_void_p), ("step_mask", C.c_void_p)]
 
 
 class FgFighterState(C.Structure):

@@ -78,6 +78,7 @@ struct Params {
     uchar4 *info_misc;
     const Tables *tables;
     const uint8_t *mask;   // reset / seed kernels
+    const uint8_t *step_mask;
     long long seed_base, first_env_index;
     int n, frame_skip, autoreset, stale_intro;
 };
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
     for (int c = blockIdx.x; c < num_chunks; c += gridDim.x, k++) {
         const int s = k % kStages;
         const int i = c * kThreads + threadIdx.x;
-        const bool valid = i < p.n;
+        const bool valid = i < p.n && (p.step_mask == nullptr || p.step_mask[i < p.n ? i : 0] != 0);
         const bool staged = c < full_chunks;
         if (threadIdx.x == 0) {                                         // producer: chunk k + kStages - 1 -> the stage read at k - 1
             const int cn = c + (kStages - 1) * gridDim.x;
@@ -800,6 +801,7 @@ Params make_params(const fg_handle *h) {
     p.act1 = h->buf.actions_p1; p.act2 = h->buf.actions_p2;
     p.obs = (float4 *)h->buf.obs; p.reward = h->buf.reward; p.terminated = h->buf.terminated;
     p.info_frame = h->buf.info_frame; p.info_misc = (uchar4 *)h->buf.info_misc;
+    p.step_mask = h->buf.step_mask;
     p.tables = h->d_tables;
     p.first_env_index = h->cfg.first_env_index;
     p.n = h->cfg.num_envs; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;

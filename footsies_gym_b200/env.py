@@ -140,6 +140,7 @@ class FootsiesEnv:
 
         self._lib = _capi.load()
         self._handle = None
+        self._step_mask = None
         self._allocate()
         self._create_handle()
         self._seed_value = seed
@@ -221,6 +222,7 @@ class FootsiesEnv:
         b.terminated = self.terminated.data_ptr()
         b.info_frame = self.info_frame.data_ptr()
         b.info_misc = self.info_misc.data_ptr()
+        b.step_mask = None if self._step_mask is None else self._step_mask.data_ptr()
         _capi.check(self._lib.fg_bind(self._handle, C.byref(b)))
 
     def _stream(self):
@@ -297,6 +299,18 @@ class FootsiesEnv:
             self._advance_delay_ring()
         obs, info = self._finish_obs()
         return obs, self.reward, self.terminated, self.truncated, info
+
+    def set_step_mask(self, mask: Optional[torch.Tensor]):
+        """Only envs with mask[i] != 0 are advanced by the following step() calls (None = all); the others keep
+        their state and their last outputs."""
+        if mask is None:
+            self._step_mask = None
+        else:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if m.shape != (self.num_envs,):
+                raise ValueError("step mask must have shape (num_envs,)")
+            self._step_mask = m
+        self._bind()
 
     def _advance_delay_ring(self):
         # footsies.py:533-535: append the newest state, pop the oldest (queue length frame_delay + 1);

@@ -46,7 +46,7 @@ class FootsiesNormalized(_Wrapper):
     Must wrap the base environment, before any other observation wrapper (normalization.py:15-19)."""
 
     def __init__(self, env, normalize_guard: bool = True):
-        if not isinstance(env, FootsiesEnv):
+        if not (isinstance(env, FootsiesEnv) or getattr(env, "is_base_footsies_env", False)):
             raise ValueError("FootsiesNormalized wrapper should be applied to the base FOOTSIES environment")
         super().__init__(env)
         self.normalize_guard = normalize_guard

@@ -75,6 +75,9 @@ typedef struct {
     uint8_t *terminated;            /* [num_envs] p1Vital == 0 or p2Vital == 0 (footsies.py:555)           */
     int32_t *info_frame;            /* [num_envs] info["frame"] (footsies.py:370-380)                      */
     uint8_t *info_misc;             /* [num_envs][4]: p1_action mask, p2_action mask, p1_hitstun, p2_hitstun */
+    const uint8_t *step_mask;       /* optional [num_envs]: fg_step only advances envs with a non-zero entry (NULL =
+                                       all); the others keep their state and outputs (used by the batched
+                                       FootsiesFrameSkipped wrapper, wrappers/frame_skip.py:46-80)          */
 } fg_buffers;
 
 /* Expanded, readable per-env state (superset of EnvironmentState.cs:12-26; the fields of

@@ -43,12 +43,38 @@ def install_gymnasium_stub():
         def reset(self, *, seed=None, options=None):
             return None
 
-    class Wrapper:
+    class Wrapper:                      # gymnasium.Wrapper semantics: forward everything to the wrapped env
         def __init__(self, env):
             self.env = env
+            self.observation_space = getattr(env, "observation_space", None)
+            self.action_space = getattr(env, "action_space", None)
+
+        def __getattr__(self, name):
+            if name.startswith("_"):
+                raise AttributeError(name)
+            return getattr(self.env, name)
+
+        def reset(self, *, seed=None, options=None):
+            return self.env.reset(seed=seed, options=options)
+
+        def step(self, action):
+            return self.env.step(action)
+
+    class ObservationWrapper(Wrapper):  # gymnasium.ObservationWrapper: observation() applied to reset and step
+        def reset(self, *, seed=None, options=None):
+            obs, info = self.env.reset(seed=seed, options=options)
+            return self.observation(obs), info
+
+        def step(self, action):
+            obs, reward, terminated, truncated, info = self.env.step(action)
+            return self.observation(obs), reward, terminated, truncated, info
+
+    class ActionWrapper(Wrapper):       # gymnasium.ActionWrapper: action() applied before step
+        def step(self, action):
+            return self.env.step(self.action(action))
 
     gym.Env = Env
-    gym.Wrapper = gym.ObservationWrapper = gym.ActionWrapper = Wrapper
+    gym.Wrapper, gym.ObservationWrapper, gym.ActionWrapper = Wrapper, ObservationWrapper, ActionWrapper
     spaces = types.ModuleType("gymnasium.spaces")
     spaces.Dict, spaces.MultiDiscrete, spaces.Box = sp.Dict, sp.MultiDiscrete, sp.Box
     spaces.MultiBinary, spaces.Discrete = sp.MultiBinary, sp.Discrete
@@ -282,6 +308,68 @@ def run_scenario(name, *, dense, frame_delay, p2_remote, n_calls, rng_seed, seed
     print(f"{name}: {len(ops)} game ops, {len(call_ops)} API calls, {n_ep} terminations -> {os.path.relpath(path, ROOT)}")
 
 
+def run_wrapper_scenario(name, chain, n_calls, rng_seed):
+    """Reference wrappers (footsies_gym/wrappers/*.py, unmodified) stacked on the reference FootsiesEnv; the
+    recorded API-level calls are replayed through the batched wrappers of footsies_gym_b200.wrappers."""
+    from footsies_gym.envs.footsies import FootsiesEnv
+    from footsies_gym.wrappers import (FootsiesActionCombinationsDiscretized, FootsiesFrameSkipped,
+                                       FootsiesNormalized, FootsiesStatistics)
+    ports = free_ports(3)
+    server = OracleGameServer(ports, p2_remote=False)
+    server.start()
+    env = FootsiesEnv(game_address="127.0.0.1", game_port=ports[0], remote_control_port=ports[1],
+                      opponent_port=ports[2], skip_instancing=True, sync_mode="synced_non_blocking")
+    stats = None
+    for w in chain:
+        if w == "normalized":
+            env = FootsiesNormalized(env)
+        elif w == "frame_skipped":
+            env = FootsiesFrameSkipped(env)
+        elif w == "discretized":
+            env = FootsiesActionCombinationsDiscretized(env)
+        elif w == "statistics":
+            env = stats = FootsiesStatistics(env)
+    rng = np.random.default_rng(rng_seed)
+    calls, obs_l, rew_l, term_l, frame_l = [], [], [], [], []
+
+    def rec(kind, a, obs, reward, terminated, info):
+        calls.append((kind, a))
+        mf = obs["move_frame"]
+        mf = list(mf) if isinstance(mf, (tuple, list)) else [float(mf), float("nan")]
+        obs_l.append([obs["guard"][0], obs["guard"][1], obs["move"][0], obs["move"][1], mf[0], mf[1],
+                      obs["position"][0], obs["position"][1]])
+        rew_l.append(float(reward))
+        term_l.append(int(terminated))
+        frame_l.append(int(info["frame"]))
+
+    obs, info = env.reset(seed=None, options=None)
+    rec(1, 0, obs, 0.0, False, info)
+    sticky = 0
+    for _ in range(n_calls):
+        if rng.random() < 0.2:
+            sticky = int(rng.integers(0, 8))
+        a = sticky if rng.random() < 0.7 else int(rng.integers(0, 8))
+        act = a if "discretized" in chain else (a & 1 != 0, a & 2 != 0, a & 4 != 0)
+        obs, reward, terminated, truncated, info = env.step(act)
+        rec(0, a, obs, reward, terminated, info)
+        if terminated:
+            obs, info = env.reset(seed=None, options=None)
+            rec(1, 0, obs, 0.0, False, info)
+    server.stop_flag = True
+    env.close()
+    server.join(timeout=5)
+    extra = {}
+    if stats is not None:
+        extra["special_moves_per_episode"] = np.array(stats.metric_special_moves_per_episode, np.int32)
+        extra["special_moves_from_neutral_per_episode"] = np.array(stats.metric_special_moves_from_neutral_per_episode, np.int32)
+    path = os.path.join(HERE, f"ref_wrappers_{name}.npz")
+    np.savez_compressed(path, calls=np.array(calls, np.int32), exp_obs=np.array(obs_l, np.float64),
+                        exp_reward=np.array(rew_l, np.float64), exp_terminated=np.array(term_l, np.int8),
+                        exp_frame=np.array(frame_l, np.int32), chain=np.array(chain), **extra)
+    print(f"{name}: {len(calls)} API calls, {len(server.ops)} game frames/resets, {int(np.sum(term_l))} terminations "
+          f"-> {os.path.relpath(path, ROOT)}")
+
+
 def main():
     install_gymnasium_stub()
     sys.path.insert(0, REF_PY)
@@ -289,6 +377,9 @@ def main():
     run_scenario("sparse_bot", dense=False, frame_delay=0, p2_remote=False, n_calls=3000, rng_seed=2)
     run_scenario("dense_delay3_bot", dense=True, frame_delay=3, p2_remote=False, n_calls=3000, rng_seed=3)
     run_scenario("dense_remote_p2", dense=True, frame_delay=0, p2_remote=True, n_calls=4000, rng_seed=4)
+    run_wrapper_scenario("normalized_frameskipped", ["normalized", "frame_skipped"], n_calls=2500, rng_seed=5)
+    run_wrapper_scenario("discretized_statistics", ["discretized", "statistics"], n_calls=4000, rng_seed=6)
+    run_wrapper_scenario("normalized", ["normalized"], n_calls=1500, rng_seed=7)
 
 
 if __name__ == "__main__":

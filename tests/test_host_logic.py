@@ -28,7 +28,7 @@ def test_header_symbols_are_all_exported():
 def test_struct_layouts_match_header_sizes():
     from footsies_gym_b200 import _capi
     assert C.sizeof(_capi.FgConfig) == 48
-    assert C.sizeof(_capi.FgBuffers) == 8 + 8 * (4 + 1 + 2 + 5)
+    assert C.sizeof(_capi.FgBuffers) == 8 + 8 * (4 + 1 + 2 + 5 + 1)
     assert C.sizeof(_capi.FgFighterState) == 72
     assert C.sizeof(_capi.FgEnvState) == 2 * 72 + 4 * 13
     assert _capi.env_state_dtype().itemsize == C.sizeof(_capi.FgEnvState)

@@ -1,0 +1,133 @@
+"""The batched wrappers against golden vectors recorded from the reference's own wrapper classes
+(footsies_gym/wrappers/*.py, run unmodified by tests/golden/make_golden.py).
+
+Integer-valued fields and termination must match exactly; normalised floats and accumulated rewards are float64
+in the reference and float32 here: tolerance 1e-6 absolute (stated)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "ref_wrappers_*.npz")))
+TOL = 1e-6
+
+
+def build_chain(base, chain):
+    from footsies_gym_b200.wrappers import (FootsiesActionCombinationsDiscretized, FootsiesFrameSkipped,
+                                            FootsiesNormalized, FootsiesStatistics)
+    env, stats = base, None
+    for w in chain:
+        if w == "normalized":
+            env = FootsiesNormalized(env)
+        elif w == "frame_skipped":
+            env = FootsiesFrameSkipped(env)
+        elif w == "discretized":
+            env = FootsiesActionCombinationsDiscretized(env)
+        elif w == "statistics":
+            env = stats = FootsiesStatistics(env)
+    return env, stats
+
+
+def replay(path, base):
+    g = np.load(path)
+    chain = [str(c) for c in g["chain"]]
+    env, stats = build_chain(base, chain)
+    n_checked = 0
+    for j, (kind, a) in enumerate(g["calls"].tolist()):
+        where = f"{os.path.basename(path)} call {j}"
+        if kind == 1:
+            obs, info = env.reset(seed=None, options=None)
+            reward, terminated = 0.0, 0
+        else:
+            act = torch.tensor([a], dtype=torch.uint8) if "discretized" not in chain else torch.tensor([a])
+            obs, reward, terminated, truncated, info = env.step(act)
+            reward, terminated = float(reward[0]), int(terminated[0])
+        exp = g["exp_obs"][j]
+        got = [float(obs["guard"][0, 0]), float(obs["guard"][0, 1]), float(obs["move"][0, 0]), float(obs["move"][0, 1])]
+        mf = obs["move_frame"]
+        got += [float(mf[0, 0]), float(mf[0, 1]) if mf.shape[1] > 1 else float("nan")]
+        got += [float(obs["position"][0, 0]), float(obs["position"][0, 1])]
+        assert got[2:4] == exp[2:4].tolist(), where                      # move indices: exact
+        assert np.allclose(np.array(got), exp, atol=TOL, rtol=0, equal_nan=True), (where, got, exp.tolist())
+        assert abs(reward - float(g["exp_reward"][j])) <= TOL, (where, reward, g["exp_reward"][j])
+        assert terminated == int(g["exp_terminated"][j]), where
+        assert int(info["frame"][0]) == int(g["exp_frame"][j]), where
+        n_checked += 1
+    if stats is not None:
+        assert stats.metric_special_moves_per_episode == g["special_moves_per_episode"].tolist()
+        assert stats.metric_special_moves_from_neutral_per_episode == g["special_moves_from_neutral_per_episode"].tolist()
+    return n_checked
+
+
+def test_wrapper_goldens_exist():
+    assert len(GOLDEN) >= 3
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[13:-4] for p in GOLDEN])
+def test_wrappers_on_cpu_stand_in(oracle, path):
+    from oracle_env import OracleTorchEnv
+    assert replay(path, OracleTorchEnv(num_envs=1, autoreset=False, seed=0)) > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[13:-4] for p in GOLDEN])
+def test_wrappers_on_gpu(path):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from footsies_gym_b200 import FootsiesEnv
+    assert replay(path, FootsiesEnv(num_envs=1, device="cuda:0", autoreset=False, seed=0)) > 1000
+
+
+@pytest.mark.gpu
+def test_step_mask_freezes_unselected_envs(oracle):
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from footsies_gym_b200 import FootsiesEnv
+    from parity import compare_state_and_outputs
+    n = 600
+    rng = np.random.default_rng(9)
+    env = FootsiesEnv(num_envs=n, device="cuda:0", seed=2)
+    orc = oracle.OracleBatch(n, p2_bot=True, seed=2)
+    env.reset()
+    orc.reset()
+    for t in range(60):
+        a = rng.integers(0, 8, size=n, dtype=np.uint8)
+        env.step(torch.from_numpy(a))
+        orc.step(a)
+    before = env.get_state().copy()
+    obs_before = env.obs.clone()
+    mask = torch.from_numpy(rng.random(n) < 0.5)
+    env.set_step_mask(mask)
+    a = rng.integers(0, 8, size=n, dtype=np.uint8)
+    env.step(torch.from_numpy(a))
+    env.set_step_mask(None)
+    after = env.get_state()
+    m = mask.numpy()
+    assert np.array_equal(after[~m], before[~m])                       # untouched
+    assert torch.equal(env.obs[~mask].cpu(), obs_before[~mask].cpu())
+    orc.step(a)                                                        # oracle steps everybody: compare the stepped half
+    st = after.copy()
+    from parity import compare_states
+    compare_states(st[m], orc.trace[m], where="masked step")
+    env.close()
+
+
+def test_frame_skipped_batch_matches_single_env_semantics(oracle):
+    """_is_obs_skippable on a batch == the reference predicate applied row by row (frame_skip.py:56-66)."""
+    from footsies_gym_b200.moves import FOOTSIES_MOVE_INDEX_TO_MOVE, FootsiesMove
+    from footsies_gym_b200.wrappers import FootsiesFrameSkipped
+    from oracle_env import OracleTorchEnv
+    w = FootsiesFrameSkipped(OracleTorchEnv(num_envs=1))
+    hit_guard = {FootsiesMove.DAMAGE, FootsiesMove.GUARD_STAND, FootsiesMove.GUARD_CROUCH, FootsiesMove.GUARD_M,
+                 FootsiesMove.GUARD_BREAK}
+    rng = np.random.default_rng(0)
+    moves = rng.integers(0, 15, size=(500, 2))
+    mf = rng.integers(0, 3, size=(500, 2)).astype(np.float32)
+    obs = {"move": torch.from_numpy(moves.astype(np.float32)), "move_frame": torch.from_numpy(mf)}
+    got = w._is_obs_skippable(obs).tolist()
+    exp = [bool((mf[i, 0] != 0.0 and FOOTSIES_MOVE_INDEX_TO_MOVE[moves[i, 1]] not in hit_guard)
+                or FOOTSIES_MOVE_INDEX_TO_MOVE[moves[i, 0]] == FootsiesMove.DAMAGE) for i in range(500)]
+    assert got == exp
