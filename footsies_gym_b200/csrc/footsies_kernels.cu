@@ -541,7 +541,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef FG_WAIT_MODE
+#define FG_WAIT_MODE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if FG_WAIT_MODE == 1
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+#elif FG_WAIT_MODE == 3
+    uint32_t ok = 0u;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(64);
+    }
+#else
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -551,6 +577,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -608,6 +635,18 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
         const int i = c * kThreads + threadIdx.x;
         const bool valid = i < p.n && (p.step_mask == nullptr || p.step_mask[i < p.n ? i : 0] != 0);
         const bool staged = c < full_chunks;
+#if FG_WAIT_MODE == 2
+        // one warp polls the transaction barrier, the others block in bar.sync (no issue slots burnt); passing this
+        // barrier also proves every warp has finished reading the stage of chunk k-1, so it can be refilled
+        if (staged) {
+            if (threadIdx.x < 32) mbar_wait(&full_bar[s], (k / kStages) & 1);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int cn = c + (kStages - 1) * gridDim.x;
+            if (cn < full_chunks) issue(cn, (k + kStages - 1) % kStages);
+        }
+#else
         if (threadIdx.x == 0) {                                         // producer: chunk k + kStages - 1 -> the stage read at k - 1
             const int cn = c + (kStages - 1) * gridDim.x;
             if (cn < full_chunks) {
@@ -616,6 +655,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
                 issue(cn, sn);
             }
         }
+#endif
         const uint32_t act1 = nin1, act2 = nin2;
         {
             const int in = i + gridDim.x * kThreads;
@@ -625,14 +665,18 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const Params p) {
         bool run = false;
         uint32_t in1 = 0u, in2 = 0u;
         if (staged) {
+#if FG_WAIT_MODE != 2
             mbar_wait(&full_bar[s], (k / kStages) & 1);
+#endif
             const uint4 a = stage[s].pl[0][threadIdx.x], b = stage[s].pl[1][threadIdx.x], cc = stage[s].pl[2][threadIdx.x];
             e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
             e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
             e.frame = (int32_t)cc.x; e.misc = cc.y; e.bq2 = cc.z; e.bq1 = cc.w;
             if (kRng) { const uint4 r = stage[s].pl[kPlanes - 1][threadIdx.x]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
+#if FG_WAIT_MODE != 2
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
+#endif
         } else if (valid) {
             load_env<kRng>(p, i, e);                                    // ragged tail chunk: plain loads
         }
