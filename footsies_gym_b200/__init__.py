@@ -4,8 +4,9 @@ Importing the package never touches CUDA; constructing a FootsiesEnv does, and f
 GPU or without the in-tree library (python -m footsies_gym_b200.build).
 """
 from .env import FootsiesEnv, FootsiesGameClosedError
+from .state import FootsiesBattleState, FootsiesFighterState, FootsiesState
 from .moves import FOOTSIES_MOVE_ID_TO_INDEX, FOOTSIES_MOVE_INDEX_TO_MOVE, FootsiesMove, FootsiesMoveInfo
 
-__all__ = ["FootsiesEnv", "FootsiesGameClosedError", "FootsiesMove", "FootsiesMoveInfo",
+__all__ = ["FootsiesEnv", "FootsiesGameClosedError", "FootsiesState", "FootsiesBattleState", "FootsiesFighterState", "FootsiesMove", "FootsiesMoveInfo",
            "FOOTSIES_MOVE_INDEX_TO_MOVE", "FOOTSIES_MOVE_ID_TO_INDEX"]
 __version__ = "0.1.0"

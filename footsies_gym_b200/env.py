@@ -430,6 +430,29 @@ class FootsiesEnv:
         states = np.ascontiguousarray(states, dtype=_capi.env_state_dtype())
         _capi.check(self._lib.fg_set_state(self._handle, int(first), len(states), C.c_void_p(states.ctypes.data)))
 
+    def save_battle_state(self, index: Optional[int] = None):
+        """FootsiesEnv.save_battle_state (footsies.py:432-437, STATE_SAVE): the battle of env `index` as a
+        FootsiesBattleState in the reference's schema; index=None returns the single state when num_envs == 1
+        (the reference's call) and a list over all envs otherwise."""
+        from .state import env_state_to_battle_state
+        if index is None:
+            states = [env_state_to_battle_state(r) for r in self.get_state()]
+            return states[0] if self.num_envs == 1 else states
+        return env_state_to_battle_state(self.get_state(int(index), 1)[0])
+
+    def load_battle_state(self, battle_state, index: int = 0):
+        """FootsiesEnv.load_battle_state (footsies.py:439-444, STATE_LOAD -> BattleCore.LoadState,
+        BattleCore.cs:677-683): overwrite the fighters and the frame counter of env `index`; actors' held inputs,
+        bot queues, RNG and the reward accumulator are untouched like in the game.  Accepts a FootsiesBattleState
+        or its JSON string.  One difference: the next dense reward is computed against the loaded guard bars (the
+        reference would compare with the last state it received before the load)."""
+        from .state import FootsiesBattleState, battle_state_into_env_state
+        if isinstance(battle_state, str):
+            battle_state = FootsiesBattleState.from_json(battle_state)
+        rec = self.get_state(int(index), 1)
+        battle_state_into_env_state(battle_state, rec[0])
+        self.set_state(rec, int(index))
+
     def episode_stats(self) -> dict:
         """Episode statistics accumulated on the device by the step kernel's warp reductions."""
         out = np.zeros(_capi.FG_STAT_COUNT, dtype=np.uint64)

@@ -26,6 +26,7 @@ from . import frame_data as _fd
 INPUT_RECORD_FRAME = 180      # Fighter.cs:98 inputRecordFrame
 _HIST_FRAMES = 16             # frames of Left/Right history kept on the device
 _ATTACK_RUN_MAX = 59          # specialAttackHoldFrame - 1 (Fighter.cs:569-583)
+MAX_SPRITE_SHAKE_FRAME = 6    # Fighter.cs:110 (a constant of the game; the kernel clamps with it)
 _ACTIONS_BY_ID = {a["actionID"]: a for a in _fd.ACTIONS}
 _f32 = np.float32
 
@@ -190,10 +191,7 @@ def fighter_to_reference(f, face_right: bool) -> FootsiesFighterState:
         currentHitStunFrame=int(f["hitstun"]), input=inp, inputDown=down, inputUp=up,
         isInputBackward=bool(f["is_input_backward"]), isReserveProximityGuard=bool(f["is_reserve_prox"]),
         bufferActionID=int(f["buffer_id"]), reserveDamageActionID=int(f["reserve_id"]),
-        spriteShakePosition=shake,
-        # maxSpriteShakeFrame (Fighter.cs:438-444) only limits how far the shake decays per frame visually;
-        # the decay rule itself (:142-151) never reads it, so |position| is a faithful value to report
-        maxSpriteShakeFrame=abs(shake), hasWon=bool(f["has_won"]))
+        spriteShakePosition=shake, maxSpriteShakeFrame=MAX_SPRITE_SHAKE_FRAME, hasWon=bool(f["has_won"]))
 
 
 def env_state_to_battle_state(rec) -> FootsiesBattleState:
@@ -224,6 +222,8 @@ def fighter_from_reference(s: FootsiesFighterState, out):
         raise UnrepresentableStateError("hasWon fighters only exist in the versus-mode End state")
     if s.bufferActionID not in (-1, 110) or s.reserveDamageActionID not in (-1, 310):
         raise UnrepresentableStateError("bufferActionID must be -1 or 110 and reserveDamageActionID -1 or 310")
+    if s.maxSpriteShakeFrame != MAX_SPRITE_SHAKE_FRAME:
+        raise UnrepresentableStateError("maxSpriteShakeFrame is the game constant 6 (Fighter.cs:110)")
     if s.currentActionID not in _ACTIONS_BY_ID:
         raise UnrepresentableStateError(f"unknown action id {s.currentActionID}")
     out["pos_x"] = _f32(s.position[0])

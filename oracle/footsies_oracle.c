@@ -1028,6 +1028,86 @@ void fo_set_state(fo_batch *b, int32_t env, const fo_fighter_state *p1, const fo
     fill_trace(e, &e->current_state, 0.0, 0, 0, 0);
 }
 void fo_get_trace(fo_batch *b, int32_t env, fo_trace *out) { *out = b->envs[env].last; }
+
+/* BattleCore.SaveState (BattleCore.cs:667-674) -> Fighter.SaveState (Fighter.cs:721-737) -> FighterState ctor
+ * (FighterState.cs:58-131) */
+void fo_save_battle_state(fo_batch *b, int32_t env, fo_battle_state *out) {
+    const Env *e = &b->envs[env];
+    memset(out, 0, sizeof *out);
+    for (int i = 0; i < 2; i++) {
+        const Fighter *f = &e->fighter[i];
+        fo_full_fighter *o = &out->p[i];
+        o->position[0] = f->pos_x; o->position[1] = f->pos_y;
+        o->velocity_x = f->velocity_x;
+        o->isFaceRight = f->isFaceRight;
+        o->n_hitboxes = f->n_hitboxes;
+        for (int k = 0; k < f->n_hitboxes; k++) {
+            const Hitbox *h = &f->hitboxes[k];
+            o->hitboxes[k].rect = (fo_rect){ h->rect.x, h->rect.y, h->rect.width, h->rect.height };
+            o->hitboxes[k].proximity = h->proximity;
+            o->hitboxes[k].attackID = h->attackID;
+        }
+        o->n_hurtboxes = f->n_hurtboxes;
+        for (int k = 0; k < f->n_hurtboxes; k++) {
+            const Rect *r = &f->hurtboxes[k].rect;
+            o->hurtboxes[k] = (fo_rect){ r->x, r->y, r->width, r->height };
+        }
+        o->pushbox = (fo_rect){ f->pushbox.rect.x, f->pushbox.rect.y, f->pushbox.rect.width, f->pushbox.rect.height };
+        o->vitalHealth = f->vitalHealth; o->guardHealth = f->guardHealth;
+        o->currentActionID = f->currentActionID; o->currentActionFrame = f->currentActionFrame;
+        o->currentActionHitCount = f->currentActionHitCount; o->currentHitStunFrame = f->currentHitStunFrame;
+        for (int k = 0; k < INPUT_RECORD_FRAME; k++) {
+            o->input[k] = f->input[k]; o->inputDown[k] = f->inputDown[k]; o->inputUp[k] = f->inputUp[k];
+        }
+        o->isInputBackward = f->isInputBackward; o->isReserveProximityGuard = f->isReserveProximityGuard;
+        o->bufferActionID = f->bufferActionID; o->reserveDamageActionID = f->reserveDamageActionID;
+        o->spriteShakePosition = f->spriteShakePosition; o->maxSpriteShakeFrame = f->maxSpriteShakeFrame;
+        o->hasWon = f->hasWon;
+    }
+    out->roundStartTime = 0.0f;   /* Time.fixedTime at round start: display only */
+    out->frameCount = e->frameCount;
+}
+
+/* BattleCore.LoadState (BattleCore.cs:677-683) -> Fighter.LoadState (Fighter.cs:739-811) */
+void fo_load_battle_state(fo_batch *b, int32_t env, const fo_battle_state *in) {
+    Env *e = &b->envs[env];
+    for (int i = 0; i < 2; i++) {
+        Fighter *f = &e->fighter[i];
+        const fo_full_fighter *s = &in->p[i];
+        f->pos_x = s->position[0]; f->pos_y = s->position[1];
+        f->velocity_x = s->velocity_x;
+        f->isFaceRight = s->isFaceRight;
+        f->n_hitboxes = s->n_hitboxes;
+        for (int k = 0; k < s->n_hitboxes; k++) {
+            f->hitboxes[k].rect = (Rect){ s->hitboxes[k].rect.x, s->hitboxes[k].rect.y, s->hitboxes[k].rect.width, s->hitboxes[k].rect.height };
+            f->hitboxes[k].attackID = s->hitboxes[k].attackID;
+            f->hitboxes[k].proximity = s->hitboxes[k].proximity;
+        }
+        f->n_hurtboxes = s->n_hurtboxes;
+        for (int k = 0; k < s->n_hurtboxes; k++)
+            f->hurtboxes[k].rect = (Rect){ s->hurtboxes[k].x, s->hurtboxes[k].y, s->hurtboxes[k].width, s->hurtboxes[k].height };
+        f->pushbox.rect = (Rect){ s->pushbox.x, s->pushbox.y, s->pushbox.width, s->pushbox.height };
+        f->vitalHealth = s->vitalHealth; f->guardHealth = s->guardHealth;
+        f->currentActionID = s->currentActionID; f->currentActionFrame = s->currentActionFrame;
+        f->currentActionHitCount = s->currentActionHitCount; f->currentHitStunFrame = s->currentHitStunFrame;
+        for (int k = 0; k < INPUT_RECORD_FRAME; k++) {
+            f->input[k] = s->input[k]; f->inputDown[k] = s->inputDown[k]; f->inputUp[k] = s->inputUp[k];
+        }
+        f->isInputBackward = s->isInputBackward; f->isReserveProximityGuard = s->isReserveProximityGuard;
+        f->bufferActionID = s->bufferActionID; f->reserveDamageActionID = s->reserveDamageActionID;
+        f->spriteShakePosition = s->spriteShakePosition; f->maxSpriteShakeFrame = s->maxSpriteShakeFrame;
+        f->hasWon = s->hasWon;
+    }
+    e->frameCount = in->frameCount;
+    /* test convenience (not in the reference, whose Python side only learns about the load from the next state it
+     * receives, so that its next dense reward compares guard bars across the load): make the loaded state the
+     * "previous state" of the next step and refresh the trace so that fo_get_trace shows the loaded fighters */
+    e->current_state = GetEnvironmentState(e);
+    e->has_terminated = f_isDead(&e->fighter[0]) || f_isDead(&e->fighter[1]);
+    fill_fighter_state(&e->fighter[0], &e->last.f[0]);
+    fill_fighter_state(&e->fighter[1], &e->last.f[1]);
+    e->last.frame = e->frameCount;
+}
 int64_t fo_frames_simulated(fo_batch *b) {
     int64_t s = 0;
     for (int i = 0; i < b->n; i++) s += b->envs[i].frames_simulated;

@@ -107,6 +107,34 @@ void fo_step(fo_batch *b, const uint8_t *actions_p1, const uint8_t *actions_p2, 
  * fo_fighter_state plus frame are taken; history is rebuilt from hist_left/right/attack_run. */
 void fo_set_state(fo_batch *b, int32_t env, const fo_fighter_state *p1, const fo_fighter_state *p2, int32_t frame);
 void fo_get_trace(fo_batch *b, int32_t env, fo_trace *out);
+
+/* Full battle state in the reference's save / load schema (BattleState.cs:9-24, FighterState.cs:26-56): the whole
+ * 180-entry input arrays and the boxes as they stand.  fo_save_battle_state = BattleCore.SaveState
+ * (BattleCore.cs:667-674, Fighter.cs:721-737); fo_load_battle_state = BattleCore.LoadState (BattleCore.cs:677-683,
+ * Fighter.cs:739-811): fighters and frameCount only -- actors, bot queues, RNG and the Python-side state of the env
+ * stay as they are. */
+#define FO_INPUT_RECORD_FRAME 180
+#define FO_MAX_BOXES 8
+typedef struct { float x, y, width, height; } fo_rect;
+typedef struct { fo_rect rect; int32_t proximity; int32_t attackID; } fo_hitbox;
+typedef struct {
+    float position[2];
+    float velocity_x;
+    int32_t isFaceRight;
+    int32_t n_hitboxes; fo_hitbox hitboxes[FO_MAX_BOXES];
+    int32_t n_hurtboxes; fo_rect hurtboxes[FO_MAX_BOXES];
+    fo_rect pushbox;
+    int32_t vitalHealth, guardHealth;
+    int32_t currentActionID, currentActionFrame, currentActionHitCount, currentHitStunFrame;
+    int32_t input[FO_INPUT_RECORD_FRAME], inputDown[FO_INPUT_RECORD_FRAME], inputUp[FO_INPUT_RECORD_FRAME];
+    int32_t isInputBackward, isReserveProximityGuard;
+    int32_t bufferActionID, reserveDamageActionID;
+    int32_t spriteShakePosition, maxSpriteShakeFrame;
+    int32_t hasWon;
+} fo_full_fighter;
+typedef struct { fo_full_fighter p[2]; float roundStartTime; int32_t frameCount; } fo_battle_state;
+void fo_save_battle_state(fo_batch *b, int32_t env, fo_battle_state *out);
+void fo_load_battle_state(fo_batch *b, int32_t env, const fo_battle_state *in);
 /* Total fight frames simulated so far (the env-frames counter of the metric). */
 int64_t fo_frames_simulated(fo_batch *b);
 /* Episode statistics accumulated so far: see FO_STAT_* */

@@ -104,94 +104,34 @@ def free_ports(k):
     return ports
 
 
-class OracleGameServer(threading.Thread):
-    """Plays the Unity game's role on the wire; the battle engine behind it is the CPU oracle."""
+class OracleGameServer:
+    """The product's wire server (footsies_gym_b200.wire.FootsiesWireServer) playing the Unity game's role, with
+    the CPU oracle as its battle engine; records what the game did as (kind, a, b) ops."""
 
     def __init__(self, ports, p2_remote, seed0=0):
-        super().__init__(daemon=True)
-        import oracle_binding as ob
-        self.ob = ob
-        self.ports = ports
-        self.p2_remote = p2_remote
-        # game side only: the oracle's own python half is irrelevant here (autoreset off, delay 0)
-        self.orc = ob.OracleBatch(1, p2_bot=not p2_remote, autoreset=False, seed=seed0)
+        from footsies_gym_b200.wire import FootsiesWireServer
+        from oracle_wire_backend import OracleBattleBackend
+        self.backend = OracleBattleBackend(seed=seed0, p2_bot=not p2_remote)
         self.ops = []
-        self.listeners = []
-        for p in ports[: 3 if p2_remote else 2]:
-            ls = socket.socket()
-            ls.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-            ls.bind(("127.0.0.1", p))
-            ls.listen(1)
-            self.listeners.append(ls)
-        self.stop_flag = False
+        self.server = FootsiesWireServer(self.backend, ports[0], ports[1], ports[2] if p2_remote else None,
+                                         on_op=self._on_op)
 
-    def state_json(self):
-        t = self.orc.trace[0]
-        f1, f2 = t["f"][0], t["f"][1]
-        d = {
-            "p1Vital": int(f1["vital"]), "p2Vital": int(f2["vital"]), "p1Guard": int(f1["guard"]),
-            "p2Guard": int(f2["guard"]), "p1Move": int(f1["action_id"]), "p1MoveFrame": int(f1["action_frame"]),
-            "p2Move": int(f2["action_id"]), "p2MoveFrame": int(f2["action_frame"]),
-            "p1Position": float(f1["pos_x"]), "p2Position": float(f2["pos_x"]), "globalFrame": int(t["frame"]),
-            "p1MostRecentAction": int(t["recorded_input"][0]), "p2MostRecentAction": int(t["recorded_input"][1]),
-            "p1Hitstun": int(f1["hitstun"]), "p2Hitstun": int(f2["hitstun"]),
-        }
-        return json.dumps(d).encode("utf-8")
+    def _on_op(self, kind, *args):
+        if kind == "frame":
+            self.ops.append((0, args[0], args[1]))
+        elif kind == "round_start":
+            self.ops.append((1, 0, 0))
+        elif kind == "seed":
+            self.ops.append((2, args[0], 0))
 
-    @staticmethod
-    def send_msg(sock, payload):
-        sock.sendall(struct.pack("!I", len(payload)) + payload)       # SocketHelper.cs:70-82
+    def start(self):
+        self.server.start()
 
-    @staticmethod
-    def recv_exact(sock, n):
-        buf = b""
-        while len(buf) < n:
-            chunk = sock.recv(n - len(buf))
-            if not chunk:
-                raise ConnectionError("peer closed")
-            buf += chunk
-        return buf
+    def stop(self):
+        self.server.stop()
 
-    def round_start(self):
-        self.orc.reset()
-        self.ops.append((1, 0, 0))
-        self.send_msg(self.p1, self.state_json())
-
-    def run(self):
-        import select
-        # accept order mirrors FootsiesEnv._connect_to_game: P1, remote control, then the opponent
-        self.p1, _ = self.listeners[0].accept()
-        self.rc, _ = self.listeners[1].accept()
-        self.p2 = None
-        if self.p2_remote:
-            self.p2, _ = self.listeners[2].accept()
-        try:
-            self.round_start()
-            while not self.stop_flag:
-                r, _, _ = select.select([self.p1, self.rc], [], [], 0.2)
-                if self.rc in r:                                       # TrainingRemoteControl.ProcessCommand
-                    size = struct.unpack("!I", self.recv_exact(self.rc, 4))[0]
-                    msg = json.loads(self.recv_exact(self.rc, size).decode("utf-8"))
-                    if msg["command"] == 1:                            # RESET
-                        self.round_start()
-                    elif msg["command"] == 5:                          # SEED
-                        self.orc.seed(int(msg["value"]))
-                        self.ops.append((2, int(msg["value"]), 0))
-                    continue
-                if self.p1 in r:
-                    a = self.recv_exact(self.p1, 3)                    # TrainingRemoteActor.cs:93-116
-                    a1 = (1 if a[0] else 0) | (2 if a[1] else 0) | (4 if a[2] else 0)
-                    a2 = 0
-                    if self.p2 is not None:
-                        b = self.recv_exact(self.p2, 3)
-                        a2 = (1 if b[0] else 0) | (2 if b[1] else 0) | (4 if b[2] else 0)
-                    self.orc.step([a1], [a2])
-                    self.ops.append((0, a1, a2))
-                    self.send_msg(self.p1, self.state_json())
-                    if self.orc.trace[0]["battle_over"]:               # the game restarts by itself
-                        self.round_start()
-        except (ConnectionError, OSError):
-            pass
+    def join(self, timeout=None):
+        self.server.join(timeout)
 
 
 def flat_obs(obs):
@@ -258,7 +198,7 @@ def run_scenario(name, *, dense, frame_delay, p2_remote, n_calls, rng_seed, seed
             record(1, obs, 0.0, False, False, info)
             call_ops.append("reset")
             steps_in_episode = 0
-    server.stop_flag = True
+    server.stop()
     env.close()
     server.join(timeout=5)
 
@@ -355,7 +295,7 @@ def run_wrapper_scenario(name, chain, n_calls, rng_seed):
         if terminated:
             obs, info = env.reset(seed=None, options=None)
             rec(1, 0, obs, 0.0, False, info)
-    server.stop_flag = True
+    server.stop()
     env.close()
     server.join(timeout=5)
     extra = {}
@@ -370,9 +310,55 @@ def run_wrapper_scenario(name, chain, n_calls, rng_seed):
           f"-> {os.path.relpath(path, ROOT)}")
 
 
+def run_battle_state_fixture():
+    """STATE_SAVE / STATE_LOAD through the reference's own client code and dataclasses (footsies.py:407-444,
+    state.py:78-137): the reference FootsiesEnv asks the wire server for battle states, its FootsiesBattleState
+    parses and re-serialises them, and its FootsiesState.from_battle_state gives the summary view.  The fixture pins
+    the JSON schema and field order our state.py must reproduce."""
+    import dataclasses
+    from footsies_gym.envs.footsies import FootsiesEnv
+    from footsies_gym.state import FootsiesBattleState as RefBattleState, FootsiesFighterState as RefFighterState
+    from footsies_gym.state import FootsiesState as RefState
+    ports = free_ports(3)
+    server = OracleGameServer(ports, p2_remote=False)
+    server.start()
+    env = FootsiesEnv(game_address="127.0.0.1", game_port=ports[0], remote_control_port=ports[1],
+                      opponent_port=ports[2], skip_instancing=True, sync_mode="synced_non_blocking")
+    rng = np.random.default_rng(11)
+    env.reset(seed=5)
+    cases = []
+    sticky = 0
+    for t in range(400):
+        if rng.random() < 0.2:
+            sticky = int(rng.integers(0, 8))
+        obs, reward, terminated, truncated, info = env.step((sticky & 1 != 0, sticky & 2 != 0, sticky & 4 != 0))
+        if terminated:
+            env.reset()
+        elif t % 40 == 17:
+            bs = env.save_battle_state()                       # reference client + reference dataclass parsing
+            st = RefState.from_battle_state(bs)
+            d = dataclasses.asdict(st)
+            d["p1MostRecentAction"] = list(d["p1MostRecentAction"])
+            d["p2MostRecentAction"] = list(d["p2MostRecentAction"])
+            cases.append({"reference_json": bs.json(), "reference_footsies_state": d})
+            # a load of the state just saved must leave the game where it is (round trip through the reference)
+            env.load_battle_state(bs)
+            again = env.save_battle_state()
+            assert again.json() == bs.json()
+    server.stop()
+    env.close()
+    server.join(timeout=5)
+    path = os.path.join(HERE, "ref_battle_state.json")
+    with open(path, "w") as f:
+        json.dump({"fighter_fields": [x.name for x in dataclasses.fields(RefFighterState)],
+                   "battle_fields": [x.name for x in dataclasses.fields(RefBattleState)], "cases": cases}, f)
+    print(f"battle_state: {len(cases)} saved states -> {os.path.relpath(path, ROOT)}")
+
+
 def main():
     install_gymnasium_stub()
     sys.path.insert(0, REF_PY)
+    run_battle_state_fixture()
     run_scenario("dense_bot", dense=True, frame_delay=0, p2_remote=False, n_calls=6000, rng_seed=1)
     run_scenario("sparse_bot", dense=False, frame_delay=0, p2_remote=False, n_calls=3000, rng_seed=2)
     run_scenario("dense_delay3_bot", dense=True, frame_delay=3, p2_remote=False, n_calls=3000, rng_seed=3)

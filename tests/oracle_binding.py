@@ -27,6 +27,20 @@ TRACE_DTYPE = np.dtype([
     ("reward_f64", "<f8"),
 ], align=True)
 
+RECT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("width", "<f4"), ("height", "<f4")])
+HITBOX_DTYPE = np.dtype([("rect", RECT_DTYPE), ("proximity", "<i4"), ("attackID", "<i4")])
+FULL_FIGHTER_DTYPE = np.dtype([
+    ("position", "<f4", (2,)), ("velocity_x", "<f4"), ("isFaceRight", "<i4"),
+    ("n_hitboxes", "<i4"), ("hitboxes", HITBOX_DTYPE, (8,)), ("n_hurtboxes", "<i4"), ("hurtboxes", RECT_DTYPE, (8,)),
+    ("pushbox", RECT_DTYPE), ("vitalHealth", "<i4"), ("guardHealth", "<i4"), ("currentActionID", "<i4"),
+    ("currentActionFrame", "<i4"), ("currentActionHitCount", "<i4"), ("currentHitStunFrame", "<i4"),
+    ("input", "<i4", (180,)), ("inputDown", "<i4", (180,)), ("inputUp", "<i4", (180,)),
+    ("isInputBackward", "<i4"), ("isReserveProximityGuard", "<i4"), ("bufferActionID", "<i4"),
+    ("reserveDamageActionID", "<i4"), ("spriteShakePosition", "<i4"), ("maxSpriteShakeFrame", "<i4"),
+    ("hasWon", "<i4"),
+])
+BATTLE_STATE_DTYPE = np.dtype([("p", FULL_FIGHTER_DTYPE, (2,)), ("roundStartTime", "<f4"), ("frameCount", "<i4")])
+
 STAT_NAMES = ["episodes", "p1_wins", "p2_wins", "double_ko", "frames", "p1_specials", "p1_specials_neutral",
               "guard_breaks", "hits", "blocks"]
 
@@ -63,6 +77,8 @@ def lib():
         L.fo_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         L.fo_set_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32]
         L.fo_get_trace.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.fo_save_battle_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.fo_load_battle_state.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.fo_frames_simulated.restype = C.c_int64
         L.fo_frames_simulated.argtypes = [C.c_void_p]
         L.fo_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -130,7 +146,19 @@ class OracleBatch:
             for k, v in d.items():
                 s[k] = v
         lib().fo_set_state(self.h, int(env), _ptr(s1), _ptr(s2), int(frame))
-        lib().fo_get_trace(self.h, int(env), C.c_void_p(self.trace.ctypes.data + env * TRACE_DTYPE.itemsize))
+        lib().fo_get_trace(self.h, int(env), C.c_void_p(self.trace.ctypes.data + int(env) * TRACE_DTYPE.itemsize))
+
+    # ---- full battle state in the reference's save / load schema (BattleCore.SaveState / LoadState) ----
+    def save_battle_state(self, env):
+        """-> dict in the JSON layout of BattleState.cs / FighterState.cs (what JsonUtility.ToJson would emit)."""
+        raw = np.zeros(1, dtype=BATTLE_STATE_DTYPE)
+        lib().fo_save_battle_state(self.h, int(env), _ptr(raw))
+        return battle_state_record_to_dict(raw[0])
+
+    def load_battle_state(self, env, state_dict):
+        raw = battle_state_dict_to_record(state_dict)
+        lib().fo_load_battle_state(self.h, int(env), _ptr(raw))
+        lib().fo_get_trace(self.h, int(env), C.c_void_p(self.trace.ctypes.data + int(env) * TRACE_DTYPE.itemsize))
 
     def frames_simulated(self):
         return int(lib().fo_frames_simulated(self.h))
@@ -148,3 +176,63 @@ def rng_stream(seed, n):
     s = (C.c_uint32 * 4)()
     lib().fo_rng_init(s, int(seed))
     return [int(lib().fo_rng_next(s)) for _ in range(n)]
+
+
+def _rect_dict(r):
+    return {"x": float(r["x"]), "y": float(r["y"]), "width": float(r["width"]), "height": float(r["height"])}
+
+
+def battle_state_record_to_dict(rec):
+    out = {}
+    for name, f in (("p1State", rec["p"][0]), ("p2State", rec["p"][1])):
+        out[name] = {
+            "position": [float(f["position"][0]), float(f["position"][1])], "velocity_x": float(f["velocity_x"]),
+            "isFaceRight": bool(f["isFaceRight"]),
+            "hitboxes": [{"rect": _rect_dict(f["hitboxes"][k]["rect"]), "proximity": bool(f["hitboxes"][k]["proximity"]),
+                          "attackID": int(f["hitboxes"][k]["attackID"])} for k in range(int(f["n_hitboxes"]))],
+            "hurtboxes": [_rect_dict(f["hurtboxes"][k]) for k in range(int(f["n_hurtboxes"]))],
+            "pushbox": _rect_dict(f["pushbox"]),
+            "vitalHealth": int(f["vitalHealth"]), "guardHealth": int(f["guardHealth"]),
+            "currentActionID": int(f["currentActionID"]), "currentActionFrame": int(f["currentActionFrame"]),
+            "currentActionHitCount": int(f["currentActionHitCount"]), "currentHitStunFrame": int(f["currentHitStunFrame"]),
+            "input": [int(v) for v in f["input"]], "inputDown": [int(v) for v in f["inputDown"]],
+            "inputUp": [int(v) for v in f["inputUp"]],
+            "isInputBackward": bool(f["isInputBackward"]), "isReserveProximityGuard": bool(f["isReserveProximityGuard"]),
+            "bufferActionID": int(f["bufferActionID"]), "reserveDamageActionID": int(f["reserveDamageActionID"]),
+            "spriteShakePosition": int(f["spriteShakePosition"]), "maxSpriteShakeFrame": int(f["maxSpriteShakeFrame"]),
+            "hasWon": bool(f["hasWon"]),
+        }
+    out["roundStartTime"] = float(rec["roundStartTime"])
+    out["frameCount"] = int(rec["frameCount"])
+    return out
+
+
+def battle_state_dict_to_record(d):
+    raw = np.zeros(1, dtype=BATTLE_STATE_DTYPE)
+    for i, name in enumerate(("p1State", "p2State")):
+        s, f = d[name], raw[0]["p"][i]
+        f["position"] = s["position"]
+        f["velocity_x"] = s["velocity_x"]
+        f["isFaceRight"] = int(s["isFaceRight"])
+        f["n_hitboxes"] = len(s["hitboxes"])
+        for k, h in enumerate(s["hitboxes"]):
+            f["hitboxes"][k]["rect"] = (h["rect"]["x"], h["rect"]["y"], h["rect"]["width"], h["rect"]["height"])
+            f["hitboxes"][k]["proximity"] = int(h["proximity"])
+            f["hitboxes"][k]["attackID"] = h["attackID"]
+        f["n_hurtboxes"] = len(s["hurtboxes"])
+        for k, h in enumerate(s["hurtboxes"]):
+            f["hurtboxes"][k] = (h["x"], h["y"], h["width"], h["height"])
+        p = s["pushbox"]
+        f["pushbox"] = (p["x"], p["y"], p["width"], p["height"])
+        for key in ("vitalHealth", "guardHealth", "currentActionID", "currentActionFrame", "currentActionHitCount",
+                    "currentHitStunFrame", "bufferActionID", "reserveDamageActionID", "spriteShakePosition",
+                    "maxSpriteShakeFrame"):
+            f[key] = s[key]
+        for key in ("input", "inputDown", "inputUp"):
+            arr = list(s[key])[:180]
+            f[key][:len(arr)] = arr
+        for key in ("isInputBackward", "isReserveProximityGuard", "hasWon"):
+            f[key] = int(s[key])
+    raw[0]["roundStartTime"] = d["roundStartTime"]
+    raw[0]["frameCount"] = d["frameCount"]
+    return raw
