@@ -29,7 +29,7 @@ def sources():
 
 def deps():
     inc = os.path.join(os.path.dirname(PKG_DIR), "include", "footsies_b200.h")
-    return sources() + [os.path.join(CSRC, "state_codec.h"), os.path.join(CSRC, "frame_tables.h"), inc]
+    return sources() + [os.path.join(CSRC, f) for f in ("state_codec.h", "frame_tables.h", "frame_logic.cuh", "tables_host.h")] + [inc]
 
 
 def is_stale():

@@ -26,18 +26,27 @@
 #define FG_PLANE_ENV 2  // {frame, misc, bot queue P2, bot queue P1}
 #define FG_PLANE_RNG 3  // xorshift128 state
 
-// packed fighter word
-#define FGP_ACT_SHIFT 0      // 5 bits: action index (moves.py order)
-#define FGP_FRAME_SHIFT 5    // 9 bits
-#define FGP_STUN_SHIFT 14    // 5 bits
-#define FGP_GUARD_SHIFT 19   // 2 bits
-#define FGP_VITAL_SHIFT 21   // 1 bit
-#define FGP_HITCNT_SHIFT 22  // 1 bit (numberOfHit == 1 for every attack)
-#define FGP_BUF_SHIFT 23     // 1 bit: bufferActionID == 110
-#define FGP_RSV_SHIFT 24     // 1 bit: reserveDamageActionID == 310
-#define FGP_INBACK_SHIFT 25  // 1 bit: isInputBackward
-#define FGP_RPROX_SHIFT 26   // 1 bit: isReserveProximityGuard
-#define FGP_SHAKE_SHIFT 27   // 4 bits two's complement: spriteShakePosition in [-6, 6]
+// packed fighter word.  The low 11 bits (frame | action << 6) are the index of the fighter's row in the
+// [action][64 frames] frame table, so the table lookup needs no arithmetic.
+#define FGP_FRAME_SHIFT 0    // 6 bits: currentActionFrame (every reachable frame is < 63; DEAD saturates)
+#define FGP_ACT_SHIFT 6      // 5 bits: action index (moves.py order)
+#define FGP_STUN_SHIFT 11    // 5 bits
+#define FGP_GUARD_SHIFT 16   // 2 bits
+#define FGP_VITAL_SHIFT 18   // 1 bit
+#define FGP_HITCNT_SHIFT 19  // 1 bit (numberOfHit == 1 for every attack)
+#define FGP_BUF_SHIFT 20     // 1 bit: bufferActionID == 110
+#define FGP_RSV_SHIFT 21     // 1 bit: reserveDamageActionID == 310
+#define FGP_INBACK_SHIFT 22  // 1 bit: isInputBackward
+#define FGP_RPROX_SHIFT 23   // 1 bit: isReserveProximityGuard
+#define FGP_SHAKE_SHIFT 24   // 4 bits sign-magnitude: |spriteShakePosition| in [24:27), negative in [27]
+#define FGP_SHAKE_SIGN_SHIFT 27
+// carry bits: facts about (action, frame) that the NEXT frame's request logic needs, copied from the row (row.w)
+#define FGP_CARRY_END (1u << 28)     // the action is over as soon as the frame counter increments (Fighter.cs:90)
+#define FGP_CARRY_ALWAYS (1u << 29)  // alwaysCancelable
+#define FGP_CARRY_NORMAL (1u << 30)  // N_ATTACK / B_ATTACK
+#define FGP_CARRY_MASK (7u << 28)
+#define FGP_ROW_MASK 0x7ffu
+#define FGP_MAX_FRAME 63
 
 // misc env word
 #define FGM_ARUN1_SHIFT 0    // 6 bits: attack run length P1 (saturates at 59)
@@ -72,7 +81,7 @@ static inline void fg_decode_fighter(const FgVec4 &v, uint32_t arun, fg_fighter_
     o->velocity_x = fg_u2f(v.y);
     uint32_t p = v.z;
     o->action_id = FG_ACTION_IDS[fg_bits(p, FGP_ACT_SHIFT, 5) % FT_NUM_ACTIONS];
-    o->action_frame = (int)fg_bits(p, FGP_FRAME_SHIFT, 9);
+    o->action_frame = (int)fg_bits(p, FGP_FRAME_SHIFT, 6);
     o->hitstun = (int)fg_bits(p, FGP_STUN_SHIFT, 5);
     o->guard = (int)fg_bits(p, FGP_GUARD_SHIFT, 2);
     o->vital = (int)fg_bits(p, FGP_VITAL_SHIFT, 1);
@@ -81,7 +90,7 @@ static inline void fg_decode_fighter(const FgVec4 &v, uint32_t arun, fg_fighter_
     o->reserve_id = fg_bits(p, FGP_RSV_SHIFT, 1) ? 310 : -1;
     o->is_input_backward = (int)fg_bits(p, FGP_INBACK_SHIFT, 1);
     o->is_reserve_prox = (int)fg_bits(p, FGP_RPROX_SHIFT, 1);
-    o->shake = ((int32_t)(fg_bits(p, FGP_SHAKE_SHIFT, 4) << 28)) >> 28;
+    o->shake = (int)fg_bits(p, FGP_SHAKE_SHIFT, 3) * (fg_bits(p, FGP_SHAKE_SIGN_SHIFT, 1) ? -1 : 1);
     o->has_won = 0;
     o->hist_left = v.w & 0xffffu;
     o->hist_right = v.w >> 16;
@@ -94,19 +103,26 @@ static inline int fg_encode_fighter(const fg_fighter_state *s, FgVec4 *v, uint32
     int idx = fg_action_index(s->action_id);
     if (idx < 0 || idx == FT_IDX_WIN || s->has_won) return -1;
     int frame_count = (int)(FG_ACTION_INFO_H[idx] & 0x1ffu);
-    if (s->action_frame < 0 || s->action_frame > frame_count || s->action_frame > 511) return -1;
+    int frame = s->action_frame;
+    // at a frame boundary an action is never at its end (the frame that reaches frameCount switches action at once,
+    // Fighter.cs:201-286); only a dead fighter's DEAD action keeps counting, and nothing reads it any more
+    if (idx == FT_IDX_DEAD && frame > FGP_MAX_FRAME) frame = FGP_MAX_FRAME;
+    if (frame < 0 || frame >= frame_count || frame > FGP_MAX_FRAME) return -1;
     if (s->hitstun < 0 || s->hitstun > 31 || s->guard < 0 || s->guard > 3 || s->vital < 0 || s->vital > 1) return -1;
     if (s->hit_count < 0 || s->hit_count > 1) return -1;
     if (!(s->buffer_id == -1 || s->buffer_id == 110) || !(s->reserve_id == -1 || s->reserve_id == 310)) return -1;
     if (s->shake < -6 || s->shake > 6 || s->attack_run < 0 || s->attack_run > 59) return -1;
     if ((s->hist_left | s->hist_right) >> 16) return -1;
-    uint32_t p = (uint32_t)idx << FGP_ACT_SHIFT | (uint32_t)s->action_frame << FGP_FRAME_SHIFT
+    uint32_t carry = (frame + 1 >= frame_count ? FGP_CARRY_END : 0u) | ((FG_ACTION_INFO_H[idx] >> 9) & 1u ? FGP_CARRY_ALWAYS : 0u)
+                   | ((idx == FT_IDX_N_ATTACK || idx == FT_IDX_B_ATTACK) ? FGP_CARRY_NORMAL : 0u);
+    uint32_t mag = (uint32_t)(s->shake < 0 ? -s->shake : s->shake);
+    uint32_t p = (uint32_t)idx << FGP_ACT_SHIFT | (uint32_t)frame << FGP_FRAME_SHIFT
                | (uint32_t)s->hitstun << FGP_STUN_SHIFT | (uint32_t)s->guard << FGP_GUARD_SHIFT
                | (uint32_t)s->vital << FGP_VITAL_SHIFT | (uint32_t)s->hit_count << FGP_HITCNT_SHIFT
                | (uint32_t)(s->buffer_id == 110) << FGP_BUF_SHIFT | (uint32_t)(s->reserve_id == 310) << FGP_RSV_SHIFT
                | (uint32_t)(s->is_input_backward != 0) << FGP_INBACK_SHIFT
                | (uint32_t)(s->is_reserve_prox != 0) << FGP_RPROX_SHIFT
-               | ((uint32_t)s->shake & 0xfu) << FGP_SHAKE_SHIFT;
+               | mag << FGP_SHAKE_SHIFT | (uint32_t)(s->shake < 0) << FGP_SHAKE_SIGN_SHIFT | carry;
     v->x = fg_f2u(s->pos_x);
     v->y = fg_f2u(s->velocity_x);
     v->z = p;

@@ -1,0 +1,116 @@
+"""Parity cases shared by the GPU tests (CUDA path through the C ABI) and the host-emulation tests (the same device
+logic compiled for the host): the implementation under test against the CPU oracle on the same seeded action tapes
+-- every env, every frame, every field (see tests/parity.py for the bar).  `scale` shrinks env counts for the CPU run."""
+import numpy as np
+import torch
+
+
+def tape_uniform(rng, steps, n):
+    """iid uniform over the 8 input bitmasks (the benchmark's synthetic actions)."""
+    return rng.integers(0, 8, size=(steps, n), dtype=np.uint8)
+
+
+def tape_sticky(rng, steps, n, p_change=0.15, weights=None):
+    """Inputs held for geometric durations: reaches charged specials, dashes, long blocks, guard breaks."""
+    out = np.zeros((steps, n), dtype=np.uint8)
+    cur = rng.integers(0, 8, size=n, dtype=np.uint8)
+    w = None if weights is None else np.asarray(weights, dtype=np.float64) / np.sum(weights)
+    for t in range(steps):
+        change = rng.random(n) < p_change
+        new = rng.choice(8, size=n, p=w).astype(np.uint8)
+        cur = np.where(change, new, cur)
+        out[t] = cur
+    return out
+
+
+def run_case(make_env, ob, n, steps, *, p1_bot=False, p2_bot=True, dense=True, frame_skip=1, autoreset=True, stale=True,
+             seed=0, tape1=None, tape2=None, first_env_index=0, check_every=1):
+    from parity import compare_state_and_outputs, compare_stats
+    env = make_env(num_envs=n, by_example=p1_bot, opponent=None if p2_bot else "self_play",
+                   dense_reward=dense, frame_skip=frame_skip, autoreset=autoreset, seed=seed,
+                   first_env_index=first_env_index, stale_intro_input=stale)
+    orc = ob.OracleBatch(n, p1_bot=p1_bot, p2_bot=p2_bot, dense_reward=dense, autoreset=autoreset,
+                         stale_intro_input=stale, first_env_index=first_env_index, seed=seed, threads=8)
+    env.reset()
+    orc.reset()
+    compare_state_and_outputs(env, orc.trace, where="reset")
+    for t in range(steps):
+        a1 = None if p1_bot else tape1[t]
+        a2 = None if p2_bot else tape2[t]
+        env.step(None if a1 is None else torch.from_numpy(a1), None if a2 is None else torch.from_numpy(a2))
+        orc.step(a1 if a1 is not None else np.zeros(n, np.uint8), a2, repeat=frame_skip)
+        if t % check_every == 0 or t == steps - 1:
+            compare_state_and_outputs(env, orc.trace, where=f"step {t}")
+    compare_stats(env, orc, where="end")
+    st = env.episode_stats()
+    env.close()
+    return st
+
+
+def case_config_b_4096_envs_random_vs_bot_every_frame(make_env, oracle, scale=1.0):
+    """BASELINE.json configs[1]: 4096 envs, random P1 vs BattleAI, frame-skip 1, 2048 frames, all compared."""
+    rng = np.random.default_rng(1234)
+    n, steps = max(64, int(4096 * scale)), 2048
+    st = run_case(make_env, oracle, n, steps, tape1=tape_uniform(rng, steps, n))
+    assert st["episodes"] > 1000 * scale and st["hits"] > 0 and st["blocks"] > 0
+
+
+def case_self_play_sticky_inputs(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(7)
+    n, steps = max(64, int(2048 * scale)), 1500
+    st = run_case(make_env, oracle, n, steps, p2_bot=False,
+                  tape1=tape_sticky(rng, steps, n), tape2=tape_sticky(rng, steps, n, p_change=0.1))
+    assert st["episodes"] > 100 * scale and st["guard_breaks"] > 0 and st["p1_specials"] > 0 and st["double_ko"] >= 0
+
+
+def case_self_play_blockers_reach_guard_break_and_proximity(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(11)
+    n, steps = max(64, int(1024 * scale)), 1500
+    # P2 mostly holds back (Right = 2) -> blocks, proximity guard, guard breaks
+    st = run_case(make_env, oracle, n, steps, p2_bot=False,
+                  tape1=tape_sticky(rng, steps, n, weights=[1, 0.2, 3, 0.2, 2, 0.2, 3, 0.2]),
+                  tape2=tape_sticky(rng, steps, n, weights=[1, 0.5, 6, 0.2, 1, 0.2, 1, 0.1]))
+    assert st["guard_breaks"] > 10 * scale and st["blocks"] > 100 * scale
+
+
+def case_both_bots_by_example(make_env, oracle, scale=1.0):
+    st = run_case(make_env, oracle, max(64, int(1024 * scale)), 1500, p1_bot=True, p2_bot=True, seed=99)
+    assert st["episodes"] > 50 * scale
+
+
+def case_p1_bot_vs_remote_p2(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(5)
+    n, steps = max(64, int(512 * scale)), 1000
+    run_case(make_env, oracle, n, steps, p1_bot=True, p2_bot=False, tape2=tape_sticky(rng, steps, n), seed=3)
+
+
+def case_sparse_reward_and_global_index_offset(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(2)
+    n, steps = max(64, int(1024 * scale)), 1000
+    run_case(make_env, oracle, n, steps, dense=False, tape1=tape_sticky(rng, steps, n), first_env_index=123456, seed=-5)
+
+
+def case_autoreset_disabled_freezes_done_envs(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(3)
+    n, steps = max(64, int(512 * scale)), 1200
+    st = run_case(make_env, oracle, n, steps, autoreset=False, tape1=tape_uniform(rng, steps, n))
+    assert st["episodes"] <= n and st["episodes"] > n // 4
+
+
+def case_stale_intro_input_off(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(4)
+    n, steps = max(64, int(512 * scale)), 1000
+    run_case(make_env, oracle, n, steps, stale=False, p2_bot=False, tape1=tape_sticky(rng, steps, n),
+             tape2=tape_sticky(rng, steps, n))
+
+
+def case_fused_frame_skip(make_env, oracle, k, p2_bot, scale=1.0):
+    """configs[2]: self-play, K = 4 fused per launch (plus bot / odd K variants)."""
+    rng = np.random.default_rng(100 + k)
+    n, steps = max(64, int(4096 * scale)), 400
+    st = run_case(make_env, oracle, n, steps, p2_bot=p2_bot, frame_skip=k, tape1=tape_sticky(rng, steps, n, p_change=0.3),
+                  tape2=None if p2_bot else tape_sticky(rng, steps, n, p_change=0.3))
+    assert st["episodes"] > 100 * scale
+
+
+FUSED_PARAMS = [(4, False), (4, True), (3, True), (16, False)]

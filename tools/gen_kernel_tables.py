@@ -1,8 +1,9 @@
 """Expanded per-(action, frame) tables for the CUDA kernel (imported by gen_frame_data.py).
 
 The kernel never scans ranges: every lookup the reference does through ActionData.Get*Data
-(ActionData.cs:87-168) is resolved here, once, for every (action, frame) pair, into one 16-byte row
-plus a few tiny geometry tables.  All fp32 constants are computed with numpy.float32 so they carry
+(ActionData.cs:87-168) is resolved here, once, for every (action, frame) pair, into one 16-byte row of a
+dense [action][64 frames] table (so that the low 11 bits of the packed fighter word ARE the row index)
+plus a few tiny geometry tables whose byte offsets are pre-positioned inside the row words.  All fp32 constants are computed with numpy.float32 so they carry
 exactly the roundings the scalar code would produce at run time:
 
   row.dx   = fl(velocity_x * dt)           (Fighter.cs:300-316; the sign flip for P2 is exact)
@@ -16,7 +17,6 @@ f32 = np.float32
 
 # attackID -> attack "kind" 1..4 used by the kernel
 KIND_OF_ATTACK = {1: 1, 2: 2, 10: 3, 11: 4}
-DEAD_ROWS = 52  # DEAD (500 frames) is constant from frame 51 on
 
 
 def fbits(v):
@@ -34,11 +34,24 @@ def all_matches(items, frame):
     return [it for it in items if it["se"][0] <= frame <= it["se"][1]]
 
 
+ROW_FRAMES = 64        # rows per action; the 6-bit frame field of the packed fighter word indexes them directly
+
+# row.z bit layout
+Z_HAS_MOVEMENT, Z_PROX, Z_REAL, Z_CANCEL, Z_GUARDING = 1, 2, 4, 8, 16
+Z_BOXCFG_SHIFT = 5     # 4 bits: box configuration id, positioned so that (z & 0x1e0) == id * 32 (byte offset)
+Z_YMASK0_SHIFT = 16    # 8 bits: which hit boxes [(kind-1)*2 + real] overlap hurt box 0 in y
+Z_YMASK1_SHIFT = 24    # 8 bits: same for hurt box 1
+# row.w bit layout
+W_KIND_SHIFT = 5       # 3 bits: attack kind, positioned so that (w & 0xe0) == kind * 32 (byte offset)
+W_CARRY_END, W_CARRY_ALWAYS, W_CARRY_NORMAL = 1 << 28, 1 << 29, 1 << 30   # same bits as the packed fighter word
+
+
 def build(consts, attacks, actions):
     dt = f32(consts["fixedDeltaTime"])
     base_hurt = tuple(consts["baseHurtBoxRect"])
     base_push = tuple(consts["basePushBoxRect"])
     idx_of = {a["actionID"]: i for i, a in enumerate(actions)}
+    name_of = {a["actionID"]: a["actionName"] for a in actions}
 
     hurt_tab = [None]          # id 0 = none
     push_tab = []
@@ -66,78 +79,117 @@ def build(consts, attacks, actions):
             hit_tab[key] = h["rect"]
     assert sorted(hit_tab) == [(k, p) for k in (1, 2, 3, 4) for p in (0, 1)]
 
-    rows, action_info = [], []
-    for a in actions:
+    def ymask_of(hid):
+        """bit (kind-1)*2 + real set <=> hurt box `hid` overlaps that hit box in y (BoxBase.Overlaps c3 && c4)"""
+        if hid == 0:
+            return 0
+        hx, hy, hw, hh = (f32(v) for v in hurt_tab[hid])
+        m = 0
+        for k in (1, 2, 3, 4):
+            for p in (0, 1):
+                x, y, w, h = (f32(v) for v in hit_tab[(k, p)])
+                if (hy + hh) >= y and hy <= (y + h):
+                    m |= 1 << ((k - 1) * 2 + p)
+        return m
+
+    # pass 1: per (action, frame) raw facts
+    raw = {}
+    cfg_tab = []
+    action_info = []
+    for ai, a in enumerate(actions):
         aid = a["actionID"]
-        nrows = min(a["frameCount"], DEAD_ROWS) if aid == 500 else a["frameCount"]
         kinds = {KIND_OF_ATTACK[h["attackID"]] for h in a["hitboxes"]}
         assert len(kinds) <= 1
         kind = kinds.pop() if kinds else 0
-        base = len(rows)
-        for fr in range(nrows):
-            dx, vel, flags = f32(0), f32(0), 0
+        assert a["frameCount"] <= ROW_FRAMES - 1 or aid == 500, a["actionName"]
+        assert not a["isLoop"] or aid == 510
+        for fr in range(ROW_FRAMES):
+            src = min(fr, a["frameCount"] - 1)          # frames past the end repeat the last frame (never read)
+            dx, vel, z = f32(0), f32(0), 0
             if aid == 1:    # FORWARD: x += forwardMoveSpeed * sign * dt, velocity_x untouched (Fighter.cs:298-302)
                 dx = f32(consts["forwardMoveSpeed"]) * dt
             elif aid == 2:  # BACKWARD: x -= backwardMoveSpeed * sign * dt (Fighter.cs:303-307)
                 dx = -(f32(consts["backwardMoveSpeed"]) * dt)
             else:
-                m = first_match(a["movements"], fr)
+                m = first_match(a["movements"], src)
                 if m is not None:
                     vel = f32(m["velocity_x"])
                     dx = vel * dt if vel != 0 else f32(0)
-                    flags |= 1
-            hb = all_matches(a["hitboxes"], fr)
+                    z |= Z_HAS_MOVEMENT
+            hb = all_matches(a["hitboxes"], src)
             assert len([h for h in hb if h["proximity"]]) <= 1 and len([h for h in hb if not h["proximity"]]) <= 1
             if any(h["proximity"] for h in hb):
-                flags |= 2
+                z |= Z_PROX
             if any(not h["proximity"] for h in hb):
-                flags |= 4
-            for c in all_matches(a["cancels"], fr):
+                z |= Z_REAL
+            for c in all_matches(a["cancels"], src):
                 assert c["actionID"] == [110] and (c["buffer"] or c["execute"])
-                flags |= 8
-            hu = all_matches(a["hurtboxes"], fr)
+                z |= Z_CANCEL
+            # Fighter.NotifyDamaged blocks when the victim is in BACKWARD or any Type == Guard action (Fighter.cs:366-369)
+            if aid == 2 or a["type"] == 3:
+                z |= Z_GUARDING
+            hu = all_matches(a["hurtboxes"], src)
             assert len(hu) <= 2, "kernel keeps two hurtbox slots"
             ids = [hurt_id(base_hurt if h["useBaseRect"] else tuple(h["rect"])) for h in hu] + [0, 0]
-            flags |= ids[0] << 4 | ids[1] << 8
-            p = first_match(a["pushboxes"], fr)
-            assert p is not None, (a["actionName"], fr)
-            flags |= push_id(base_push if p["useBaseRect"] else tuple(p["rect"])) << 12
-            rows.append((fbits(dx), fbits(vel), flags, 0))
-        assert a["frameCount"] < 512 and base < 1024 and nrows - 1 < 64
-        info = (a["frameCount"] | a["alwaysCancelable"] << 9 | (1 if a["type"] == 3 else 0) << 10 | kind << 11
-                | base << 14 | (nrows - 1) << 24)
-        action_info.append(info)
-        assert not a["isLoop"] or aid == 510
-    assert len(hurt_tab) <= 16 and len(push_tab) <= 8
-
-    # y-overlap masks: bit j set <=> hurtbox id j overlaps this hitbox in y (BoxBase.Overlaps c3 && c4)
-    hit_rows = []
-    for k in (1, 2, 3, 4):
-        for p in (0, 1):
-            x, y, w, h = (f32(v) for v in hit_tab[(k, p)])
-            ymask = 0
-            for j in range(1, len(hurt_tab)):
-                hx, hy, hw, hh = (f32(v) for v in hurt_tab[j])
-                c3 = (hy + hh) >= y
-                c4 = hy <= (y + h)
-                if c3 and c4:
-                    ymask |= 1 << j
-            hit_rows.append((fbits(x), fbits(w / f32(2)), ymask, 0))
-    hurt_rows = [(0, 0)] + [(fbits(f32(r[0])), fbits(f32(r[2]) / f32(2))) for r in hurt_tab[1:]]
+            pb = first_match(a["pushboxes"], src)
+            assert pb is not None, (a["actionName"], fr)
+            cfg = (ids[0], ids[1], push_id(base_push if pb["useBaseRect"] else tuple(pb["rect"])))
+            if cfg not in cfg_tab:
+                cfg_tab.append(cfg)
+            raw[(ai, fr)] = (dx, vel, z, cfg, kind)
+        action_info.append(a["frameCount"] | a["alwaysCancelable"] << 9 | (1 if a["type"] == 3 else 0) << 10 | kind << 11)
+    assert len(cfg_tab) <= 16 and len(hurt_tab) <= 16 and len(push_tab) <= 8
     for r in hurt_tab[1:]:
         assert r[1] >= 0 and r[3] > 0
-    push_rows = [(fbits(f32(r[0])), fbits(f32(r[2]))) for r in push_tab]
     for r in push_tab:  # the Rect.Overlaps y test (BattleCore.cs:488) is then always true
         assert r[1] == 0 and r[3] > 0
 
-    atk_rows = [0]
+    # pass 2: rows
+    rows = []
+    for ai, a in enumerate(actions):
+        is_normal = name_of[a["actionID"]] in ("N_ATTACK", "B_ATTACK")
+        for fr in range(ROW_FRAMES):
+            dx, vel, z, cfg, kind = raw[(ai, fr)]
+            z |= cfg_tab.index(cfg) << Z_BOXCFG_SHIFT
+            z |= ymask_of(cfg[0]) << Z_YMASK0_SHIFT | ymask_of(cfg[1]) << Z_YMASK1_SHIFT
+            w = kind << W_KIND_SHIFT
+            # carry bits describe what the NEXT frame's request logic needs to know about this action:
+            #   END:    the action is over once the frame counter increments (frame + 1 >= frameCount, Fighter.cs:90)
+            #   ALWAYS: alwaysCancelable;   NORMAL: N_ATTACK / B_ATTACK (attack press cancels into N_SPECIAL, Fighter.cs:246-252)
+            if fr + 1 >= a["frameCount"]:
+                w |= W_CARRY_END
+            if a["alwaysCancelable"]:
+                w |= W_CARRY_ALWAYS
+            if is_normal:
+                w |= W_CARRY_NORMAL
+            rows.append((fbits(dx), fbits(vel), z, w))
+
+    # box configurations: {hurt0 centre, hurt0 width/2, hurt1 centre, hurt1 width/2, push centre, push width, 0, 0}
+    cfg_rows = []
+    for (h0, h1, pb) in cfg_tab:
+        def hb(hid):
+            if hid == 0:
+                return (0, 0)
+            r = hurt_tab[hid]
+            return (fbits(f32(r[0])), fbits(f32(r[2]) / f32(2)))
+        pr = push_tab[pb]
+        cfg_rows.append(hb(h0) + hb(h1) + (fbits(f32(pr[0])), fbits(f32(pr[2])), 0, 0))
+
+    # attacks [kind]: {prox centre, prox width/2, real centre, real width/2, prox y-bit pair, real y-bit pair, result word, 0}
     by_kind = {KIND_OF_ATTACK[t["attackID"]]: t for t in attacks}
+    atk_rows = [(0,) * 8]
     for k in (1, 2, 3, 4):
         t = by_kind[k]
         assert t["numberOfHit"] == 1 and t["guardHealthDamage"] == 1 and t["vitalHealthDamage"] in (0, 1)
         assert max(t["hitStunFrame"], t["guardStunFrame"], t["guardBreakStunFrame"]) < 32
-        atk_rows.append(idx_of[t["damageActionID"]] | idx_of[t["guardActionID"]] << 5 | t["vitalHealthDamage"] << 10
-                        | t["hitStunFrame"] << 11 | t["guardStunFrame"] << 16 | t["guardBreakStunFrame"] << 21)
+        result = (idx_of[t["damageActionID"]] | idx_of[t["guardActionID"]] << 5 | t["vitalHealthDamage"] << 10
+                  | t["hitStunFrame"] << 11 | t["guardStunFrame"] << 16 | t["guardBreakStunFrame"] << 21)
+        px, _, pw, _ = (f32(v) for v in hit_tab[(k, 0)])
+        rx, _, rw, _ = (f32(v) for v in hit_tab[(k, 1)])
+        pbit, rbit = 1 << ((k - 1) * 2), 1 << ((k - 1) * 2 + 1)
+        atk_rows.append((fbits(px), fbits(pw / f32(2)), fbits(rx), fbits(rw / f32(2)),
+                         pbit << Z_YMASK0_SHIFT | pbit << Z_YMASK1_SHIFT, rbit << Z_YMASK0_SHIFT | rbit << Z_YMASK1_SHIFT,
+                         result, 0))
 
     # dense-reward automaton (footsies.py:388-405): Python accumulates 0.3 steps in float64; the set of
     # reachable cumulative values is tiny, so the kernel carries an index and the doubles live in a table.
@@ -196,9 +248,9 @@ def build(consts, attacks, actions):
         if code & 2:
             r += 0.3
         step_reward.append(r)
-    return dict(rows=rows, action_info=action_info, hit_rows=hit_rows, hurt_rows=hurt_rows, push_rows=push_rows,
-                atk_rows=atk_rows, cum_vals=vals, cum_next=cum_next, term=term, step_reward=step_reward,
-                hurt_tab=hurt_tab, push_tab=push_tab)
+    return dict(rows=rows, action_info=action_info, cfg_rows=cfg_rows, cfg_tab=cfg_tab, atk_rows=atk_rows, cum_vals=vals,
+                cum_next=cum_next, term=term, step_reward=step_reward, hurt_tab=hurt_tab, push_tab=push_tab)
+
 
 
 def emit(consts, attacks, actions, path):
@@ -210,30 +262,36 @@ def emit(consts, attacks, actions, path):
     w("#ifndef FOOTSIES_B200_FRAME_TABLES_H")
     w("#define FOOTSIES_B200_FRAME_TABLES_H")
     w("#define FT_NUM_ACTIONS %d" % len(actions))
+    w("#define FT_ROW_FRAMES %d" % ROW_FRAMES)
     w("#define FT_NUM_ROWS %d" % len(t["rows"]))
-    w("#define FT_NUM_HURT %d" % len(t["hurt_rows"]))
-    w("#define FT_NUM_PUSH %d" % len(t["push_rows"]))
+    w("#define FT_NUM_BOXCFG %d" % len(t["cfg_rows"]))
     w("#define FT_NUM_CUM %d" % len(t["cum_vals"]))
     for i, a in enumerate(actions):
         w("#define FT_IDX_%s %d" % (a["actionName"], i))
+    w("/* row.z / row.w bit layout (tools/gen_kernel_tables.py) */")
+    for name in ("Z_HAS_MOVEMENT", "Z_PROX", "Z_REAL", "Z_CANCEL", "Z_GUARDING", "Z_BOXCFG_SHIFT", "Z_YMASK0_SHIFT",
+                 "Z_YMASK1_SHIFT", "W_KIND_SHIFT", "W_CARRY_END", "W_CARRY_ALWAYS", "W_CARRY_NORMAL"):
+        w("#define FT_%s 0x%xu" % (name, globals()[name]))
     w("/* action idx -> CommonActionID (Fighter.cs:42-61) in moves.py order */")
     w("#define FT_ACTION_IDS_INIT {%s}" % ", ".join(str(a["actionID"]) for a in actions))
-    w("/* per action: frameCount[0:9) | alwaysCancelable[9] | Type==Guard[10] | attack kind[11:14) | row base[14:24) | rows-1[24:30) */")
+    w("/* per action (host side only): frameCount[0:9) | alwaysCancelable[9] | Type==Guard[10] | attack kind[11:14) */")
     w("#define FT_ACTION_INFO_INIT {%s}" % ", ".join("0x%08xu" % v for v in t["action_info"]))
-    w("/* per (action, frame) row: {dx = fl(v*dt) bits, velocity_x bits, flags, 0};")
-    w(" * flags: has_movement[0] | prox hitbox[1] | real hitbox[2] | cancel->110 window[3] | hurt id0[4:8) | hurt id1[8:12) | push id[12:15) */")
+    w("/* rows[action * 64 + frame] = {dx = fl(v*dt) bits, velocity_x bits, z, w};")
+    w(" * z: has_movement[0] | prox hitbox[1] | real hitbox[2] | cancel->110 window[3] | blocks when hit[4] | box config id[5:9) |")
+    w(" *    y-overlap bits of hurt box 0 [16:24) and hurt box 1 [24:32) over hit boxes (kind-1)*2+real;")
+    w(" * w: attack kind[5:8) | carry END[28] ALWAYS[29] NORMAL[30] (copied into the packed fighter word) */")
     w("#define FT_ROWS_INIT { \\")
     for r in t["rows"]:
         w("  {0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}, \\" % r)
     w("}")
-    w("/* hit boxes [(kind-1)*2 + real]: {centre offset bits, width/2 bits, y-overlap mask over hurt ids, 0} */")
-    w("#define FT_HIT_INIT {%s}" % ", ".join("{0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}" % r for r in t["hit_rows"]))
-    w("/* hurt boxes [id]: {centre offset bits, width/2 bits}; id 0 = none.  %s */" % (t["hurt_tab"][1:],))
-    w("#define FT_HURT_INIT {%s}" % ", ".join("{0x%08xu, 0x%08xu}" % r for r in t["hurt_rows"]))
-    w("/* push boxes [id]: {centre offset bits, width bits}.  %s */" % (t["push_tab"],))
-    w("#define FT_PUSH_INIT {%s}" % ", ".join("{0x%08xu, 0x%08xu}" % r for r in t["push_rows"]))
-    w("/* attack [kind]: damageAction idx[0:5) | guardAction idx[5:10) | vitalDamage[10] | hitStun[11:16) | guardStun[16:21) | breakStun[21:26) */")
-    w("#define FT_ATTACK_INIT {%s}" % ", ".join("0x%08xu" % v for v in t["atk_rows"]))
+    w("/* box configurations [id]: {hurt0 centre, hurt0 width/2, hurt1 centre, hurt1 width/2, push centre, push width, 0, 0} (fp32 bits)")
+    w(" * (hurt0 id, hurt1 id, push id) = %s" % (t["cfg_tab"],))
+    w(" * hurt boxes %s" % (t["hurt_tab"][1:],))
+    w(" * push boxes %s */" % (t["push_tab"],))
+    w("#define FT_BOXCFG_INIT {%s}" % ", ".join("{%s}" % ", ".join("0x%08xu" % v for v in r) for r in t["cfg_rows"]))
+    w("/* attacks [kind]: {prox centre, prox width/2, real centre, real width/2, prox y-bits, real y-bits, result, 0};")
+    w(" * result: damageAction idx[0:5) | guardAction idx[5:10) | vitalDamage[10] | hitStun[11:16) | guardStun[16:21) | breakStun[21:26) */")
+    w("#define FT_ATTACK_INIT {%s}" % ", ".join("{%s}" % ", ".join("0x%08xu" % v for v in r) for r in t["atk_rows"]))
     w("/* dense reward automaton (footsies.py:388-405): cumulative float64 values, next index per guard-drop code, terminal reward */")
     w("#define FT_CUM_VALUES_INIT {%s}" % ", ".join(float(v).hex() for v in t["cum_vals"]))
     w("#define FT_CUM_NEXT_INIT {%s}" % ", ".join("{%s}" % ", ".join(map(str, r)) for r in t["cum_next"]))
@@ -244,3 +302,14 @@ def emit(consts, attacks, actions, path):
     w("#endif")
     with open(path, "w") as f:
         f.write("\n".join(o) + "\n")
+
+
+if __name__ == "__main__":
+    # regenerate from the committed Python literals (no reference tree needed)
+    import os
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, repo)
+    from footsies_gym_b200 import frame_data as fd
+    emit(fd.CONSTS, fd.ATTACKS, fd.ACTIONS, os.path.join(repo, "footsies_gym_b200", "csrc", "frame_tables.h"))
+    print("wrote footsies_gym_b200/csrc/frame_tables.h")
