@@ -82,13 +82,14 @@ def main():
         ent[3] += 1
         total += n
         listing.append((off, key, n, t, s, r[col["Source"]]))
-    src = open(os.path.join(ROOT, "footsies_gym_b200", "csrc", "footsies_kernels.cu")).read().splitlines()
+    csrc = os.path.join(ROOT, "footsies_gym_b200", "csrc")
+    srcs = {f: open(os.path.join(csrc, f)).read().splitlines() for f in os.listdir(csrc)}
     print(f"total warp-instructions executed: {total}")
     print(f"{'line':>16} {'winst':>11} {'%':>6} {'thr/inst':>8} {'samples':>8} {'#sass':>5}  source")
     for key, (n, t, s, k) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:a.top]:
         text = ""
-        if key and key[0] == "footsies_kernels.cu" and key[1] <= len(src):
-            text = src[key[1] - 1].strip()[:110]
+        if key and key[0] in srcs and key[1] <= len(srcs[key[0]]):
+            text = srcs[key[0]][key[1] - 1].strip()[:110]
         name = f"{key[0][:9]}:{key[1]}" if key else "?"
         print(f"{name:>16} {n:>11} {100.0 * n / total:>6.2f} {t / max(n, 1):>8.1f} {s:>8} {k:>5}  {text}")
     if a.sass:
