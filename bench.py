@@ -37,7 +37,7 @@ WORKLOAD = ("D-weak: random-action P1 vs in-game BattleAI, frame-skip 1, auto-re
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=DEFAULT_ENVS_PER_GPU)
@@ -48,6 +48,17 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     return ap.parse_args()
+
+
+def measured_traffic(bytes_per_env_alg, n):
+    """DRAM bytes per launch of the step kernel from the committed `ncu --set full` capture (profiles/traffic.json,
+    written by tools/ncu_summary.py from dram__bytes_read.sum + dram__bytes_write.sum), scaled to this launch's envs."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(path))
+        return float(t["dram_bytes_per_env_step"]) * n, t.get("source")
+    except Exception:  # noqa: BLE001
+        return None, None
 
 
 def measured_peaks():
@@ -326,6 +337,34 @@ def main():
         extra["1Mi_bot_k1"] = quick(1 << 20, 1, False)
         extra["1Mi_bot_k4"] = quick(1 << 20, 4, False, steps=100)
 
+        def ppo_rollout(n_envs=16384, horizon=128, reps=5):
+            """configs[4]: torch MLP policy (8-64-64-8) consuming env.obs in place, sampling Discrete(8) actions into
+            the tensor the step kernel is bound to; the whole horizon is one CUDA graph.  Policy time included."""
+            from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
+            e = FootsiesEnv(num_envs=n_envs, device=dev, opponent=None, seed=0)
+            pol = MLPPolicy().to(dev)
+            out = {}
+            for graph in (True, False):
+                col = RolloutCollector(e, pol, horizon=horizon, use_cuda_graph=graph)
+                col.collect()
+                torch.cuda.synchronize(dev)
+                f0 = e.episode_stats()["env_frames"]
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                for _ in range(reps):
+                    col.collect()
+                s1.record()
+                torch.cuda.synchronize(dev)
+                ms = s0.elapsed_time(s1)
+                fr = e.episode_stats()["env_frames"] - f0
+                out["cuda_graph" if graph else "eager"] = {"env_frames_per_sec": fr / (ms * 1e-3),
+                                                           "ms_per_horizon": ms / reps}
+            e.close()
+            out.update(envs=n_envs, horizon=horizon, policy="torch MLP 8-64-64-8 fp32, multinomial sampling",
+                       note="per GPU; policy forward + sampling + rollout-buffer writes inside the timed region")
+            return out
+        extra["E_ppo_rollout_16384x128"] = ppo_rollout()
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -341,6 +380,7 @@ def main():
         bytes_per_env = env.algorithmic_bytes_per_env_step
         ms_per_launch = ms_total / max(args.steps, 1)
         achieved = bytes_per_env * n / (ms_per_launch * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(bytes_per_env, n)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_launch, "higher_is_better": True,
@@ -352,7 +392,8 @@ def main():
                        "frames_counted": "kernel simulated-frame counter (FG_STAT_ENV_FRAMES)",
                        "burnin_steps": args.burnin},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": bytes_per_env * n,
                          "algorithmic_bytes_per_env_frame": bytes_per_env, "peak_source": peak_src,
                          "kernel": "step_kernel<K=1, P2 bot, dense>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -42,5 +42,31 @@ def main():
                 w.writerow([n, name, k, units[i], r[i]])
 
 
+def traffic(report, envs, out_path):
+    """profiles/traffic.json: DRAM bytes per env-step of the captured step-kernel launches (mean over launches)."""
+    import json
+    out = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = []
+    for r in rows[2:]:
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            b += float(r[i]) * scale[units[i]]
+        tot.append(b)
+    per_env = sum(tot) / len(tot) / envs
+    json.dump({"kernel": rows[2][hdr.index("Kernel Name")], "launches": len(tot), "envs_per_launch": envs,
+               "dram_bytes_per_env_step": per_env,
+               "source": f"ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, {os.path.basename(report)}"},
+              open(out_path, "w"), indent=1)
+    print(f"{per_env:.2f} B/env-step over {len(tot)} launches -> {out_path}", file=sys.stderr)
+
+
 if __name__ == "__main__":
-    main()
+    import os
+    if len(sys.argv) >= 5 and sys.argv[2] == "--traffic":
+        traffic(sys.argv[1], int(sys.argv[3]), sys.argv[4])
+    else:
+        main()
