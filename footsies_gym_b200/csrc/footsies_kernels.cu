@@ -19,8 +19,22 @@ namespace {
 
 using namespace fg;
 
-#ifndef FG_THREADS
-#define FG_THREADS 256
+// CTA shape of the step kernel.  A CTA is GROUPS independent pipeline groups of GROUP threads: each group walks its
+// own sequence of GROUP-env chunks with its own TMA stages and mbarriers; all groups share the one copy of the tables
+// in shared memory.  Two shapes are compiled (measured on B200, tools/probes/run_sizes.sh):
+//   ShapeSmall  256 threads = 1 group, 2 stages, 4 CTAs/SM: many small CTAs, best below ~0.75 Mi envs per launch
+//               (65 536 envs, K = 4: 10.1 us vs 15.2 us with the large shape)
+//   ShapeLarge  1024 threads = 4 groups x 256, 3 stages, 1 CTA/SM: one copy of the tables per SM and a deeper prefetch
+//               (4 Mi envs K = 1: -2 %, 1 Mi envs K = 4: -9 %)
+template <int THREADS_, int GROUP_, int STAGES_, int MIN_BLOCKS_>
+struct StepShape {
+    static constexpr int kThreads = THREADS_, kGroupThreads = GROUP_, kGroups = THREADS_ / GROUP_, kStages = STAGES_,
+                         kMinBlocks = MIN_BLOCKS_;
+    static_assert(THREADS_ % GROUP_ == 0 && GROUP_ % 32 == 0, "groups are whole warps");
+};
+#if defined(FG_THREADS)   // developer override: one shape for every batch size
+#ifndef FG_GROUP
+#define FG_GROUP FG_THREADS
 #endif
 #ifndef FG_STAGES
 #define FG_STAGES 2
@@ -28,8 +42,14 @@ using namespace fg;
 #ifndef FG_BLOCKS_PER_SM
 #define FG_BLOCKS_PER_SM 4
 #endif
-constexpr int kThreads = FG_THREADS;
-constexpr int kStages = FG_STAGES;
+using ShapeSmall = StepShape<FG_THREADS, FG_GROUP, FG_STAGES, FG_BLOCKS_PER_SM>;
+using ShapeLarge = ShapeSmall;
+#else
+using ShapeSmall = StepShape<256, 256, 2, 4>;
+using ShapeLarge = StepShape<1024, 256, 3, 1>;
+#endif
+constexpr int kLargeShapeMinEnvs = 768 * 1024;
+constexpr int kThreads = 256;                    // reset / seed kernels
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct Params {
@@ -130,40 +150,44 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int PLANES>
+template <class SH, int PLANES>
 struct __align__(128) StepSmem {
     Tables T;
-    uint4 stage[kStages][PLANES][kThreads];
-    uint64_t full_bar[kStages], empty_bar[kStages];
+    uint4 stage[SH::kGroups][SH::kStages][PLANES][SH::kGroupThreads];
+    uint64_t full_bar[SH::kGroups][SH::kStages], empty_bar[SH::kGroups][SH::kStages];
     unsigned long long stats[FG_STAT_COUNT];
 };
 
 // FootsiesEnv.step for every env: up to K fused fight frames, or the reset of a finished env (autoreset).
 // Persistent CTAs walk chunks of 256 consecutive envs; chunk c+grid is prefetched by one elected thread with
 // 3-4 bulk copies of 4 KB (one per state plane) while chunk c is simulated out of registers.
-template <bool KFUSED, bool P1BOT, bool P2BOT, bool DENSE, bool MASKED>
-__global__ void __launch_bounds__(kThreads, FG_BLOCKS_PER_SM) step_kernel(const Params p) {
+template <class SH, bool KFUSED, bool P1BOT, bool P2BOT, bool DENSE, bool MASKED>
+__global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(const Params p) {
     constexpr bool kRng = P1BOT || P2BOT;
     constexpr int kPlanes = kRng ? 4 : 3;
+    constexpr int kGroupThreads = SH::kGroupThreads, kGroups = SH::kGroups, kStages = SH::kStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem<kPlanes> &S = *reinterpret_cast<StepSmem<kPlanes> *>(smem_raw);
+    StepSmem<SH, kPlanes> &S = *reinterpret_cast<StepSmem<SH, kPlanes> *>(smem_raw);
     const Tables &T = S.T;
     const int lane = threadIdx.x & 31;
-    const int num_chunks = (p.n + kThreads - 1) / kThreads;
-    const int full_chunks = p.n / kThreads;                             // chunks that can be bulk-copied whole
+    const int g = threadIdx.x / kGroupThreads, lt = threadIdx.x % kGroupThreads;   // pipeline group, thread within it
+    const int num_chunks = (p.n + kGroupThreads - 1) / kGroupThreads;
+    const int full_chunks = p.n / kGroupThreads;                        // chunks that can be bulk-copied whole
+    const int first = blockIdx.x * kGroups + g, stride = gridDim.x * kGroups;       // this group's chunk sequence
     const uint4 *const planes[4] = { p.pl_f1, p.pl_f2, p.pl_env, p.pl_rng };
-    auto issue = [&](int chunk, int s) {                                // elected thread only
-        mbar_expect_tx(&S.full_bar[s], (uint32_t)(kPlanes * kThreads * sizeof(uint4)));
+    auto issue = [&](int chunk, int s) {                                // the group's elected thread only
+        mbar_expect_tx(&S.full_bar[g][s], (uint32_t)(kPlanes * kGroupThreads * sizeof(uint4)));
 #pragma unroll
         for (int k = 0; k < kPlanes; k++)
-            tma_load_1d(S.stage[s][k], planes[k] + (size_t)chunk * kThreads, (uint32_t)(kThreads * sizeof(uint4)), &S.full_bar[s]);
+            tma_load_1d(S.stage[g][s][k], planes[k] + (size_t)chunk * kGroupThreads, (uint32_t)(kGroupThreads * sizeof(uint4)),
+                        &S.full_bar[g][s]);
     };
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&S.full_bar[s], 1u); mbar_init(&S.empty_bar[s], kThreads / 32); }
+    if (lt == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&S.full_bar[g][s], 1u); mbar_init(&S.empty_bar[g][s], kGroupThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // prologue: chunks 0 .. kStages-2 of this CTA are in flight while the tables are being staged
+        // prologue: the group's first kStages-1 chunks are in flight while the tables are being staged
         for (int j = 0; j < kStages - 1; j++) {
-            const int cj = blockIdx.x + j * gridDim.x;
+            const int cj = first + j * stride;
             if (cj < full_chunks) issue(cj, j);
         }
     }
@@ -176,41 +200,41 @@ __global__ void __launch_bounds__(kThreads, FG_BLOCKS_PER_SM) step_kernel(const 
     // 256-byte bulk copy +3.5 %, register-less cp.async into per-thread slots +3 %, loading at the point of use +16 %.)
     uint32_t nin1 = 0u, nin2 = 0u;
     {
-        const int i0 = blockIdx.x * kThreads + threadIdx.x;
+        const int i0 = first * kGroupThreads + lt;
         if (i0 < p.n) { if (!P1BOT) nin1 = p.act1[i0]; if (!P2BOT) nin2 = p.act2[i0]; }
     }
     int k = 0;
-    for (int c = blockIdx.x; c < num_chunks; c += gridDim.x, k++) {
+    for (int c = first; c < num_chunks; c += stride, k++) {
         const int s = k % kStages;
-        const int i = c * kThreads + threadIdx.x;
+        const int i = c * kGroupThreads + lt;
         const bool staged = c < full_chunks;
         bool valid = staged || i < p.n;
         if (MASKED) valid = valid && p.step_mask[valid ? i : 0] != 0;
-        if (threadIdx.x == 0) {                                         // producer: chunk k + kStages - 1 -> the stage read at k - 1
-            const int cn = c + (kStages - 1) * gridDim.x;
+        if (lt == 0) {                                                  // producer: chunk k + kStages - 1 -> the stage read at k - 1
+            const int cn = c + (kStages - 1) * stride;
             if (cn < full_chunks) {
                 const int sn = (k + kStages - 1) % kStages;
-                if (k >= 1) mbar_wait(&S.empty_bar[sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
+                if (k >= 1) mbar_wait(&S.empty_bar[g][sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
                 issue(cn, sn);
             }
         }
         const uint32_t act1 = nin1, act2 = nin2;
         {
-            const int in = i + gridDim.x * kThreads;
+            const int in = i + stride * kGroupThreads;
             if (in < p.n) { if (!P1BOT) nin1 = p.act1[in]; if (!P2BOT) nin2 = p.act2[in]; }
         }
         Env e;
         bool run = false;
         uint32_t in1 = 0u, in2 = 0u;
         if (staged) {
-            mbar_wait(&S.full_bar[s], (k / kStages) & 1);
-            const uint4 a = S.stage[s][0][threadIdx.x], b = S.stage[s][1][threadIdx.x], cc = S.stage[s][2][threadIdx.x];
+            mbar_wait(&S.full_bar[g][s], (k / kStages) & 1);
+            const uint4 a = S.stage[g][s][0][lt], b = S.stage[g][s][1][lt], cc = S.stage[g][s][2][lt];
             e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
             e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
             e.frame = (int32_t)cc.x; e.misc = cc.y; e.bq2 = cc.z; e.bq1 = cc.w;
-            if (kRng) { const uint4 r = S.stage[s][kPlanes - 1][threadIdx.x]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
+            if (kRng) { const uint4 r = S.stage[g][s][kPlanes - 1][lt]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[s]);
+            if (lane == 0) mbar_arrive(&S.empty_bar[g][s]);
         } else if (valid) {
             load_env<kRng>(p, i, e);                                    // ragged tail chunk: plain loads
         }
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, FG_BLOCKS_PER_SM) step_kernel(const 
             store_env<kRng>(p, i, e);
             write_outputs(p, i, e, (float)reward, terminal);
         }
-        frames_since_flush += (uint32_t)K;                              // uniform across the CTA
+        frames_since_flush += (uint32_t)K;                              // uniform across the group
         if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, S.stats, lane); frames_since_flush = 0u; }
     }
     flush_stats(acc, S.stats, lane);
@@ -338,33 +362,40 @@ Params make_params(const fg_handle *h) {
 
 // The step kernel keeps its tables and the TMA stages in dynamic shared memory (> 48 KB): every instantiation is
 // opted in once per process.
-template <bool KF, bool B1, bool B2, bool D, bool M>
-cudaError_t launch_step(int grid, cudaStream_t s, const Params &p) {
+template <class SH, bool KF, bool B1, bool B2, bool D, bool M>
+cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
     constexpr int kPlanes = (B1 || B2) ? 4 : 3;
-    constexpr size_t bytes = sizeof(StepSmem<kPlanes>);
+    constexpr size_t bytes = sizeof(StepSmem<SH, kPlanes>);
     static bool configured[64] = {};                    // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<KF, B1, B2, D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(step_kernel<SH, KF, B1, B2, D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    step_kernel<KF, B1, B2, D, M><<<grid, kThreads, bytes, s>>>(p);
+    const int want = (p.n + SH::kThreads - 1) / SH::kThreads, cap = sm_count * SH::kMinBlocks;
+    const int grid = want < cap ? (want > 0 ? want : 1) : cap;
+    step_kernel<SH, KF, B1, B2, D, M><<<grid, SH::kThreads, bytes, s>>>(p);
     return cudaSuccess;
 }
+template <bool KF, bool B1, bool B2, bool D, bool M>
+cudaError_t launch_step(int sm_count, cudaStream_t s, const Params &p) {
+    return p.n >= kLargeShapeMinEnvs ? launch_step_shape<ShapeLarge, KF, B1, B2, D, M>(sm_count, s, p)
+                                     : launch_step_shape<ShapeSmall, KF, B1, B2, D, M>(sm_count, s, p);
+}
 template <bool KF, bool B1, bool B2>
-cudaError_t launch_step_d(bool dense, bool masked, int grid, cudaStream_t s, const Params &p) {
-    if (dense) return masked ? launch_step<KF, B1, B2, true, true>(grid, s, p) : launch_step<KF, B1, B2, true, false>(grid, s, p);
-    return masked ? launch_step<KF, B1, B2, false, true>(grid, s, p) : launch_step<KF, B1, B2, false, false>(grid, s, p);
+cudaError_t launch_step_d(bool dense, bool masked, int sm_count, cudaStream_t s, const Params &p) {
+    if (dense) return masked ? launch_step<KF, B1, B2, true, true>(sm_count, s, p) : launch_step<KF, B1, B2, true, false>(sm_count, s, p);
+    return masked ? launch_step<KF, B1, B2, false, true>(sm_count, s, p) : launch_step<KF, B1, B2, false, false>(sm_count, s, p);
 }
 template <bool KF>
-cudaError_t launch_step_k(const fg_config &c, int grid, cudaStream_t s, const Params &p) {
+cudaError_t launch_step_k(const fg_config &c, int sm_count, cudaStream_t s, const Params &p) {
     const bool d = c.dense_reward != 0, m = p.step_mask != nullptr;
-    if (c.p1_bot && c.p2_bot) return launch_step_d<KF, true, true>(d, m, grid, s, p);
-    if (c.p1_bot) return launch_step_d<KF, true, false>(d, m, grid, s, p);
-    if (c.p2_bot) return launch_step_d<KF, false, true>(d, m, grid, s, p);
-    return launch_step_d<KF, false, false>(d, m, grid, s, p);
+    if (c.p1_bot && c.p2_bot) return launch_step_d<KF, true, true>(d, m, sm_count, s, p);
+    if (c.p1_bot) return launch_step_d<KF, true, false>(d, m, sm_count, s, p);
+    if (c.p2_bot) return launch_step_d<KF, false, true>(d, m, sm_count, s, p);
+    return launch_step_d<KF, false, false>(d, m, sm_count, s, p);
 }
 
 template <bool B1, bool B2>
@@ -490,9 +521,8 @@ int32_t fg_step(fg_handle *h, void *stream) {
     if (int rc = check_bound(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     const Params p = make_params(h);
-    const int grid = grid_for(h, FG_BLOCKS_PER_SM);
-    CUDA_TRY(h->cfg.frame_skip == 1 ? launch_step_k<false>(h->cfg, grid, (cudaStream_t)stream, p)
-                                    : launch_step_k<true>(h->cfg, grid, (cudaStream_t)stream, p));
+    CUDA_TRY(h->cfg.frame_skip == 1 ? launch_step_k<false>(h->cfg, h->sm_count, (cudaStream_t)stream, p)
+                                    : launch_step_k<true>(h->cfg, h->sm_count, (cudaStream_t)stream, p));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FG_OK;
