@@ -97,7 +97,7 @@ static_assert(sizeof(BoxCfg) == 32 && sizeof(AttackRow) == 32 && sizeof(BotRow) 
 // reduction when a thread has gone kStatFlushFrames frames without a flush (and at kernel end).
 //   a: episodes | P1 wins | P2 wins | double KOs      (1 << 8*w trick: w = winner code)
 //   r: (none)   | hits    | blocks  | guard breaks    (1 << 8*DamageResult for each of the two attack passes)
-//   s: specials | specials-from-neutral | resets | (unused)
+//   s: specials | specials-from-neutral | resets | env-frames simulated (bumped by the step loop)
 //   ep_frames: sum of the lengths of the episodes that ended (plain 32-bit sum)
 struct StatAcc { uint32_t a, r, s, ep_frames; };
 constexpr uint32_t kStatFlushFrames = 120u;   // <= 2 events per lane per frame -> a byte lane cannot overflow
@@ -182,10 +182,13 @@ FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel,
     //      effect a request can have is buffering N_SPECIAL inside a cancel window. ----
     bool want_buffer = false, set, differs = true;
     uint32_t req;
-    if ((pk & (M_RSV | M_STUN)) == M_RSV) {                             // reserved GUARD_BREAK (Fighter.cs:212-218)
-        req = GUARD_BREAK; set = true;
-    } else if ((pk & (M_BUF | M_HIT | M_STUN)) == (M_BUF | M_HIT)) {    // buffered cancel (Fighter.cs:222-229)
-        req = N_SPECIAL; set = true;
+    // Forced requests, both only once hit stun is over: the reserved GUARD_BREAK (Fighter.cs:212-218), else the
+    // buffered cancel into N_SPECIAL after a connected hit (Fighter.cs:222-229).  STUN sits below RSV / BUF in the
+    // word, so "no stun and one of them set" is one range check on the masked word.
+    const uint32_t forced = pk & (M_RSV | M_BUF | M_STUN);
+    static_assert(FGP_STUN_SHIFT < FGP_BUF_SHIFT && FGP_BUF_SHIFT < FGP_RSV_SHIFT, "range check below");
+    if (forced >= M_BUF && !(forced & M_STUN) && ((forced & M_RSV) || (pk & M_HIT))) {
+        req = (forced & M_RSV) ? (uint32_t)GUARD_BREAK : (uint32_t)N_SPECIAL; set = true;
     } else {
         const uint32_t dir = in_lr != 0u ? 1u : 0u;
         const bool in_normal = normal && !ended;
@@ -201,8 +204,10 @@ FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel,
         want_buffer = !free_to_switch && req == N_SPECIAL;
         pk = (pk & ~(M_INBACK | M_RPROX)) | (back ? M_INBACK : 0u);     // isInputBackward = back; reserve flag consumed
     }
-    fo.special_started = set && differs && (req - N_SPECIAL) < 2u;
-    fo.from_neutral = !normal;
+    if (SIDE == 0) {                                                    // statistics are about P1 only
+        fo.special_started = set && differs && (req - N_SPECIAL) < 2u;
+        fo.from_neutral = !normal;
+    }
     if (set) pk = (pk & (M_STUN | M_GUARD | M_VITAL | M_INBACK | M_RPROX)) + (req << FGP_ACT_SHIFT);   // SetCurrentAction (Fighter.cs:546-563)
 
     // ---- frame data of the (action, frame) the fighter ends up in: the low bits of the packed word are the row index ----
@@ -270,7 +275,7 @@ FG_DEV void attack_overlaps(const AttackRow &ar, const BoxCfg &vb, const FrameOu
 // Returns the DamageResult (0 none, 1 damage, 2 guard, 3 guard break) | 4 when the victim's guard bar dropped.
 template <int ASIDE>
 FG_DEV uint32_t attack_apply(uint32_t result, uint32_t &apk, uint32_t &vpk, const FrameOut &af, const FrameOut &vf,
-                             bool real_hit, bool prox_hit) {
+                             bool real_hit, bool prox_hit, StatAcc &acc) {
     const bool can = (af.z & (FT_Z_PROX | FT_Z_REAL)) && !(apk & M_HIT);   // a hitbox is out and CanAttackHit
     if (can && real_hit) {
         const bool brk = (vpk & M_GUARD) == 0u;                         // guardHealth < 0 after the decrement
@@ -283,11 +288,13 @@ FG_DEV uint32_t attack_apply(uint32_t result, uint32_t &apk, uint32_t &vpk, cons
             stun = brk ? (result >> 21) & 31u : (result >> 16) & 31u;
             if (brk) keep |= M_RSV;
             res = brk ? 3u : 6u;                                        // 2 | guard dropped
+            acc.r += brk ? (1u << 24) : (1u << 16);                     // byte lane = DamageResult: 3 guard break, 2 guard
         } else {
             if (result & (1u << 10)) keep &= ~M_VITAL;
             nact = result & 31u;
             stun = (result >> 11) & 31u;
             res = brk ? 1u : 5u;
+            acc.r += 1u << 8;                                           // 1 damage
         }
         // SetSpriteShakeFrame: min(stun / 3, 6), the victim of P1 faces left -> positive, of P2 -> negative
         const uint32_t mag = umin(stun / 3u, 6u);
@@ -460,11 +467,10 @@ FG_DEV void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, 
         bool real_a, prox_a, real_b, prox_b;
         attack_overlaps<0>(ar1, b2, f1, f2, s1, t1, s2, t2, real_a, prox_a);
         attack_overlaps<1>(ar2, b1, f2, f1, s2, t2, s1, t1, real_b, prox_b);
-        res_a = attack_apply<0>(ar1.result, e.pk1, e.pk2, f1, f2, real_a, prox_a);   // result on P2
-        res_b = attack_apply<1>(ar2.result, e.pk2, e.pk1, f2, f1, real_b, prox_b);   // result on P1
+        res_a = attack_apply<0>(ar1.result, e.pk1, e.pk2, f1, f2, real_a, prox_a, acc);   // result on P2
+        res_b = attack_apply<1>(ar2.result, e.pk2, e.pk1, f2, f1, real_b, prox_b, acc);   // result on P1
     }
 
-    acc.r += (1u << (8u * (res_a & 3u))) + (1u << (8u * (res_b & 3u)));  // byte lane = DamageResult of each pass
     // P1 started a special move and still is in it after the collision phase (wrappers/statistics.py:36-46)
     if (f1.special_started && res_b == 0u) acc.s += f1.from_neutral ? 0x101u : 1u;
 

@@ -51,7 +51,7 @@ static void write_outputs(he_handle *h, int i, const Env &e, float reward, bool 
 static void flush(he_handle *h, StatAcc &acc) {
     static const int map[3][4] = { { FG_STAT_EPISODES, FG_STAT_P1_WINS, FG_STAT_P2_WINS, FG_STAT_DOUBLE_KO },
                                    { -1, FG_STAT_HITS, FG_STAT_BLOCKS, FG_STAT_GUARD_BREAKS },
-                                   { FG_STAT_P1_SPECIALS, FG_STAT_P1_SPECIALS_NEUTRAL, FG_STAT_RESETS, -1 } };
+                                   { FG_STAT_P1_SPECIALS, FG_STAT_P1_SPECIALS_NEUTRAL, FG_STAT_RESETS, FG_STAT_ENV_FRAMES } };
     const uint32_t w[3] = { acc.a, acc.r, acc.s };
     for (int k = 0; k < 3; k++)
         for (int b = 0; b < 4; b++)
@@ -101,7 +101,7 @@ static void step_t(he_handle *h, const uint8_t *a1, const uint8_t *a2, const uin
         for (int kk = 0; kk < h->frame_skip; kk++) {
             if (run && !terminal) {
                 simulate_frame<B1, B2, DENSE>(h->T, e, in1, in2, reward, terminal, acc);
-                h->stats[FG_STAT_ENV_FRAMES]++;
+                acc.s += 1u << 24;
                 if (B1) in1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u;
                 if (B2) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
             }

@@ -94,7 +94,8 @@ def main():
         print(f"{name:>16} {n:>11} {100.0 * n / total:>6.2f} {t / max(n, 1):>8.1f} {s:>8} {k:>5}  {text}")
     if a.sass:
         for off, key, n, t, s, text in listing:
-            print(f"{off:06x} {str(key[1]) if key else '?':>5} {n:>9} {t / max(n, 1):>5.1f} {s:>5}  {text}")
+            where = f"{key[0][:6]}:{key[1]}" if key else "?"
+            print(f"{off:06x} {where:>11} {n:>9} {t / max(n, 1):>5.1f} {s:>5}  {text}")
 
 
 if __name__ == "__main__":
