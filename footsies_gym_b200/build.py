@@ -1,10 +1,15 @@
-"""Compile the sm_100a CUDA library in-tree (nvcc cross-compiles without a GPU)."""
+"""Compile the sm_100a CUDA library in-tree (nvcc cross-compiles without a GPU).
+
+The 64 step-kernel variants are spread over eight translation units (csrc/step_instances.cu compiled once per
+(KFUSED, P1BOT, P2BOT)) next to the C-ABI unit, all compiled in parallel and linked into libfootsies_b200.so."""
+import concurrent.futures
 import os
 import shutil
 import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
+OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_NAME = "libfootsies_b200.so"
 LIB_PATH = os.environ.get("FOOTSIES_B200_LIB") or os.path.join(PKG_DIR, LIB_NAME)   # override: developer experiments only
 
@@ -12,7 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",            # fp32 ops round one by one, like the scalar C# expressions they restate
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -24,33 +29,64 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, "footsies_kernels.cu")]
+    return [os.path.join(CSRC, "footsies_kernels.cu"), os.path.join(CSRC, "step_instances.cu")]
 
 
 def deps():
     inc = os.path.join(os.path.dirname(PKG_DIR), "include", "footsies_b200.h")
-    return sources() + [os.path.join(CSRC, f) for f in ("state_codec.h", "frame_tables.h", "frame_logic.cuh", "tables_host.h")] + [inc]
+    return sources() + [os.path.join(CSRC, f) for f in ("state_codec.h", "frame_tables.h", "frame_logic.cuh",
+                                                        "tables_host.h", "step_kernel.cuh")] + [inc]
 
 
-def is_stale():
-    if not os.path.exists(LIB_PATH):
+def is_stale(lib_path=None):
+    lib_path = lib_path or LIB_PATH
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(lib_path)
     return any(os.path.getmtime(d) > t for d in deps() if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+def translation_units():
+    """(object name, source, extra defines)"""
+    units = [("abi.o", os.path.join(CSRC, "footsies_kernels.cu"), [])]
+    for kf in (0, 1):
+        for b1 in (0, 1):
+            for b2 in (0, 1):
+                units.append((f"step_k{kf}_b{b1}{b2}.o", os.path.join(CSRC, "step_instances.cu"),
+                              [f"-DFG_INST_KF={kf}", f"-DFG_INST_B1={b1}", f"-DFG_INST_B2={b2}"]))
+    return units
+
+
+def build(force=False, verbose=False, extra_flags=(), lib_path=None):
     """Build libfootsies_b200.so next to this file; returns its path."""
-    if not force and not is_stale():
-        return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    lib_path = lib_path or LIB_PATH
+    if not force and not is_stale(lib_path):
+        return lib_path
+    nvcc = _nvcc()
+    obj_dir = OBJ_DIR if lib_path == LIB_PATH else lib_path + ".obj"
+    os.makedirs(obj_dir, exist_ok=True)
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(unit):
+        name, src, defs = unit
+        out = os.path.join(obj_dir, name)
+        res = subprocess.run([nvcc] + flags + defs + ["-c", src, "-o", out], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {name}:\n" + res.stdout + res.stderr)
+        return out, res.stderr
+
+    units = translation_units()
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 2)) as pool:
+        results = list(pool.map(compile_one, units))
     if verbose:
-        print(res.stderr)
-    return LIB_PATH
+        for _, log in results:
+            print(log)
+    res = subprocess.run([nvcc, "-shared", "-o", lib_path] + [o for o, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))

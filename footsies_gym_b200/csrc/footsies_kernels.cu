@@ -1,318 +1,12 @@
-// footsies_kernels.cu -- sm_100a kernels + C ABI of the batched FOOTSIES simulator.
-//
-// One CUDA thread owns one battle.  The whole reference frame update (csrc/frame_logic.cuh) runs in registers
-// between one 64-byte state load and one 64-byte state store per env (four 16-byte SoA planes, fully coalesced
-// 128-bit accesses).  Frame data is pre-expanded per (action, frame) (frame_tables.h) and staged once per CTA into
-// shared memory; CTAs are persistent (grid-stride over chunks of 256 envs) and the state planes of the next chunk
-// stream into shared memory with TMA bulk copies while the current chunk is simulated.
-// No tensor cores: nothing here is a contraction.  Bounds: the ALU pipe first, then HBM bandwidth (K = 1).
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-#include <new>
-#include <vector>
+// footsies_kernels.cu -- C ABI of the batched FOOTSIES simulator (include/footsies_b200.h) on top of the kernels in
+// step_kernel.cuh.
+#include "step_kernel.cuh"
 
-#include "tables_host.h"
+using namespace fg;
+using namespace fgk;
 
 namespace {
 
-using namespace fg;
-
-// CTA shape of the step kernel.  A CTA is GROUPS independent pipeline groups of GROUP threads: each group walks its
-// own sequence of GROUP-env chunks with its own TMA stages and mbarriers; all groups share the one copy of the tables
-// in shared memory.  Two shapes are compiled (measured on B200, tools/probes/run_sizes.sh):
-//   ShapeSmall  256 threads = 1 group, 2 stages, 4 CTAs/SM: many small CTAs, best below ~0.75 Mi envs per launch
-//               (65 536 envs, K = 4: 10.1 us vs 15.2 us with the large shape)
-//   ShapeLarge  1024 threads = 4 groups x 256, 3 stages, 1 CTA/SM: one copy of the tables per SM and a deeper prefetch
-//               (4 Mi envs K = 1: -2 %, 1 Mi envs K = 4: -9 %)
-template <int THREADS_, int GROUP_, int STAGES_, int MIN_BLOCKS_>
-struct StepShape {
-    static constexpr int kThreads = THREADS_, kGroupThreads = GROUP_, kGroups = THREADS_ / GROUP_, kStages = STAGES_,
-                         kMinBlocks = MIN_BLOCKS_;
-    static_assert(THREADS_ % GROUP_ == 0 && GROUP_ % 32 == 0, "groups are whole warps");
-};
-#if defined(FG_THREADS)   // developer override: one shape for every batch size
-#ifndef FG_GROUP
-#define FG_GROUP FG_THREADS
-#endif
-#ifndef FG_STAGES
-#define FG_STAGES 2
-#endif
-#ifndef FG_BLOCKS_PER_SM
-#define FG_BLOCKS_PER_SM 4
-#endif
-using ShapeSmall = StepShape<FG_THREADS, FG_GROUP, FG_STAGES, FG_BLOCKS_PER_SM>;
-using ShapeLarge = ShapeSmall;
-#else
-using ShapeSmall = StepShape<256, 256, 2, 4>;
-using ShapeLarge = StepShape<1024, 256, 3, 1>;
-#endif
-constexpr int kLargeShapeMinEnvs = 768 * 1024;
-constexpr int kThreads = 256;                    // reset / seed kernels
-constexpr uint32_t kFull = 0xffffffffu;
-
-struct Params {
-    uint4 *pl_f1, *pl_f2, *pl_env, *pl_rng;
-    unsigned long long *stats;
-    const uint8_t *act1, *act2;
-    float4 *obs;
-    float *reward;
-    uint8_t *terminated;
-    int32_t *info_frame;
-    uint32_t *info_misc;
-    const Tables *tables;
-    const uint8_t *mask;   // reset / seed kernels
-    const uint8_t *step_mask;
-    long long seed_base, first_env_index;
-    int n, frame_skip, autoreset, stale_intro;
-};
-
-__device__ __forceinline__ void write_outputs(const Params &p, int i, const Env &e, float reward, bool terminated) {
-    StepOutputs o;
-    make_outputs(e, o);
-    p.obs[2 * (size_t)i] = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]);
-    p.obs[2 * (size_t)i + 1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
-    p.reward[i] = reward;
-    p.terminated[i] = terminated ? 1 : 0;
-    p.info_frame[i] = e.frame;
-    p.info_misc[i] = o.info_misc;
-}
-
-__device__ __forceinline__ void load_tables(Tables *dst, const Tables *src) {
-    const uint4 *s = reinterpret_cast<const uint4 *>(src);
-    uint4 *d = reinterpret_cast<uint4 *>(dst);
-    for (int k = threadIdx.x; k < (int)(sizeof(Tables) / 16); k += blockDim.x) d[k] = s[k];
-}
-
-template <bool WITH_RNG>
-__device__ __forceinline__ void load_env(const Params &p, int i, Env &e) {
-    const uint4 a = p.pl_f1[i], b = p.pl_f2[i], c = p.pl_env[i];
-    e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
-    e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
-    e.frame = (int32_t)c.x; e.misc = c.y; e.bq2 = c.z; e.bq1 = c.w;
-    if (WITH_RNG) { const uint4 r = p.pl_rng[i]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
-}
-template <bool WITH_RNG>
-__device__ __forceinline__ void store_env(const Params &p, int i, const Env &e) {
-    p.pl_f1[i] = make_uint4(f2u(e.pos1), f2u(e.vel1), e.pk1, e.hist1);
-    p.pl_f2[i] = make_uint4(f2u(e.pos2), f2u(e.vel2), e.pk2, e.hist2);
-    p.pl_env[i] = make_uint4((uint32_t)e.frame, e.misc, e.bq2, e.bq1);
-    if (WITH_RNG) p.pl_rng[i] = make_uint4(e.r0, e.r1, e.r2, e.r3);
-}
-
-// Warp-cooperative fold of the packed per-thread counters into the CTA's shared-memory vector.
-__device__ __forceinline__ void flush_stats(StatAcc &acc, unsigned long long *s_stats, int lane) {
-    const uint32_t w[3] = { acc.a, acc.r, acc.s };
-    // (word, byte lane) -> statistic index; -1 = unused
-    const int map[3][4] = { { FG_STAT_EPISODES, FG_STAT_P1_WINS, FG_STAT_P2_WINS, FG_STAT_DOUBLE_KO },
-                            { -1, FG_STAT_HITS, FG_STAT_BLOCKS, FG_STAT_GUARD_BREAKS },
-                                            { FG_STAT_P1_SPECIALS, FG_STAT_P1_SPECIALS_NEUTRAL, FG_STAT_RESETS, FG_STAT_ENV_FRAMES } };
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) {
-            if (map[k][b] < 0) continue;
-            const uint32_t tot = __reduce_add_sync(kFull, (w[k] >> (8 * b)) & 255u);
-            if (lane == 0 && tot) atomicAdd(&s_stats[map[k][b]], (unsigned long long)tot);
-        }
-    // episode lengths: two 16-bit halves so that the 32-lane sums cannot overflow
-    const uint32_t lo = __reduce_add_sync(kFull, acc.ep_frames & 0xffffu), hi = __reduce_add_sync(kFull, acc.ep_frames >> 16);
-    if (lane == 0 && (lo | hi)) atomicAdd(&s_stats[FG_STAT_EPISODE_FRAMES], ((unsigned long long)hi << 16) + lo);
-    acc.a = 0u; acc.r = 0u; acc.s = 0u; acc.ep_frames = 0u;
-}
-
-// ---- TMA (1-D bulk async copy) + mbarrier helpers: the state planes of the NEXT chunk of 256 envs stream into
-//      shared memory while the current chunk is being simulated ----
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <class SH, int PLANES>
-struct __align__(128) StepSmem {
-    Tables T;
-    uint4 stage[SH::kGroups][SH::kStages][PLANES][SH::kGroupThreads];
-    uint64_t full_bar[SH::kGroups][SH::kStages], empty_bar[SH::kGroups][SH::kStages];
-    unsigned long long stats[FG_STAT_COUNT];
-};
-
-// FootsiesEnv.step for every env: up to K fused fight frames, or the reset of a finished env (autoreset).
-// Persistent CTAs walk chunks of 256 consecutive envs; chunk c+grid is prefetched by one elected thread with
-// 3-4 bulk copies of 4 KB (one per state plane) while chunk c is simulated out of registers.
-template <class SH, bool KFUSED, bool P1BOT, bool P2BOT, bool DENSE, bool MASKED>
-__global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(const Params p) {
-    constexpr bool kRng = P1BOT || P2BOT;
-    constexpr int kPlanes = kRng ? 4 : 3;
-    constexpr int kGroupThreads = SH::kGroupThreads, kGroups = SH::kGroups, kStages = SH::kStages;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem<SH, kPlanes> &S = *reinterpret_cast<StepSmem<SH, kPlanes> *>(smem_raw);
-    const Tables &T = S.T;
-    const int lane = threadIdx.x & 31;
-    const int g = threadIdx.x / kGroupThreads, lt = threadIdx.x % kGroupThreads;   // pipeline group, thread within it
-    const int num_chunks = (p.n + kGroupThreads - 1) / kGroupThreads;
-    const int full_chunks = p.n / kGroupThreads;                        // chunks that can be bulk-copied whole
-    const int first = blockIdx.x * kGroups + g, stride = gridDim.x * kGroups;       // this group's chunk sequence
-    const uint4 *const planes[4] = { p.pl_f1, p.pl_f2, p.pl_env, p.pl_rng };
-    auto issue = [&](int chunk, int s) {                                // the group's elected thread only
-        mbar_expect_tx(&S.full_bar[g][s], (uint32_t)(kPlanes * kGroupThreads * sizeof(uint4)));
-#pragma unroll
-        for (int k = 0; k < kPlanes; k++)
-            tma_load_1d(S.stage[g][s][k], planes[k] + (size_t)chunk * kGroupThreads, (uint32_t)(kGroupThreads * sizeof(uint4)),
-                        &S.full_bar[g][s]);
-    };
-    if (lt == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&S.full_bar[g][s], 1u); mbar_init(&S.empty_bar[g][s], kGroupThreads / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // prologue: the group's first kStages-1 chunks are in flight while the tables are being staged
-        for (int j = 0; j < kStages - 1; j++) {
-            const int cj = first + j * stride;
-            if (cj < full_chunks) issue(cj, j);
-        }
-    }
-    load_tables(&S.T, p.tables);
-    if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
-    __syncthreads();
-    StatAcc acc = { 0u, 0u, 0u, 0u };
-    uint32_t frames_since_flush = 0u;
-    // Actions are prefetched one chunk ahead.  (Measured alternatives, 4 Mi envs: riding the TMA barrier as a fifth
-    // 256-byte bulk copy +3.5 %, register-less cp.async into per-thread slots +3 %, loading at the point of use +16 %.)
-    uint32_t nin1 = 0u, nin2 = 0u;
-    {
-        const int i0 = first * kGroupThreads + lt;
-        if (i0 < p.n) { if (!P1BOT) nin1 = p.act1[i0]; if (!P2BOT) nin2 = p.act2[i0]; }
-    }
-    int k = 0;
-    for (int c = first; c < num_chunks; c += stride, k++) {
-        const int s = k % kStages;
-        const int i = c * kGroupThreads + lt;
-        const bool staged = c < full_chunks;
-        bool valid = staged || i < p.n;
-        if (MASKED) valid = valid && p.step_mask[valid ? i : 0] != 0;
-        if (lt == 0) {                                                  // producer: chunk k + kStages - 1 -> the stage read at k - 1
-            const int cn = c + (kStages - 1) * stride;
-            if (cn < full_chunks) {
-                const int sn = (k + kStages - 1) % kStages;
-                if (k >= 1) mbar_wait(&S.empty_bar[g][sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
-                issue(cn, sn);
-            }
-        }
-        const uint32_t act1 = nin1, act2 = nin2;
-        {
-            const int in = i + stride * kGroupThreads;
-            if (in < p.n) { if (!P1BOT) nin1 = p.act1[in]; if (!P2BOT) nin2 = p.act2[in]; }
-        }
-        Env e;
-        bool run = false;
-        uint32_t in1 = 0u, in2 = 0u;
-        if (staged) {
-            mbar_wait(&S.full_bar[g][s], (k / kStages) & 1);
-            const uint4 a = S.stage[g][s][0][lt], b = S.stage[g][s][1][lt], cc = S.stage[g][s][2][lt];
-            e.pos1 = u2f(a.x); e.vel1 = u2f(a.y); e.pk1 = a.z; e.hist1 = a.w;
-            e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
-            e.frame = (int32_t)cc.x; e.misc = cc.y; e.bq2 = cc.z; e.bq1 = cc.w;
-            if (kRng) { const uint4 r = S.stage[g][s][kPlanes - 1][lt]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.empty_bar[g][s]);
-        } else if (valid) {
-            load_env<kRng>(p, i, e);                                    // ragged tail chunk: plain loads
-        }
-        if (valid) {
-            if ((e.misc >> FGM_DONE_SHIFT) & 1u) {
-                if (p.autoreset) {                                      // next-step autoreset: this call only resets
-                    reset_env<P1BOT, P2BOT>(T, e, p.stale_intro != 0);
-                    store_env<kRng>(p, i, e);
-                    write_outputs(p, i, e, 0.0f, false);
-                    acc.s += 0x10000u;
-                } else {
-                    p.reward[i] = 0.0f;                                 // frozen until fg_reset
-                }
-            } else {
-                run = true;
-                in1 = P1BOT ? (e.misc >> FGM_ACTOR1_SHIFT) & 7u : act1 & 7u;
-                in2 = P2BOT ? (e.misc >> FGM_ACTOR2_SHIFT) & 7u : act2 & 7u;
-            }
-        }
-        double reward = 0.0;
-        bool terminal = false;
-        const int K = KFUSED ? p.frame_skip : 1;
-        for (int kk = 0; kk < K; kk++) {
-            if (run && !terminal) {
-                simulate_frame<P1BOT, P2BOT, DENSE>(T, e, in1, in2, reward, terminal, acc);
-                acc.s += 1u << 24;                                      // byte lane 3: env-frames simulated (<= 120 per flush)
-                if (KFUSED) {
-                    if (P1BOT) in1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u;
-                    if (P2BOT) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
-                }
-            }
-        }
-        if (run) {
-            store_env<kRng>(p, i, e);
-            write_outputs(p, i, e, (float)reward, terminal);
-        }
-        frames_since_flush += (uint32_t)K;                              // uniform across the group
-        if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, S.stats, lane); frames_since_flush = 0u; }
-    }
-    flush_stats(acc, S.stats, lane);
-    __syncthreads();
-    if (threadIdx.x < FG_STAT_COUNT && S.stats[threadIdx.x]) atomicAdd(&p.stats[threadIdx.x], S.stats[threadIdx.x]);
-}
-
-// FootsiesEnv.reset / RESET command for the envs selected by mask (NULL = all).
-template <bool P1BOT, bool P2BOT>
-__global__ void __launch_bounds__(kThreads) reset_kernel(const Params p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Tables &T = *reinterpret_cast<Tables *>(smem_raw);
-    load_tables(&T, p.tables);
-    __syncthreads();
-    constexpr bool kRng = P1BOT || P2BOT;
-    unsigned long long resets = 0ull;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
-        if (p.mask && !p.mask[i]) continue;
-        Env e;
-        load_env<kRng>(p, i, e);
-        reset_env<P1BOT, P2BOT>(T, e, p.stale_intro != 0);
-        store_env<kRng>(p, i, e);
-        write_outputs(p, i, e, 0.0f, false);
-        resets++;
-    }
-    if (resets) atomicAdd(&p.stats[FG_STAT_RESETS], resets);
-}
-
-// Random.InitState(seed_base + global env index) (BattleCore.cs:170-173)
-__global__ void __launch_bounds__(kThreads) seed_kernel(const Params p) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
-        if (p.mask && !p.mask[i]) continue;
-        uint32_t s0 = (uint32_t)(int32_t)(p.seed_base + p.first_env_index + i);
-        uint32_t s1 = s0 * 1812433253u + 1u, s2 = s1 * 1812433253u + 1u, s3 = s2 * 1812433253u + 1u;
-        p.pl_rng[i] = make_uint4(s0, s1, s2, s3);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
 int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof g_err, fmt, detail);
@@ -358,35 +52,6 @@ Params make_params(const fg_handle *h) {
     return p;
 }
 
-// The step kernel keeps its tables and the TMA stages in dynamic shared memory (> 48 KB): every instantiation is
-// opted in once per process.
-template <class SH, bool KF, bool B1, bool B2, bool D, bool M>
-cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
-    constexpr int kPlanes = (B1 || B2) ? 4 : 3;
-    constexpr size_t bytes = sizeof(StepSmem<SH, kPlanes>);
-    static bool configured[64] = {};                    // per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<SH, KF, B1, B2, D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = true;
-    }
-    const int want = (p.n + SH::kThreads - 1) / SH::kThreads, cap = sm_count * SH::kMinBlocks;
-    const int grid = want < cap ? (want > 0 ? want : 1) : cap;
-    step_kernel<SH, KF, B1, B2, D, M><<<grid, SH::kThreads, bytes, s>>>(p);
-    return cudaSuccess;
-}
-template <bool KF, bool B1, bool B2, bool D, bool M>
-cudaError_t launch_step(int sm_count, cudaStream_t s, const Params &p) {
-    return p.n >= kLargeShapeMinEnvs ? launch_step_shape<ShapeLarge, KF, B1, B2, D, M>(sm_count, s, p)
-                                     : launch_step_shape<ShapeSmall, KF, B1, B2, D, M>(sm_count, s, p);
-}
-template <bool KF, bool B1, bool B2>
-cudaError_t launch_step_d(bool dense, bool masked, int sm_count, cudaStream_t s, const Params &p) {
-    if (dense) return masked ? launch_step<KF, B1, B2, true, true>(sm_count, s, p) : launch_step<KF, B1, B2, true, false>(sm_count, s, p);
-    return masked ? launch_step<KF, B1, B2, false, true>(sm_count, s, p) : launch_step<KF, B1, B2, false, false>(sm_count, s, p);
-}
 template <bool KF>
 cudaError_t launch_step_k(const fg_config &c, int sm_count, cudaStream_t s, const Params &p) {
     const bool d = c.dense_reward != 0, m = p.step_mask != nullptr;

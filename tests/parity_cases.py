@@ -113,4 +113,36 @@ def case_fused_frame_skip(make_env, oracle, k, p2_bot, scale=1.0):
     assert st["episodes"] > 100 * scale
 
 
+def tape_profiles(rng, steps, n):
+    """Every env gets its own input personality: how long it holds an input and which of the 8 combinations it
+    prefers (turtles, dash spammers, button holders, ...).  Reaches corners of the state space that uniform or
+    uniformly sticky tapes visit rarely: long charges released at odd moments, double KOs, guard breaks in the corner."""
+    p_change = rng.choice([0.02, 0.05, 0.15, 0.4, 0.9], size=n)
+    prefs = rng.dirichlet(np.full(8, 0.35), size=n)                      # sparse preferences per env
+    cdf = np.cumsum(prefs, axis=1)
+    cur = (rng.random(n)[:, None] > cdf).sum(axis=1).astype(np.uint8)
+    out = np.zeros((steps, n), dtype=np.uint8)
+    for t in range(steps):
+        change = rng.random(n) < p_change
+        new = np.minimum((rng.random(n)[:, None] > cdf).sum(axis=1), 7).astype(np.uint8)
+        cur = np.where(change, new, cur).astype(np.uint8)
+        out[t] = cur
+    return out
+
+
+def case_input_personalities_self_play(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(2718)
+    n, steps = max(64, int(4096 * scale)), 2500
+    st = run_case(make_env, oracle, n, steps, p2_bot=False, tape1=tape_profiles(rng, steps, n),
+                  tape2=tape_profiles(rng, steps, n))
+    assert st["episodes"] > 200 * scale and st["guard_breaks"] > 0 and st["p1_specials_neutral"] > 0
+
+
+def case_input_personalities_vs_bot_sparse(make_env, oracle, scale=1.0):
+    rng = np.random.default_rng(3141)
+    n, steps = max(64, int(4096 * scale)), 2500
+    st = run_case(make_env, oracle, n, steps, dense=False, tape1=tape_profiles(rng, steps, n), seed=77)
+    assert st["episodes"] > 200 * scale and st["p1_specials_neutral"] > 0
+
+
 FUSED_PARAMS = [(4, False), (4, True), (3, True), (16, False)]

@@ -1,5 +1,10 @@
 #!/bin/bash
 # usage: tools/probes/build_variant.sh <tag> [-DFLAG=V ...]   ->  tools/probes/lib_<tag>.so (developer experiments)
 TAG=$1; shift
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC -shared "$@" \
-  -o tools/probes/lib_$TAG.so footsies_gym_b200/csrc/footsies_kernels.cu
+python - "$TAG" "$@" <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+from footsies_gym_b200 import build
+tag, flags = sys.argv[1], sys.argv[2:]
+print(build.build(force=True, extra_flags=flags, lib_path=os.path.join(os.getcwd(), "tools", "probes", f"lib_{tag}.so")))
+PY
