@@ -23,11 +23,15 @@ using namespace fg;
 
 // CTA shape of the step kernel.  A CTA is GROUPS independent pipeline groups of GROUP threads: each group walks its
 // own sequence of GROUP-env chunks with its own TMA stages and mbarriers; all groups share the one copy of the tables
-// in shared memory.  Two shapes are compiled (measured on B200, tools/probes/run_sizes.sh):
-//   ShapeSmall  256 threads = 1 group, 2 stages, 4 CTAs/SM: many small CTAs, best below ~0.75 Mi envs per launch
-//               (65 536 envs, K = 4: 10.1 us vs 15.2 us with the large shape)
-//   ShapeLarge  1024 threads = 4 groups x 256, 3 stages, 1 CTA/SM: one copy of the tables per SM and a deeper prefetch
-//               (4 Mi envs K = 1: -2 %, 1 Mi envs K = 4: -9 %)
+// in shared memory.  Three shapes are compiled (measured on B200, tools/probes/run_sizes.sh):
+//   ShapeSmall        256 threads = 1 group, 2 stages, 3 CTAs/SM (85 registers): many small CTAs, best below ~0.75 Mi envs
+//                     (65 536 envs, K = 4: 10.1 us vs 15.2 us with a 1024-thread shape)
+//   ShapeLargeSingle  768 threads = 3 groups x 256, 3 stages, 1 CTA/SM, K = 1: 85 registers per thread instead of 64 (the
+//                     frame update wants ~85: no spills, more instruction-level parallelism) beats the extra 8 warps of
+//                     a 1024-thread CTA while HBM is the co-limiter (4 Mi envs: 128 us vs 136 us)
+//   ShapeLargeFused   1024 threads = 4 groups x 256, 3 stages, 1 CTA/SM, K > 1: purely ALU-bound, occupancy wins
+//                     (1 Mi envs, K = 4: 97.8 us vs 103.3 us with 768 threads)
+// All large shapes keep one copy of the tables per SM and prefetch two chunks ahead per group.
 template <int THREADS_, int GROUP_, int STAGES_, int MIN_BLOCKS_>
 struct StepShape {
     static constexpr int kThreads = THREADS_, kGroupThreads = GROUP_, kGroups = THREADS_ / GROUP_, kStages = STAGES_,
@@ -45,10 +49,12 @@ struct StepShape {
 #define FG_BLOCKS_PER_SM 4
 #endif
 using ShapeSmall = StepShape<FG_THREADS, FG_GROUP, FG_STAGES, FG_BLOCKS_PER_SM>;
-using ShapeLarge = ShapeSmall;
+using ShapeLargeSingle = ShapeSmall;
+using ShapeLargeFused = ShapeSmall;
 #else
-using ShapeSmall = StepShape<256, 256, 2, 4>;
-using ShapeLarge = StepShape<1024, 256, 3, 1>;
+using ShapeSmall = StepShape<256, 256, 2, 3>;
+using ShapeLargeSingle = StepShape<768, 256, 3, 1>;
+using ShapeLargeFused = StepShape<1024, 256, 3, 1>;
 #endif
 constexpr int kLargeShapeMinEnvs = 768 * 1024;
 constexpr int kThreads = 256;                    // reset / seed kernels
@@ -333,8 +339,9 @@ cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
 }
 template <bool KF, bool B1, bool B2, bool D, bool M>
 cudaError_t launch_step(int sm_count, cudaStream_t s, const Params &p) {
-    return p.n >= kLargeShapeMinEnvs ? launch_step_shape<ShapeLarge, KF, B1, B2, D, M>(sm_count, s, p)
-                                     : launch_step_shape<ShapeSmall, KF, B1, B2, D, M>(sm_count, s, p);
+    if (p.n < kLargeShapeMinEnvs) return launch_step_shape<ShapeSmall, KF, B1, B2, D, M>(sm_count, s, p);
+    if (KF) return launch_step_shape<ShapeLargeFused, KF, B1, B2, D, M>(sm_count, s, p);
+    return launch_step_shape<ShapeLargeSingle, KF, B1, B2, D, M>(sm_count, s, p);
 }
 template <bool KF, bool B1, bool B2>
 cudaError_t launch_step_d(bool dense, bool masked, int sm_count, cudaStream_t s, const Params &p) {
