@@ -183,13 +183,17 @@ FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel,
     bool want_buffer = false, set, differs = true;
     uint32_t req;
     // Forced requests, both only once hit stun is over: the reserved GUARD_BREAK (Fighter.cs:212-218), else the
-    // buffered cancel into N_SPECIAL after a connected hit (Fighter.cs:222-229).  STUN sits below RSV / BUF in the
-    // word, so "no stun and one of them set" is one range check on the masked word.
-    const uint32_t forced = pk & (M_RSV | M_BUF | M_STUN);
-    static_assert(FGP_STUN_SHIFT < FGP_BUF_SHIFT && FGP_BUF_SHIFT < FGP_RSV_SHIFT, "range check below");
-    if (forced >= M_BUF && !(forced & M_STUN) && ((forced & M_RSV) || (pk & M_HIT))) {
-        req = (forced & M_RSV) ? (uint32_t)GUARD_BREAK : (uint32_t)N_SPECIAL; set = true;
-    } else {
+    // buffered cancel into N_SPECIAL after a connected hit (Fighter.cs:222-229).  Rare: one test keeps them off the
+    // common path.
+    bool is_forced = false;
+    if (pk & (M_RSV | M_BUF)) {
+        if (!(pk & M_STUN) && ((pk & M_RSV) || (pk & M_HIT))) {
+            is_forced = true;
+            req = (pk & M_RSV) ? (uint32_t)GUARD_BREAK : (uint32_t)N_SPECIAL;
+            set = true;
+        }
+    }
+    if (!is_forced) {
         const uint32_t dir = in_lr != 0u ? 1u : 0u;
         const bool in_normal = normal && !ended;
         // attack request: N_ATTACK 5 / B_ATTACK 6 / N_SPECIAL 7 / B_SPECIAL 8 (the B_ variant when a direction is held)
@@ -212,7 +216,7 @@ FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel,
 
     // ---- frame data of the (action, frame) the fighter ends up in: the low bits of the packed word are the row index ----
     const uint4 row = T.rows[pk & FGP_ROW_MASK];
-    if (want_buffer && (row.z & FT_Z_CANCEL)) pk |= M_BUF;              // cancel window (Fighter.cs:492-505)
+    if (want_buffer) pk |= (row.z & FT_Z_CANCEL) << (FGP_BUF_SHIFT - 3);   // cancel window (Fighter.cs:492-505)
     pk = (pk & ~FGP_CARRY_MASK) | (row.w & FGP_CARRY_MASK);
 
     // ---- UpdateMovement (Fighter.cs:291-319) ----
@@ -234,6 +238,7 @@ FG_DEV const AttackRow &attack_of(const Tables &T, uint32_t w) {
     return *reinterpret_cast<const AttackRow *>(reinterpret_cast<const char *>(T.attack) + (w & (7u << FT_W_KIND_SHIFT)));
 }
 static_assert(FT_Z_BOXCFG_SHIFT == 5 && FT_W_KIND_SHIFT == 5, "id << 5 == byte offset of a 32-byte table row");
+static_assert(FT_Z_CANCEL == 8u, "update_fighter shifts the cancel bit into the buffered-cancel bit");
 
 // World x-extent of a box built at position pos_b (Fighter.cs:706-719: x = pos + data.x * sign; BoxBase xMin/xMax,
 // Fighter.cs:12-13) and then displaced by the push (s) and the wall clamp (t) like ApplyPositionChange does to
