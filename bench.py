@@ -182,10 +182,21 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints to fd 1 while the
+    benchmark runs (e.g. NCCL's version banner) is diverted to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
 
 
 def main():
+    sys.stdout.flush()
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -420,7 +431,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         if extra:
             line["extra"] = extra
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
