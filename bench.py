@@ -30,6 +30,8 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 METRIC = "env_frames_per_sec"
 UNIT = "env-frames/s"
 DEFAULT_ENVS_PER_GPU = 4 * 1024 * 1024
+STRONG_WORKLOAD = ("D: random-action P1 vs in-game BattleAI, frame-skip 1, auto-reset, {t} envs sharded over {w} GPU(s) "
+                   "(BASELINE configs[3]; per-GPU shards below ~2 Mi envs fit the 126 MB L2)")
 WORKLOAD = ("D-weak: random-action P1 vs in-game BattleAI, frame-skip 1, auto-reset, "
             "{n} envs per GPU (BASELINE configs[3] weak-scaled so the per-GPU working set exceeds L2)")
 
@@ -41,6 +43,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=DEFAULT_ENVS_PER_GPU)
+    ap.add_argument("--total-envs", type=int, default=0,
+                    help="strong scaling: shard this many envs over the ranks (BASELINE configs[3]: 1048576); "
+                         "default 0 = weak scaling with --envs-per-gpu envs on every GPU")
     ap.add_argument("--burnin", type=int, default=600,
                     help="untimed steps before the warm-up so that episodes are desynchronised (steady state)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
@@ -219,8 +224,12 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
-    n = args.envs_per_gpu
-    env = FootsiesEnv(num_envs=n, device=dev, opponent=None, seed=0, first_env_index=rank * n)
+    if args.total_envs > 0:
+        from footsies_gym_b200.distributed import shard_range
+        first_index, n = shard_range(args.total_envs, rank, world)
+    else:
+        n, first_index = args.envs_per_gpu, rank * args.envs_per_gpu
+    env = FootsiesEnv(num_envs=n, device=dev, opponent=None, seed=0, first_env_index=first_index)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -409,11 +418,17 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_launch, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD.format(n=n), "envs_per_gpu": n, "frame_skip": 1, "opponent": "bot",
+            "scaling": "strong" if args.total_envs > 0 else "weak", "vs_baseline": None, "dtype": "int32+fp32",
+            "data": "synthetic",
+            "config": {"workload": (STRONG_WORKLOAD.format(t=args.total_envs, w=world) if args.total_envs > 0
+                                    else WORKLOAD.format(n=n)),
+                       "envs_per_gpu": n, "frame_skip": 1, "opponent": "bot",
                        "actions": "iid uniform over 8 bitmasks, torch.Generator(device).manual_seed(1234 + rank)",
-                       "l2": f"inputs larger than L2: {2 * 64 * n / 1e6:.0f} MB of state traffic + "
-                             f"{46 * n / 1e6:.0f} MB of outputs per step vs 126 MB L2; no flush",
+                       "l2": (f"inputs larger than L2: {2 * 64 * n / 1e6:.0f} MB of state traffic + "
+                              f"{46 * n / 1e6:.0f} MB of outputs per step vs 126 MB L2; no flush"
+                              if (2 * 64 + 46) * n > 2 * 126e6 else
+                              f"NOT larger than L2: {(2 * 64 + 46) * n / 1e6:.0f} MB touched per step vs 126 MB L2 and no "
+                              f"flush -> informational only, use the default weak-scaling workload for the roofline"),
                        "frames_counted": "kernel simulated-frame counter (FG_STAT_ENV_FRAMES)",
                        "burnin_steps": args.burnin},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -29,3 +29,14 @@ def all_reduce_stats(stats: torch.Tensor) -> dict:
         torch.distributed.all_reduce(s, op=torch.distributed.ReduceOp.SUM)
     vals = s.cpu().tolist()
     return {k: int(v) for k, v in zip(_capi.STAT_NAMES, vals)}
+
+
+def make_sharded_env(total_envs: int, **env_kwargs):
+    """This rank's shard of a `total_envs`-battle job launched one process per GPU (torchrun: RANK / LOCAL_RANK /
+    WORLD_SIZE): contiguous global env indices, device cuda:LOCAL_RANK, bot seeds derived from the GLOBAL index so
+    that results do not depend on the number of GPUs (tests/test_gpu_full_size.py checks exactly that)."""
+    from .env import FootsiesEnv
+    rank, local_rank, world = env_rank_world()
+    first, count = shard_range(total_envs, rank, world)
+    torch.cuda.set_device(local_rank)
+    return FootsiesEnv(num_envs=count, device=torch.device("cuda", local_rank), first_env_index=first, **env_kwargs)
