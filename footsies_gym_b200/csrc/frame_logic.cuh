@@ -87,6 +87,8 @@ struct FG_ALIGN16 Tables {
     uint8_t cum_next[16][4];
     uint32_t move_meta[8], att_meta[8];   // pattern offset | length << 16
     uint8_t bucket_of[16];                // [clamp(ceil(2 * distance), 4, 9) - 4] -> bucket
+    uint16_t dash_fsm[256][4];            // [state][Left | Right << 1] -> next state | dash-by-Left << 8 | dash-by-Right << 9
+    uint8_t arun_lut[64 * 8];             // [run * 8 + input] -> new run | special << 6 | attack-down << 7
     uint8_t move_pat[2][kMovePatBytes];   // [side] InputDefine bits (P1: forward = Right, P2: forward = Left)
     uint8_t att_pat[kAttPatBytes];
 };
@@ -133,38 +135,22 @@ struct FrameOut {       // per-fighter products of the pre-collision phases
 };
 
 // Fighter.UpdateInput + IncrementActionFrame + UpdateActionRequest + UpdateMovement for one fighter.
-// SIDE 0 = P1 (faces right: forward = Right), 1 = P2 (faces left: forward = Left).  The Attack run length of the
-// fighter lives in `misc` (bits [0:6) for P1, [6:12) for P2) and is updated in place.
+// SIDE 0 = P1 (faces right: forward = Right), 1 = P2 (faces left: forward = Left).  `hist` is the fighter's input word:
+// dash-automaton state [0:8) | Attack run length [8:14).
 template <int SIDE>
-FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel, uint32_t &pk, uint32_t &hist,
-                           uint32_t &misc, FrameOut &fo) {
-    // ---- UpdateInput (Fighter.cs:172-188): Attack run length; special = release after >= 59 held frames (:569-583) ----
-    constexpr uint32_t AR_SHIFT = SIDE == 0 ? FGM_ARUN1_SHIFT : FGM_ARUN2_SHIFT;
-    constexpr uint32_t AR_MASK = 63u << AR_SHIFT, AR_ONE = 1u << AR_SHIFT, AR_SAT = 59u << AR_SHIFT;
-    const uint32_t ar = misc & AR_MASK;
-    const bool in_a = (in & 4u) != 0u;
-    const bool special = !in_a && ar == AR_SAT;                         // CheckSpecialAttackInput
-    const bool atk_down = in_a && ar == 0u;                             // IsAttackInput(inputDown[0])
-    misc = in_a ? (ar == AR_SAT ? misc : misc + AR_ONE) : (misc & ~AR_MASK);
-
-    // ---- CheckForwardDashInput / CheckBackwardDashInput (Fighter.cs:585-635) on the history BEFORE this frame:
-    //      bit i of the low half = Left held i + 1 frames ago, high half = Right.  The most recent of the last 8 frames
-    //      with a direction held decides (it must hold only the pressed direction), and one of the 8 frames before
-    //      it must be neutral. ----
-    const uint32_t hr = hist >> 16;
-    const uint32_t any_dir = hist | hr;                                 // (the high half is garbage, masked below)
-    const uint32_t e8 = any_dir & 0xffu;
-    const uint32_t low = e8 & (0u - e8);                                // that frame, one-hot (0: none -> no dash)
-    const uint32_t window = low * 0x1feu;                               // the 8 frames before it (bits <= 15)
-    const bool gap = (~any_dir & window) != 0u;
-    const uint32_t f_old = SIDE == 0 ? hr : hist, b_old = SIDE == 0 ? hist : hr;
-    const uint32_t f_bit = SIDE == 0 ? 2u : 1u, b_bit = SIDE == 0 ? 1u : 2u;
-    const bool fwd = (in & f_bit) != 0u, back = (in & b_bit) != 0u;
-    const bool dash_f = fwd && !(f_old & 1u) && gap && !(b_old & low);
-    const bool dash_b = back && !(b_old & 1u) && gap && !(f_old & low);
-    // shift the new frame in: Left -> bit 0, Right -> bit 16
+FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel, uint32_t &pk, uint32_t &hist, FrameOut &fo) {
+    // ---- UpdateInput (Fighter.cs:172-188) + CheckSpecialAttackInput (:569-583) + CheckForward/BackwardDashInput
+    //      (:585-635), each as one table step: the Attack run length (new run | special | attack-down) and the
+    //      dash-detection automaton over the Left/Right bits (next state | dash-by-Left | dash-by-Right) ----
     const uint32_t in_lr = in & 3u;
-    hist = ((hist << 1) & 0xfffefffeu) | ((in_lr * 0x8001u) & 0x00010001u);
+    const uint32_t au = T.arun_lut[((hist >> (FGH_ARUN_SHIFT - 3)) & (63u << 3)) + in];
+    const uint32_t du = T.dash_fsm[hist & 255u][in_lr];
+    hist = (du & 255u) | (au & 63u) << FGH_ARUN_SHIFT;
+    const bool special = (au & 64u) != 0u;                              // Attack released after >= 59 held frames
+    const bool atk_down = (au & 128u) != 0u;                            // IsAttackInput(inputDown[0])
+    const bool dash_f = (du & (SIDE == 0 ? 0x200u : 0x100u)) != 0u;     // P1's forward is Right, P2's is Left
+    const bool dash_b = (du & (SIDE == 0 ? 0x100u : 0x200u)) != 0u;
+    const bool back = (in & (SIDE == 0 ? 1u : 2u)) != 0u;
 
     // ---- IncrementActionFrame (Fighter.cs:140-166): sprite shake decays (sign flips, magnitude - 1); hit stun ticks
     //      down and freezes the frame counter, else the frame counter advances ----
@@ -389,16 +375,15 @@ FG_DEV void reset_env(const Tables &T, Env &e, bool stale_intro) {
     }
     e.pk1 = npk[0]; e.pk2 = npk[1];
     e.pos1 = -2.0f; e.pos2 = 2.0f; e.vel1 = 0.0f; e.vel2 = 0.0f;
-    e.hist1 = (a1 & 1u) | ((a1 >> 1) & 1u) << 16;                       // UpdateInput(stale) after ClearInput
-    e.hist2 = (a2 & 1u) | ((a2 >> 1) & 1u) << 16;
+    // UpdateInput(stale input) after ClearInput: one automaton / run-length step from the cleared state
+    e.hist1 = (T.dash_fsm[0][a1 & 3u] & 255u) | ((a1 >> 2) & 1u) << FGH_ARUN_SHIFT;
+    e.hist2 = (T.dash_fsm[0][a2 & 3u] & 255u) | ((a2 >> 2) & 1u) << FGH_ARUN_SHIFT;
     e.frame = -1;
     e.bq1 = 0u; e.bq2 = 0u;                                            // BattleAI.Reset (BattleAI.cs:393-403)
-    const uint32_t run1 = (a1 >> 2) & 1u, run2 = (a2 >> 2) & 1u;       // Attack run after the Intro frame's input
     // first bot query at the Fight transition (BattleCore.cs:289): decision input = round-start state
     if (P1BOT) a1 = bot_next<0>(T, e, e.bq1, 4.0f, STAND);
     if (P2BOT) a2 = bot_next<1>(T, e, e.bq2, 4.0f, STAND);
-    e.misc = run1 << FGM_ARUN1_SHIFT | run2 << FGM_ARUN2_SHIFT
-           | a1 << FGM_ACTOR1_SHIFT | a2 << FGM_ACTOR2_SHIFT;           // recorded inputs 0, done 0, cum 0
+    e.misc = a1 << FGM_ACTOR1_SHIFT | a2 << FGM_ACTOR2_SHIFT;           // recorded inputs 0, done 0, cum 0
 }
 
 // What one env-step hands back: FootsiesEnv._extract_obs / _extract_info (footsies.py:336-380) incl. the
@@ -439,8 +424,8 @@ FG_DEV void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, 
         e.misc = (e.misc & ~(63u << FGM_REC1_SHIFT)) | (in1 + in2 * 8u) << FGM_REC1_SHIFT;
 
     FrameOut f1, f2;
-    update_fighter<0>(T, in1, e.pos1, e.vel1, e.pk1, e.hist1, e.misc, f1);
-    update_fighter<1>(T, in2, e.pos2, e.vel2, e.pk2, e.hist2, e.misc, f2);
+    update_fighter<0>(T, in1, e.pos1, e.vel1, e.pk1, e.hist1, f1);
+    update_fighter<1>(T, in2, e.pos2, e.vel2, e.pk2, e.hist2, f2);
 
     // ---- UpdatePushCharacterVsCharacter (BattleCore.cs:483-501), UnityEngine.Rect semantics: x = left edge, strict ----
     const BoxCfg &b1 = boxcfg_of(T, f1.z), &b2 = boxcfg_of(T, f2.z);
@@ -501,7 +486,7 @@ FG_DEV void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, 
         e.hist1 = 0u; e.hist2 = 0u;
         acc.a += 1u + (1u << (8u * (dead1 && dead2 ? 3u : dead2 ? 1u : 2u)));
         acc.ep_frames += (uint32_t)(e.frame + 1);
-        e.misc = (e.misc & ~((63u << FGM_ARUN1_SHIFT) | (63u << FGM_ARUN2_SHIFT))) | 1u << FGM_DONE_SHIFT;
+        e.misc |= 1u << FGM_DONE_SHIFT;
     } else {
         // ---- TrainingManager.Step (TrainingManager.cs:59-77): actors' inputs for the next frame; bots are asked
         //      after the frame, P1 first, and not on the terminal frame ----

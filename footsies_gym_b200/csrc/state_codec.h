@@ -2,11 +2,14 @@
 // expanded form.  Shared by the CUDA kernels and the host-side fg_get_state / fg_set_state.
 //
 // Why this is enough (vs. the reference's 3 x 180 ints of input history per fighter, Fighter.cs:98-101):
-//   * dash detection reads Left/Right of input[0..16] only (Fighter.cs:585-635 with dashAllowFrame 9:
-//     i <= 8, j <= i + 8)                                   -> 16 stored frames + the new one = 17
-//   * the hold-release special reads "Attack held on input[1..59]" (Fighter.cs:569-583) -> a run length
-//     saturating at 59
+//   * dash detection reads Left/Right of input[0..16] only (Fighter.cs:585-635 with dashAllowFrame 9: i <= 8,
+//     j <= i + 8), and all it can learn from them is: how long ago the most recent direction-held frame was, which
+//     directions it held and how long the run of direction-held frames ending there is -> a 217-state automaton
+//     (tools/gen_kernel_tables.py build_dash_fsm), stored as its 8-bit state id
+//   * the hold-release special reads "Attack held on input[1..59]" (Fighter.cs:569-583) -> a run length saturating at 59
 //   * inputDown / inputUp are functions of input[0], input[1] (Fighter.cs:184-185).
+// fg_get_state expands the automaton state into an equivalent Left/Right bit history (the run of `lastdir` frames
+// ending `since` frames ago); fg_set_state reduces any bit history to its automaton state.
 #ifndef FOOTSIES_B200_STATE_CODEC_H
 #define FOOTSIES_B200_STATE_CODEC_H
 
@@ -21,7 +24,7 @@
 #endif
 
 // plane indices
-#define FG_PLANE_F1 0   // {pos_x bits, velocity_x bits, packed, hist}
+#define FG_PLANE_F1 0   // {pos_x bits, velocity_x bits, packed, input word}
 #define FG_PLANE_F2 1
 #define FG_PLANE_ENV 2  // {frame, misc, bot queue P2, bot queue P1}
 #define FG_PLANE_RNG 3  // xorshift128 state
@@ -48,9 +51,11 @@
 #define FGP_ROW_MASK 0x7ffu
 #define FGP_MAX_FRAME 63
 
-// misc env word
-#define FGM_ARUN1_SHIFT 0    // 6 bits: attack run length P1 (saturates at 59)
-#define FGM_ARUN2_SHIFT 6
+// input word of a fighter (4th word of its plane)
+#define FGH_DASH_SHIFT 0     // 8 bits: dash-detection automaton state (0 = COLD / cleared history)
+#define FGH_ARUN_SHIFT 8     // 6 bits: attack run length (saturates at 59)
+
+// misc env word (bits [0:12) unused)
 #define FGM_REC1_SHIFT 12    // 3 bits: last recorded input P1 (BattleCore.cs:593-607 stops recording after 18000 frames)
 #define FGM_REC2_SHIFT 15
 #define FGM_DONE_SHIFT 18    // battle over, waiting for reset
@@ -76,7 +81,34 @@ static inline int fg_action_index(int id) {
     return -1;
 }
 
-static inline void fg_decode_fighter(const FgVec4 &v, uint32_t arun, fg_fighter_state *o) {
+static const uint16_t FG_DASH_STATE_INFO[FT_NUM_DASH_STATES] = FT_DASH_STATE_INFO_INIT;   // since | runlen << 4 | lastdir << 8
+
+// Left / Right bit history (bit i = held i frames ago) equivalent to a dash-automaton state
+static inline void fg_dash_state_to_history(uint32_t id, uint32_t *left, uint32_t *right) {
+    *left = 0; *right = 0;
+    if (id == 0 || id >= FT_NUM_DASH_STATES) return;
+    const uint32_t info = FG_DASH_STATE_INFO[id], since = info & 15u, runlen = (info >> 4) & 15u, lastdir = info >> 8;
+    const uint32_t last = runlen >= 9u ? 16u : since + runlen;        // "9 or more": fill what a 16-frame history shows
+    for (uint32_t k = since; k < last && k < 16u; k++) {
+        if (lastdir & 1u) *left |= 1u << k;
+        if (lastdir & 2u) *right |= 1u << k;
+    }
+}
+// ... and back: any 16-frame bit history reduces to (since, runlen, lastdir)
+static inline uint32_t fg_history_to_dash_state(uint32_t left, uint32_t right) {
+    const uint32_t any = (left | right) & 0xffffu;
+    uint32_t since = 0;
+    while (since < 8u && !((any >> since) & 1u)) since++;
+    if (since >= 8u) return 0u;
+    uint32_t runlen = 0;
+    while (since + runlen < 16u && ((any >> (since + runlen)) & 1u) && runlen < 9u) runlen++;
+    const uint32_t lastdir = ((left >> since) & 1u) | ((right >> since) & 1u) << 1;
+    const uint32_t want = since | runlen << 4 | lastdir << 8;
+    for (uint32_t i = 1; i < FT_NUM_DASH_STATES; i++) if (FG_DASH_STATE_INFO[i] == want) return i;
+    return 0u;
+}
+
+static inline void fg_decode_fighter(const FgVec4 &v, fg_fighter_state *o) {
     o->pos_x = fg_u2f(v.x);
     o->velocity_x = fg_u2f(v.y);
     uint32_t p = v.z;
@@ -92,14 +124,13 @@ static inline void fg_decode_fighter(const FgVec4 &v, uint32_t arun, fg_fighter_
     o->is_reserve_prox = (int)fg_bits(p, FGP_RPROX_SHIFT, 1);
     o->shake = (int)fg_bits(p, FGP_SHAKE_SHIFT, 3) * (fg_bits(p, FGP_SHAKE_SIGN_SHIFT, 1) ? -1 : 1);
     o->has_won = 0;
-    o->hist_left = v.w & 0xffffu;
-    o->hist_right = v.w >> 16;
-    o->attack_run = (int)arun;
-    o->input0 = (int)((o->hist_left & 1u) | (o->hist_right & 1u) << 1 | (arun > 0 ? 4u : 0u));
+    fg_dash_state_to_history(fg_bits(v.w, FGH_DASH_SHIFT, 8), &o->hist_left, &o->hist_right);
+    o->attack_run = (int)fg_bits(v.w, FGH_ARUN_SHIFT, 6);
+    o->input0 = (int)((o->hist_left & 1u) | (o->hist_right & 1u) << 1 | (o->attack_run > 0 ? 4u : 0u));
 }
 
 // returns 0 on success, -1 if the state cannot be represented
-static inline int fg_encode_fighter(const fg_fighter_state *s, FgVec4 *v, uint32_t *arun) {
+static inline int fg_encode_fighter(const fg_fighter_state *s, FgVec4 *v) {
     int idx = fg_action_index(s->action_id);
     if (idx < 0 || idx == FT_IDX_WIN || s->has_won) return -1;
     int frame_count = (int)(FG_ACTION_INFO_H[idx] & 0x1ffu);
@@ -126,15 +157,14 @@ static inline int fg_encode_fighter(const fg_fighter_state *s, FgVec4 *v, uint32
     v->x = fg_f2u(s->pos_x);
     v->y = fg_f2u(s->velocity_x);
     v->z = p;
-    v->w = (s->hist_left & 0xffffu) | (s->hist_right & 0xffffu) << 16;
-    *arun = (uint32_t)s->attack_run;
+    v->w = fg_history_to_dash_state(s->hist_left, s->hist_right) << FGH_DASH_SHIFT | (uint32_t)s->attack_run << FGH_ARUN_SHIFT;
     return 0;
 }
 
 static inline void fg_decode_env(const FgVec4 &f1, const FgVec4 &f2, const FgVec4 &e, const FgVec4 &r, fg_env_state *o) {
     uint32_t m = e.y;
-    fg_decode_fighter(f1, fg_bits(m, FGM_ARUN1_SHIFT, 6), &o->f[0]);
-    fg_decode_fighter(f2, fg_bits(m, FGM_ARUN2_SHIFT, 6), &o->f[1]);
+    fg_decode_fighter(f1, &o->f[0]);
+    fg_decode_fighter(f2, &o->f[1]);
     o->frame = (int32_t)e.x;
     o->recorded_input[0] = (int)fg_bits(m, FGM_REC1_SHIFT, 3);
     o->recorded_input[1] = (int)fg_bits(m, FGM_REC2_SHIFT, 3);
@@ -147,11 +177,9 @@ static inline void fg_decode_env(const FgVec4 &f1, const FgVec4 &f2, const FgVec
 }
 
 static inline int fg_encode_env(const fg_env_state *s, FgVec4 *f1, FgVec4 *f2, FgVec4 *e, FgVec4 *r) {
-    uint32_t a1 = 0, a2 = 0;
-    if (fg_encode_fighter(&s->f[0], f1, &a1) || fg_encode_fighter(&s->f[1], f2, &a2)) return -1;
+    if (fg_encode_fighter(&s->f[0], f1) || fg_encode_fighter(&s->f[1], f2)) return -1;
     if (s->cum_reward_index < 0 || s->cum_reward_index >= FT_NUM_CUM) return -1;
-    uint32_t m = a1 << FGM_ARUN1_SHIFT | a2 << FGM_ARUN2_SHIFT
-               | ((uint32_t)s->recorded_input[0] & 7u) << FGM_REC1_SHIFT | ((uint32_t)s->recorded_input[1] & 7u) << FGM_REC2_SHIFT
+    uint32_t m = ((uint32_t)s->recorded_input[0] & 7u) << FGM_REC1_SHIFT | ((uint32_t)s->recorded_input[1] & 7u) << FGM_REC2_SHIFT
                | (uint32_t)(s->done != 0) << FGM_DONE_SHIFT | (uint32_t)s->cum_reward_index << FGM_CUM_SHIFT
                | ((uint32_t)s->actor_input[0] & 7u) << FGM_ACTOR1_SHIFT | ((uint32_t)s->actor_input[1] & 7u) << FGM_ACTOR2_SHIFT;
     e->x = (uint32_t)s->frame; e->y = m; e->z = s->bot_queue[1]; e->w = s->bot_queue[0];

@@ -76,6 +76,10 @@ inline void build_tables(Tables &t) {
         t.bot[b].magic_m = (~0ull) / (unsigned long long)n_m[b] + 1ull;   // floor(2^64 / n) + 1
         t.bot[b].magic_a = (~0ull) / (unsigned long long)n_a[b] + 1ull;
     }
+    static const uint16_t dash_fsm[FT_NUM_DASH_STATES][4] = FT_DASH_FSM_INIT;
+    static const uint8_t arun_lut[64 * 8] = FT_ARUN_LUT_INIT;
+    for (int i = 0; i < FT_NUM_DASH_STATES; i++) for (int d = 0; d < 4; d++) t.dash_fsm[i][d] = dash_fsm[i][d];
+    memcpy(t.arun_lut, arun_lut, sizeof arun_lut);
     // index = clamp(ceil(2 * distance), 4, 9) - 4
     static const uint8_t bucket_of[6] = { 4, 3, 2, 1, 1, 0 };
     for (int i = 0; i < 6; i++) t.bucket_of[i] = bucket_of[i];

@@ -29,6 +29,38 @@ def _eq(where, name, got, exp):
         _fail(where, name, got, exp)
 
 
+def canonical_history(left, right):
+    """The kernel keeps, of the Left/Right input history, exactly what dash detection can ever read (Fighter.cs:585-635):
+    how long ago the most recent direction-held frame of the last 8 was (`since`), which directions it held and the
+    length (capped at 9) of the unbroken run of direction-held frames ending there.  fg_get_state expands that back into
+    a bit history; this reduces the oracle's real history (bit i = held i frames ago) to the same canonical form."""
+    left = np.asarray(left, dtype=np.uint32) & 0xFFFF
+    right = np.asarray(right, dtype=np.uint32) & 0xFFFF
+    anyd = left | right
+    since = np.full(left.shape, 8, dtype=np.int64)
+    for k in range(7, -1, -1):
+        since = np.where((anyd >> k) & 1 == 1, k, since)
+    cold = since >= 8
+    s = np.minimum(since, 7)
+    runlen = np.zeros(left.shape, dtype=np.int64)
+    alive = ~cold
+    for j in range(16):
+        pos = s + j
+        held = alive & (pos < 16) & (((anyd >> np.minimum(pos, 15)) & 1) == 1) & (runlen < 9)
+        runlen = np.where(held, runlen + 1, runlen)
+        alive = alive & held
+    last_l = (left >> s) & 1
+    last_r = (right >> s) & 1
+    out_l = np.zeros(left.shape, dtype=np.uint32)
+    out_r = np.zeros(left.shape, dtype=np.uint32)
+    end = np.where(runlen >= 9, 16, s + runlen)
+    for k in range(16):
+        inside = (~cold) & (k >= s) & (k < end)
+        out_l |= np.where(inside & (last_l == 1), np.uint32(1 << k), np.uint32(0))
+        out_r |= np.where(inside & (last_r == 1), np.uint32(1 << k), np.uint32(0))
+    return out_l, out_r
+
+
 def compare_states(kernel_state, oracle_trace, where="", check_rng=True, check_actor=(True, True)):
     """kernel_state: structured array from FootsiesEnv.get_state(); oracle_trace: OracleBatch.trace."""
     ks, ot = kernel_state, oracle_trace
@@ -36,8 +68,9 @@ def compare_states(kernel_state, oracle_trace, where="", check_rng=True, check_a
         _eq(where, f"f.{f}", ks["f"][f], ot["f"][f])
     for f in FIGHTER_FLOAT_FIELDS:
         _eq(where, f"f.{f}", ks["f"][f], ot["f"][f])
-    _eq(where, "f.hist_left[0:16]", ks["f"]["hist_left"] & 0xFFFF, ot["f"]["hist_left"] & 0xFFFF)
-    _eq(where, "f.hist_right[0:16]", ks["f"]["hist_right"] & 0xFFFF, ot["f"]["hist_right"] & 0xFFFF)
+    exp_l, exp_r = canonical_history(ot["f"]["hist_left"], ot["f"]["hist_right"])
+    _eq(where, "f.hist_left (canonical form)", ks["f"]["hist_left"] & 0xFFFF, exp_l)
+    _eq(where, "f.hist_right (canonical form)", ks["f"]["hist_right"] & 0xFFFF, exp_r)
     _eq(where, "frame", ks["frame"], ot["frame"])
     _eq(where, "recorded_input", ks["recorded_input"], ot["recorded_input"])
     _eq(where, "done", ks["done"], ot["terminated"])

@@ -15,6 +15,7 @@ import numpy as np
 import pytest
 
 from footsies_gym_b200 import _capi
+from parity import canonical_history
 from footsies_gym_b200.state import (FootsiesBattleState, FootsiesState, UnrepresentableStateError,
                                      battle_state_into_env_state, env_state_to_battle_state)
 
@@ -81,7 +82,13 @@ def test_compact_mapping_preserves_behaviour(oracle):
         for side in ("p1State", "p2State"):
             for key in kept:
                 assert small[side][key] == full[side][key], (side, key)
-            assert [v & 3 for v in small[side]["input"][:16]] == [v & 3 for v in full[side]["input"][:16]]
+            # of the Left/Right history the device keeps the canonical form dash detection can read (tests/parity.py)
+            fl = sum((v & 1) << k for k, v in enumerate(full[side]["input"][:16]))
+            fr = sum(((v >> 1) & 1) << k for k, v in enumerate(full[side]["input"][:16]))
+            sl = sum((v & 1) << k for k, v in enumerate(small[side]["input"][:16]))
+            sr = sum(((v >> 1) & 1) << k for k, v in enumerate(small[side]["input"][:16]))
+            cf, cs = canonical_history(np.array([fl]), np.array([fr])), canonical_history(np.array([sl]), np.array([sr]))
+            assert int(cf[0][0]) == int(cs[0][0]) and int(cf[1][0]) == int(cs[1][0])
         assert small["frameCount"] == full["frameCount"]
         b.load_battle_state(i, small)
     assert alive.sum() >= n // 3

@@ -34,6 +34,63 @@ def all_matches(items, frame):
     return [it for it in items if it["se"][0] <= frame <= it["se"][1]]
 
 
+def build_dash_fsm():
+    """Dash detection (Fighter.CheckForwardDashInput / CheckBackwardDashInput, Fighter.cs:585-635) as a finite automaton
+    over the Left/Right bits of each frame's input.
+
+    The checks look, among the 8 most recent past frames, for the most recent one with a direction held; it must hold
+    only the direction being pressed now, and one of the 8 frames before it must be neutral.  All they can ever read
+    of the past is therefore: how many frames ago that frame was (`since`, 0 = the previous frame), which directions
+    it held (`lastdir`, Left 1 | Right 2) and how long the unbroken run of direction-held frames ending there is
+    (`runlen`: the frame before the run is neutral, so the neutral-frame condition is runlen <= 8).  Once `since`
+    exceeds 7 nothing can be read any more: one COLD state (id 0, also the state of a cleared history).
+
+    Returns (states, table): states[id] = (since, runlen, lastdir) with COLD = (8, 0, 0); table[id][d] =
+    next id | dash-by-Left << 8 | dash-by-Right << 9 for the new frame's direction bits d."""
+    states = [(8, 0, 0)]
+    for since in range(8):
+        for runlen in range(1, 10):       # 9 = "9 or more"
+            for lastdir in (1, 2, 3):
+                states.append((since, runlen, lastdir))
+    index = {st: i for i, st in enumerate(states)}
+    table = []
+    for (since, runlen, lastdir) in states:
+        row = []
+        cold = since >= 8
+        for d in range(4):
+            dash = 0
+            for bit in (1, 2):            # pressing Left (1) / Right (2) this frame
+                pressed = (d & bit) and not (not cold and since == 0 and (lastdir & bit))
+                if pressed and not cold and since <= 7 and lastdir == bit and runlen <= 8:
+                    dash |= bit
+            if d:
+                nxt = (0, min(runlen + 1, 9) if (not cold and since == 0) else 1, d)
+            elif cold or since + 1 >= 8:
+                nxt = (8, 0, 0)
+            else:
+                nxt = (since + 1, runlen, lastdir)
+            row.append(index[nxt] | dash << 8)
+        table.append(row)
+    assert len(states) <= 256
+    return states, table
+
+
+def build_attack_run_lut():
+    """Attack-button run length (saturating at 59 = specialAttackHoldFrame - 1) as a lookup: [run * 8 + input] ->
+    new run | special << 6 | attack-down << 7.  special = Attack released after being held on input[1..59]
+    (Fighter.CheckSpecialAttackInput, Fighter.cs:569-583); attack-down = IsAttackInput(inputDown[0]) (:184-185)."""
+    lut = []
+    for run in range(64):
+        for inp in range(8):
+            a = (inp >> 2) & 1
+            r = min(run, 59)
+            new = min(r + 1, 59) if a else 0
+            special = int((not a) and r >= 59)
+            down = int(a and r == 0)
+            lut.append(new | special << 6 | down << 7)
+    return lut
+
+
 ROW_FRAMES = 64        # rows per action; the 6-bit frame field of the packed fighter word indexes them directly
 
 # row.z bit layout
@@ -248,8 +305,10 @@ def build(consts, attacks, actions):
         if code & 2:
             r += 0.3
         step_reward.append(r)
+    dash_states, dash_table = build_dash_fsm()
     return dict(rows=rows, action_info=action_info, cfg_rows=cfg_rows, cfg_tab=cfg_tab, atk_rows=atk_rows, cum_vals=vals,
-                cum_next=cum_next, term=term, step_reward=step_reward, hurt_tab=hurt_tab, push_tab=push_tab)
+                cum_next=cum_next, term=term, step_reward=step_reward, hurt_tab=hurt_tab, push_tab=push_tab,
+                dash_states=dash_states, dash_table=dash_table, arun_lut=build_attack_run_lut())
 
 
 
@@ -292,6 +351,14 @@ def emit(consts, attacks, actions, path):
     w("/* attacks [kind]: {prox centre, prox width/2, real centre, real width/2, prox y-bits, real y-bits, result, 0};")
     w(" * result: damageAction idx[0:5) | guardAction idx[5:10) | vitalDamage[10] | hitStun[11:16) | guardStun[16:21) | breakStun[21:26) */")
     w("#define FT_ATTACK_INIT {%s}" % ", ".join("{%s}" % ", ".join("0x%08xu" % v for v in r) for r in t["atk_rows"]))
+    w("/* dash detection automaton (tools/gen_kernel_tables.py build_dash_fsm): [state][direction bits] = next state |")
+    w(" * dash-by-Left << 8 | dash-by-Right << 9; state 0 = COLD (nothing readable in the last 8 frames) */")
+    w("#define FT_NUM_DASH_STATES %d" % len(t["dash_states"]))
+    w("#define FT_DASH_FSM_INIT {%s}" % ", ".join("{%s}" % ", ".join("0x%03x" % v for v in r) for r in t["dash_table"]))
+    w("/* [state] = since | runlen << 4 | lastdir << 8 (host side: expansion to / from a Left/Right bit history) */")
+    w("#define FT_DASH_STATE_INFO_INIT {%s}" % ", ".join("0x%03x" % (st[0] | st[1] << 4 | st[2] << 8) for st in t["dash_states"]))
+    w("/* attack run length [run * 8 + input] = new run | special << 6 | attack-down << 7 */")
+    w("#define FT_ARUN_LUT_INIT {%s}" % ", ".join(str(v) for v in t["arun_lut"]))
     w("/* dense reward automaton (footsies.py:388-405): cumulative float64 values, next index per guard-drop code, terminal reward */")
     w("#define FT_CUM_VALUES_INIT {%s}" % ", ".join(float(v).hex() for v in t["cum_vals"]))
     w("#define FT_CUM_NEXT_INIT {%s}" % ", ".join("{%s}" % ", ".join(map(str, r)) for r in t["cum_next"]))
