@@ -89,6 +89,7 @@ struct FG_ALIGN16 Tables {
     uint8_t bucket_of[16];                // [clamp(ceil(2 * distance), 4, 9) - 4] -> bucket
     uint16_t dash_fsm[256][4];            // [state][Left | Right << 1] -> next state | dash-by-Left << 8 | dash-by-Right << 9
     uint8_t arun_lut[64 * 8];             // [run * 8 + input] -> new run | special << 6 | attack-down << 7
+    uint8_t req_lut[2][1024];             // [side][inputs + flags] -> requested action | FREE | WANT_BUFFER | ENDED
     uint8_t move_pat[2][kMovePatBytes];   // [side] InputDefine bits (P1: forward = Right, P2: forward = Left)
     uint8_t att_pat[kAttPatBytes];
 };
@@ -137,7 +138,10 @@ struct FrameOut {       // per-fighter products of the pre-collision phases
 // Fighter.UpdateInput + IncrementActionFrame + UpdateActionRequest + UpdateMovement for one fighter.
 // SIDE 0 = P1 (faces right: forward = Right), 1 = P2 (faces left: forward = Left).  `hist` is the fighter's input word:
 // dash-automaton state [0:8) | Attack run length [8:14).
-template <int SIDE>
+// LUT_REQUEST selects how the request is decided: by one more table lookup (fewest ALU-pipe instructions: the fused-K
+// kernels, which are purely ALU-bound, gain 4 %) or by a short select chain on predicates (one dependent shared-memory
+// access less per fighter: the K = 1 kernels, which run 24 warps per SM against HBM latency, are 3 % faster with it).
+template <int SIDE, bool LUT_REQUEST>
 FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel, uint32_t &pk, uint32_t &hist, FrameOut &fo) {
     // ---- UpdateInput (Fighter.cs:172-188) + CheckSpecialAttackInput (:569-583) + CheckForward/BackwardDashInput
     //      (:585-635), each as one table step: the Attack run length (new run | special | attack-down) and the
@@ -146,53 +150,59 @@ FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel,
     const uint32_t au = T.arun_lut[((hist >> (FGH_ARUN_SHIFT - 3)) & (63u << 3)) + in];
     const uint32_t du = T.dash_fsm[hist & 255u][in_lr];
     hist = (du & 255u) | (au & 63u) << FGH_ARUN_SHIFT;
-    const bool special = (au & 64u) != 0u;                              // Attack released after >= 59 held frames
-    const bool atk_down = (au & 128u) != 0u;                            // IsAttackInput(inputDown[0])
-    const bool dash_f = (du & (SIDE == 0 ? 0x200u : 0x100u)) != 0u;     // P1's forward is Right, P2's is Left
-    const bool dash_b = (du & (SIDE == 0 ? 0x100u : 0x200u)) != 0u;
-    const bool back = (in & (SIDE == 0 ? 1u : 2u)) != 0u;
-
     // ---- IncrementActionFrame (Fighter.cs:140-166): sprite shake decays (sign flips, magnitude - 1); hit stun ticks
     //      down and freezes the frame counter, else the frame counter advances ----
-    const bool stunned = (pk & M_STUN) != 0u;
-    uint32_t delta = stunned ? (0u - M_STUN1) : M_FRAME1;
+    uint32_t delta = (pk & M_STUN) ? (0u - M_STUN1) : M_FRAME1;
     if (pk & M_SHMAG) { delta -= M_SHMAG1; pk ^= M_SHSIGN; }
     pk += delta;
     const bool stun0 = (pk & M_STUN) == 0u;
-    const bool ended = !stunned && (pk & FGP_CARRY_END);                // currentActionFrame >= frameCount (Fighter.cs:90)
-    const bool always = (pk & FGP_CARRY_ALWAYS) != 0u;
-    const bool normal = (pk & FGP_CARRY_NORMAL) != 0u;                  // current action is N_ATTACK / B_ATTACK
 
-    // ---- UpdateActionRequest (Fighter.cs:201-286) with the RequestAction chain (Fighter.cs:472-510) collapsed:
-    //      when the action ended or is alwaysCancelable the FIRST request of the chain wins, otherwise the only
-    //      effect a request can have is buffering N_SPECIAL inside a cancel window. ----
-    bool want_buffer = false, set, differs = true;
+    // ---- UpdateActionRequest (Fighter.cs:201-286) with the RequestAction chain (Fighter.cs:472-510) collapsed: when the
+    //      action ended or is alwaysCancelable ("free") the FIRST request of the chain wins, otherwise the only effect
+    //      a request can have is buffering N_SPECIAL inside a cancel window.  The carry bit END is only ever set while
+    //      the fighter is out of hit stun, so it means "currentActionFrame >= frameCount now" (Fighter.cs:90). ----
     uint32_t req;
-    // Forced requests, both only once hit stun is over: the reserved GUARD_BREAK (Fighter.cs:212-218), else the
-    // buffered cancel into N_SPECIAL after a connected hit (Fighter.cs:222-229).  Rare: one test keeps them off the
-    // common path.
-    bool is_forced = false;
-    if (pk & (M_RSV | M_BUF)) {
-        if (!(pk & M_STUN) && ((pk & M_RSV) || (pk & M_HIT))) {
-            is_forced = true;
-            req = (pk & M_RSV) ? (uint32_t)GUARD_BREAK : (uint32_t)N_SPECIAL;
-            set = true;
-        }
-    }
-    if (!is_forced) {
+    bool differs, set, want_buffer;
+    if (LUT_REQUEST) {
+        // one lookup (tools/gen_kernel_tables.py build_request_lut); its index is assembled from bit-fields that are
+        // already integers: this frame's Left/Right, the run-length and dash-automaton outputs, and the packed word's
+        // isReserveProximityGuard and carry bits
+        static_assert(FGP_RPROX_SHIFT == 23 && FGP_CARRY_END == (1u << 28), "request LUT index assembly");
+        const uint32_t ridx = in_lr | ((pk >> 21) & 0x384u) | ((au >> 3) & 0x18u) | ((du >> 3) & 0x60u);
+        const uint32_t rq = T.req_lut[SIDE][ridx];
+        req = rq & 15u;
+        differs = ((pk ^ (req << FGP_ACT_SHIFT)) & M_ACT) != 0u;
+        set = (rq & FT_REQ_FREE) && ((rq & FT_REQ_ENDED) || differs);
+        want_buffer = (rq & FT_REQ_WANT_BUFFER) != 0u;
+    } else {
+        const bool special = (au & 64u) != 0u;                          // Attack released after >= 59 held frames
+        const bool atk_down = (au & 128u) != 0u;                        // IsAttackInput(inputDown[0])
+        const bool dash_f = (du & (SIDE == 0 ? 0x200u : 0x100u)) != 0u; // P1's forward is Right, P2's is Left
+        const bool dash_b = (du & (SIDE == 0 ? 0x100u : 0x200u)) != 0u;
+        const bool ended = (pk & FGP_CARRY_END) != 0u;
+        const bool in_normal = (pk & FGP_CARRY_NORMAL) && !ended;
         const uint32_t dir = in_lr != 0u ? 1u : 0u;
-        const bool in_normal = normal && !ended;
         // attack request: N_ATTACK 5 / B_ATTACK 6 / N_SPECIAL 7 / B_SPECIAL 8 (the B_ variant when a direction is held)
         const uint32_t areq = special ? N_SPECIAL + dir : in_normal ? (uint32_t)N_SPECIAL : N_ATTACK + dir;
         // movement request by (Left, Right, isReserveProximityGuard): byte LUT in two registers (PRMT)
         const uint32_t mv = byte_lut(SIDE == 0 ? 0x00010200u : 0x00020100u, SIDE == 0 ? 0x00010e00u : 0x000e0100u,
                                      in_lr | ((pk >> (FGP_RPROX_SHIFT - 2)) & 4u));
         req = (special || atk_down) ? areq : dash_f ? (uint32_t)DASH_FORWARD : dash_b ? (uint32_t)DASH_BACKWARD : mv;
-        const bool free_to_switch = ended || always;
+        const bool free_to_switch = ended || (pk & FGP_CARRY_ALWAYS);
         differs = ((pk ^ (req << FGP_ACT_SHIFT)) & M_ACT) != 0u;
         set = free_to_switch && (ended || differs);
         want_buffer = !free_to_switch && req == N_SPECIAL;
-        pk = (pk & ~(M_INBACK | M_RPROX)) | (back ? M_INBACK : 0u);     // isInputBackward = back; reserve flag consumed
+    }
+    const bool normal = (pk & FGP_CARRY_NORMAL) != 0u;                  // current action is N_ATTACK / B_ATTACK
+    // Forced requests take precedence, both only once hit stun is over: the reserved GUARD_BREAK (Fighter.cs:212-218),
+    // else the buffered cancel into N_SPECIAL after a connected hit (Fighter.cs:222-229); they return before the
+    // isInputBackward / isReserveProximityGuard bookkeeping.
+    if ((pk & (M_RSV | M_BUF)) && stun0 && ((pk & M_RSV) || (pk & M_HIT))) {
+        req = (pk & M_RSV) ? (uint32_t)GUARD_BREAK : (uint32_t)N_SPECIAL;
+        set = true; differs = true; want_buffer = false;
+    } else {
+        // isInputBackward = holding back now; the proximity-guard reservation is consumed (Fighter.cs:271-285)
+        pk = (pk & ~(M_INBACK | M_RPROX)) | (in & (SIDE == 0 ? 1u : 2u)) << (FGP_INBACK_SHIFT - (SIDE == 0 ? 0 : 1));
     }
     if (SIDE == 0) {                                                    // statistics are about P1 only
         fo.special_started = set && differs && (req - N_SPECIAL) < 2u;
@@ -203,7 +213,8 @@ FG_DEV void update_fighter(const Tables &T, uint32_t in, float &pos, float &vel,
     // ---- frame data of the (action, frame) the fighter ends up in: the low bits of the packed word are the row index ----
     const uint4 row = T.rows[pk & FGP_ROW_MASK];
     if (want_buffer) pk |= (row.z & FT_Z_CANCEL) << (FGP_BUF_SHIFT - 3);   // cancel window (Fighter.cs:492-505)
-    pk = (pk & ~FGP_CARRY_MASK) | (row.w & FGP_CARRY_MASK);
+    // refresh the carry bits; END only while out of hit stun (a stunned fighter's frame counter does not advance)
+    pk = (pk & ~FGP_CARRY_MASK) | (row.w & (stun0 ? FGP_CARRY_MASK : (FGP_CARRY_MASK & ~FGP_CARRY_END)));
 
     // ---- UpdateMovement (Fighter.cs:291-319) ----
     if (stun0) {
@@ -293,7 +304,7 @@ FG_DEV uint32_t attack_apply(uint32_t result, uint32_t &apk, uint32_t &vpk, cons
             | (ASIDE == 0 ? 0u : (mag ? M_SHSIGN : 0u));
         // the victim's new action starts at frame 0: never END (every hit action lasts >= 15 frames), never
         // ALWAYS / NORMAL -> carry bits 0
-        apk = (apk & ~M_STUN) | stun << FGP_STUN_SHIFT | M_HIT;
+        apk = (apk & ~(M_STUN | (stun ? FGP_CARRY_END : 0u))) | stun << FGP_STUN_SHIFT | M_HIT;   // END is void in hit stun
         return res;
     }
     // NotifyInProximityGuardRange: latch only while the victim holds back (Fighter.cs:400-406)
@@ -407,7 +418,7 @@ FG_DEV void make_outputs(const Env &e, StepOutputs &o) {
 
 // One fight frame for one env (everything between "inputs known" and "state after the frame").
 // Sets `terminal`, accumulates the Python float64 reward into `reward`, bumps the packed statistics.
-template <bool P1BOT, bool P2BOT, bool DENSE>
+template <bool P1BOT, bool P2BOT, bool DENSE, bool LUT_REQUEST>
 FG_DEV void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, double &reward, bool &terminal, StatAcc &acc) {
     // state the bots will be shown after this frame (previous call's capture == state before this frame)
     float pre_dist = 0.0f;
@@ -424,8 +435,8 @@ FG_DEV void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, 
         e.misc = (e.misc & ~(63u << FGM_REC1_SHIFT)) | (in1 + in2 * 8u) << FGM_REC1_SHIFT;
 
     FrameOut f1, f2;
-    update_fighter<0>(T, in1, e.pos1, e.vel1, e.pk1, e.hist1, f1);
-    update_fighter<1>(T, in2, e.pos2, e.vel2, e.pk2, e.hist2, f2);
+    update_fighter<0, LUT_REQUEST>(T, in1, e.pos1, e.vel1, e.pk1, e.hist1, f1);
+    update_fighter<1, LUT_REQUEST>(T, in2, e.pos2, e.vel2, e.pk2, e.hist2, f2);
 
     // ---- UpdatePushCharacterVsCharacter (BattleCore.cs:483-501), UnityEngine.Rect semantics: x = left edge, strict ----
     const BoxCfg &b1 = boxcfg_of(T, f1.z), &b2 = boxcfg_of(T, f2.z);

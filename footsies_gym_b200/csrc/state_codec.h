@@ -44,7 +44,8 @@
 #define FGP_SHAKE_SHIFT 24   // 4 bits sign-magnitude: |spriteShakePosition| in [24:27), negative in [27]
 #define FGP_SHAKE_SIGN_SHIFT 27
 // carry bits: facts about (action, frame) that the NEXT frame's request logic needs, copied from the row (row.w)
-#define FGP_CARRY_END (1u << 28)     // the action is over as soon as the frame counter increments (Fighter.cs:90)
+#define FGP_CARRY_END (1u << 28)     // the action is over as soon as the frame counter increments (Fighter.cs:90);
+                                     // never set while in hit stun (the counter is frozen then)
 #define FGP_CARRY_ALWAYS (1u << 29)  // alwaysCancelable
 #define FGP_CARRY_NORMAL (1u << 30)  // N_ATTACK / B_ATTACK
 #define FGP_CARRY_MASK (7u << 28)
@@ -144,7 +145,7 @@ static inline int fg_encode_fighter(const fg_fighter_state *s, FgVec4 *v) {
     if (!(s->buffer_id == -1 || s->buffer_id == 110) || !(s->reserve_id == -1 || s->reserve_id == 310)) return -1;
     if (s->shake < -6 || s->shake > 6 || s->attack_run < 0 || s->attack_run > 59) return -1;
     if ((s->hist_left | s->hist_right) >> 16) return -1;
-    uint32_t carry = (frame + 1 >= frame_count ? FGP_CARRY_END : 0u) | ((FG_ACTION_INFO_H[idx] >> 9) & 1u ? FGP_CARRY_ALWAYS : 0u)
+    uint32_t carry = ((frame + 1 >= frame_count && s->hitstun == 0) ? FGP_CARRY_END : 0u) | ((FG_ACTION_INFO_H[idx] >> 9) & 1u ? FGP_CARRY_ALWAYS : 0u)
                    | ((idx == FT_IDX_N_ATTACK || idx == FT_IDX_B_ATTACK) ? FGP_CARRY_NORMAL : 0u);
     uint32_t mag = (uint32_t)(s->shake < 0 ? -s->shake : s->shake);
     uint32_t p = (uint32_t)idx << FGP_ACT_SHIFT | (uint32_t)frame << FGP_FRAME_SHIFT

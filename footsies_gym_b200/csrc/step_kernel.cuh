@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
         const int K = KFUSED ? p.frame_skip : 1;
         for (int kk = 0; kk < K; kk++) {
             if (run && !terminal) {
-                simulate_frame<P1BOT, P2BOT, DENSE>(T, e, in1, in2, reward, terminal, acc);
+                simulate_frame<P1BOT, P2BOT, DENSE, KFUSED>(T, e, in1, in2, reward, terminal, acc);
                 acc.s += 1u << 24;                                      // byte lane 3: env-frames simulated (<= 120 per flush)
                 if (KFUSED) {
                     if (P1BOT) in1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u;

@@ -78,6 +78,8 @@ inline void build_tables(Tables &t) {
     }
     static const uint16_t dash_fsm[FT_NUM_DASH_STATES][4] = FT_DASH_FSM_INIT;
     static const uint8_t arun_lut[64 * 8] = FT_ARUN_LUT_INIT;
+    static const uint8_t req_lut[2][1024] = FT_REQ_LUT_INIT;
+    memcpy(t.req_lut, req_lut, sizeof req_lut);
     for (int i = 0; i < FT_NUM_DASH_STATES; i++) for (int d = 0; d < 4; d++) t.dash_fsm[i][d] = dash_fsm[i][d];
     memcpy(t.arun_lut, arun_lut, sizeof arun_lut);
     // index = clamp(ceil(2 * distance), 4, 9) - 4

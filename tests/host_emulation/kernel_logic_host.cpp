@@ -73,7 +73,8 @@ static void reset_t(he_handle *h, const uint8_t *mask) {
     }
 }
 
-template <bool B1, bool B2, bool DENSE>
+// FUSED mirrors the kernel's KFUSED template parameter (frame_skip > 1), which also selects the request-LUT variant
+template <bool B1, bool B2, bool DENSE, bool FUSED>
 static void step_t(he_handle *h, const uint8_t *a1, const uint8_t *a2, const uint8_t *step_mask) {
     for (int i = 0; i < h->n; i++) {
         if (step_mask && !step_mask[i]) continue;
@@ -100,7 +101,7 @@ static void step_t(he_handle *h, const uint8_t *a1, const uint8_t *a2, const uin
         bool terminal = false;
         for (int kk = 0; kk < h->frame_skip; kk++) {
             if (run && !terminal) {
-                simulate_frame<B1, B2, DENSE>(h->T, e, in1, in2, reward, terminal, acc);
+                simulate_frame<B1, B2, DENSE, FUSED>(h->T, e, in1, in2, reward, terminal, acc);
                 acc.s += 1u << 24;
                 if (B1) in1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u;
                 if (B2) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
@@ -143,7 +144,10 @@ void he_reset(he_handle *h, const uint8_t *mask) {
     else reset_t<false, false>(h, mask);
 }
 void he_step(he_handle *h, const uint8_t *a1, const uint8_t *a2, const uint8_t *step_mask) {
-#define GO(B1, B2) do { if (h->dense) step_t<B1, B2, true>(h, a1, a2, step_mask); else step_t<B1, B2, false>(h, a1, a2, step_mask); } while (0)
+#define GO(B1, B2) do { \
+        if (h->frame_skip > 1) { if (h->dense) step_t<B1, B2, true, true>(h, a1, a2, step_mask); else step_t<B1, B2, false, true>(h, a1, a2, step_mask); } \
+        else { if (h->dense) step_t<B1, B2, true, false>(h, a1, a2, step_mask); else step_t<B1, B2, false, false>(h, a1, a2, step_mask); } \
+    } while (0)
     if (h->p1_bot && h->p2_bot) GO(true, true);
     else if (h->p1_bot) GO(true, false);
     else if (h->p2_bot) GO(false, true);

@@ -105,12 +105,16 @@ def case_stale_intro_input_off(make_env, oracle, scale=1.0):
 
 
 def case_fused_frame_skip(make_env, oracle, k, p2_bot, scale=1.0):
-    """configs[2]: self-play, K = 4 fused per launch (plus bot / odd K variants)."""
+    """configs[2]: self-play, K = 4 fused per launch (plus bot / odd K variants).  K = 2 runs the input personalities,
+    which reach charged specials, dashes and guard breaks under frame skip (the fused kernels decide requests through
+    the request lookup table, the single-frame kernels through the select chain: both are covered)."""
     rng = np.random.default_rng(100 + k)
-    n, steps = max(64, int(4096 * scale)), 400
-    st = run_case(make_env, oracle, n, steps, p2_bot=p2_bot, frame_skip=k, tape1=tape_sticky(rng, steps, n, p_change=0.3),
-                  tape2=None if p2_bot else tape_sticky(rng, steps, n, p_change=0.3))
+    n, steps = max(64, int(4096 * scale)), 400 if k != 2 else 1200
+    tape = (lambda: tape_profiles(rng, steps, n)) if k == 2 else (lambda: tape_sticky(rng, steps, n, p_change=0.3))
+    st = run_case(make_env, oracle, n, steps, p2_bot=p2_bot, frame_skip=k, tape1=tape(), tape2=None if p2_bot else tape())
     assert st["episodes"] > 100 * scale
+    if k == 2:
+        assert st["p1_specials_neutral"] > 0 and st["guard_breaks"] > 0
 
 
 def tape_profiles(rng, steps, n):
@@ -145,4 +149,4 @@ def case_input_personalities_vs_bot_sparse(make_env, oracle, scale=1.0):
     assert st["episodes"] > 200 * scale and st["p1_specials_neutral"] > 0
 
 
-FUSED_PARAMS = [(4, False), (4, True), (3, True), (16, False)]
+FUSED_PARAMS = [(4, False), (4, True), (3, True), (16, False), (2, False), (2, True)]

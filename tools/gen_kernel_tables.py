@@ -91,6 +91,57 @@ def build_attack_run_lut():
     return lut
 
 
+# request LUT index bits (frame_logic.cuh assembles them with three shifts): Left/Right now [0:2) |
+# isReserveProximityGuard [2] | special [3] | attack-down [4] | dash-by-Left [5] | dash-by-Right [6] | carry END [7] |
+# carry ALWAYS [8] | carry NORMAL [9]
+REQ_FREE, REQ_WANT_BUFFER, REQ_ENDED = 16, 32, 64
+
+
+def build_request_lut(idx_of):
+    """Fighter.UpdateActionRequest (Fighter.cs:201-286) with the RequestAction chain (Fighter.cs:472-510) collapsed, as a
+    lookup per side: [side][index] = requested action index | FREE (the action ended or is alwaysCancelable, so the
+    first request of the chain wins) | WANT_BUFFER (not free and the request is N_SPECIAL: buffered if the frame is
+    inside a cancel window) | ENDED.  Priority: special release (-> B_SPECIAL if a direction is held, else N_SPECIAL),
+    attack press (-> N_SPECIAL while in N/B_ATTACK, else B_ATTACK / N_ATTACK), forward dash, backward dash, movement
+    (both or no direction -> STAND, forward -> FORWARD, back -> GUARD_PROXIMITY if reserved else BACKWARD)."""
+    A = idx_of
+    luts = []
+    for side in (0, 1):                       # P1 faces right: forward = Right (2); P2 faces left: forward = Left (1)
+        fwd_bit, back_bit = (2, 1) if side == 0 else (1, 2)
+        lut = []
+        for idx in range(1024):
+            lr = idx & 3
+            rprox, special, down = (idx >> 2) & 1, (idx >> 3) & 1, (idx >> 4) & 1
+            dash_l, dash_r = (idx >> 5) & 1, (idx >> 6) & 1
+            ended, always, normal = (idx >> 7) & 1, (idx >> 8) & 1, (idx >> 9) & 1
+            dash_f, dash_b = (dash_r, dash_l) if side == 0 else (dash_l, dash_r)
+            dirn = 1 if lr else 0
+            in_normal = normal and not ended
+            fwd, back = bool(lr & fwd_bit), bool(lr & back_bit)
+            if special:
+                req = A["N_SPECIAL"] + dirn               # B_SPECIAL = N_SPECIAL + 1
+            elif down:
+                req = A["N_SPECIAL"] if in_normal else A["N_ATTACK"] + dirn
+            elif dash_f:
+                req = A["DASH_FORWARD"]
+            elif dash_b:
+                req = A["DASH_BACKWARD"]
+            elif fwd and back:
+                req = A["STAND"]
+            elif fwd:
+                req = A["FORWARD"]
+            elif back:
+                req = A["GUARD_PROXIMITY"] if rprox else A["BACKWARD"]
+            else:
+                req = A["STAND"]
+            free = ended or always
+            want_buffer = (not free) and req == A["N_SPECIAL"]
+            lut.append(req | (REQ_FREE if free else 0) | (REQ_WANT_BUFFER if want_buffer else 0) | (REQ_ENDED if ended else 0))
+        luts.append(lut)
+    assert A["B_SPECIAL"] == A["N_SPECIAL"] + 1 and A["B_ATTACK"] == A["N_ATTACK"] + 1
+    return luts
+
+
 ROW_FRAMES = 64        # rows per action; the 6-bit frame field of the packed fighter word indexes them directly
 
 # row.z bit layout
@@ -306,9 +357,10 @@ def build(consts, attacks, actions):
             r += 0.3
         step_reward.append(r)
     dash_states, dash_table = build_dash_fsm()
+    req_lut = build_request_lut({a["actionName"]: i for i, a in enumerate(actions)})
     return dict(rows=rows, action_info=action_info, cfg_rows=cfg_rows, cfg_tab=cfg_tab, atk_rows=atk_rows, cum_vals=vals,
                 cum_next=cum_next, term=term, step_reward=step_reward, hurt_tab=hurt_tab, push_tab=push_tab,
-                dash_states=dash_states, dash_table=dash_table, arun_lut=build_attack_run_lut())
+                dash_states=dash_states, dash_table=dash_table, arun_lut=build_attack_run_lut(), req_lut=req_lut)
 
 
 
@@ -357,6 +409,12 @@ def emit(consts, attacks, actions, path):
     w("#define FT_DASH_FSM_INIT {%s}" % ", ".join("{%s}" % ", ".join("0x%03x" % v for v in r) for r in t["dash_table"]))
     w("/* [state] = since | runlen << 4 | lastdir << 8 (host side: expansion to / from a Left/Right bit history) */")
     w("#define FT_DASH_STATE_INFO_INIT {%s}" % ", ".join("0x%03x" % (st[0] | st[1] << 4 | st[2] << 8) for st in t["dash_states"]))
+    w("/* request lookup [side][Left/Right | rprox << 2 | special << 3 | attack-down << 4 | dash-by-Left << 5 | dash-by-Right << 6 |")
+    w(" * END << 7 | ALWAYS << 8 | NORMAL << 9] = requested action | FREE 16 | WANT_BUFFER 32 | ENDED 64 (build_request_lut) */")
+    w("#define FT_REQ_FREE %du" % REQ_FREE)
+    w("#define FT_REQ_WANT_BUFFER %du" % REQ_WANT_BUFFER)
+    w("#define FT_REQ_ENDED %du" % REQ_ENDED)
+    w("#define FT_REQ_LUT_INIT {%s}" % ", ".join("{%s}" % ", ".join(str(v) for v in l) for l in t["req_lut"]))
     w("/* attack run length [run * 8 + input] = new run | special << 6 | attack-down << 7 */")
     w("#define FT_ARUN_LUT_INIT {%s}" % ", ".join(str(v) for v in t["arun_lut"]))
     w("/* dense reward automaton (footsies.py:388-405): cumulative float64 values, next index per guard-drop code, terminal reward */")
