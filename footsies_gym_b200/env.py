@@ -316,11 +316,10 @@ class FootsiesEnv:
         # footsies.py:533-535: append the newest state, pop the oldest (queue length frame_delay + 1);
         # an env that was just auto-reset restarts with a queue full of its first state (footsies.py:502-504)
         d = self.frame_delay + 1
-        was_reset = self.info_frame == -1
-        if bool(was_reset.any()):
-            self._ring_obs[:, was_reset] = self.obs[was_reset]
-            self._ring_frame[:, was_reset] = self.info_frame[was_reset]
-            self._ring_misc[:, was_reset] = self.info_misc[was_reset]
+        was_reset = self.info_frame == -1       # no host sync: masked writes for every env, every step
+        self._ring_obs.copy_(torch.where(was_reset[None, :, None], self.obs[None], self._ring_obs))
+        self._ring_frame.copy_(torch.where(was_reset[None, :], self.info_frame[None], self._ring_frame))
+        self._ring_misc.copy_(torch.where(was_reset[None, :, None], self.info_misc[None], self._ring_misc))
         p = self._ring_pos
         self._ring_obs[p].copy_(self.obs)
         self._ring_frame[p].copy_(self.info_frame)

@@ -45,7 +45,7 @@ def main():
     base = int(inst[0][col["Address"]], 16)
 
     with tempfile.TemporaryDirectory() as td:
-        subprocess.run(["cuobjdump", "-xelf", "all", a.lib], cwd=td, capture_output=True)
+        subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(a.lib)], cwd=td, capture_output=True)
         cubin = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
         dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cubin)], capture_output=True, text=True).stdout
     # walk the function's listing: "//## File "...", line N" markers (possibly with inlined-at), then instructions
