@@ -1,5 +1,7 @@
 // footsies_kernels.cu -- C ABI of the batched FOOTSIES simulator (include/footsies_b200.h) on top of the kernels in
 // step_kernel.cuh.
+#include <stdlib.h>
+
 #include "step_kernel.cuh"
 
 using namespace fg;
@@ -25,6 +27,7 @@ struct fg_handle {
     int sm_count;
     int64_t launches;
     uint8_t *d_mask;       // staging for fg_reset_host
+    int large_shape_min_envs;
 };
 
 namespace {
@@ -49,6 +52,7 @@ Params make_params(const fg_handle *h) {
     p.first_env_index = h->cfg.first_env_index;
     p.n = h->cfg.num_envs; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
     p.stale_intro = h->cfg.stale_intro_input;
+    p.large_shape_min_envs = h->large_shape_min_envs;
     return p;
 }
 
@@ -114,6 +118,9 @@ int32_t fg_create(const fg_config *cfg, fg_handle **out) {
     h->bound = false;
     h->launches = 0;
     h->d_mask = nullptr;
+    // developer / test knob: force the large CTA shapes onto small batches (or the small shape onto large ones)
+    h->large_shape_min_envs = kLargeShapeMinEnvs;
+    if (const char *v = getenv("FOOTSIES_B200_LARGE_SHAPE_MIN_ENVS")) h->large_shape_min_envs = atoi(v);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     h->sm_count = prop.multiProcessorCount;

@@ -74,6 +74,7 @@ struct Params {
     const uint8_t *step_mask;
     long long seed_base, first_env_index;
     int n, frame_skip, autoreset, stale_intro;
+    int large_shape_min_envs;   // host side only: batch size from which the large CTA shapes are launched
 };
 
 __device__ __forceinline__ void write_outputs(const Params &p, int i, const Env &e, float reward, bool terminated) {
@@ -339,7 +340,7 @@ cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
 }
 template <bool KF, bool B1, bool B2, bool D, bool M>
 cudaError_t launch_step(int sm_count, cudaStream_t s, const Params &p) {
-    if (p.n < kLargeShapeMinEnvs) return launch_step_shape<ShapeSmall, KF, B1, B2, D, M>(sm_count, s, p);
+    if (p.n < p.large_shape_min_envs) return launch_step_shape<ShapeSmall, KF, B1, B2, D, M>(sm_count, s, p);
     if (KF) return launch_step_shape<ShapeLargeFused, KF, B1, B2, D, M>(sm_count, s, p);
     return launch_step_shape<ShapeLargeSingle, KF, B1, B2, D, M>(sm_count, s, p);
 }
