@@ -378,8 +378,9 @@ def main():
             e = FootsiesEnv(num_envs=n_envs, device=dev, opponent=None, seed=0)
             pol = MLPPolicy().to(dev)
             out = {}
-            for graph in (True, False):
-                col = RolloutCollector(e, pol, horizon=horizon, use_cuda_graph=graph)
+            for name, graph, fused in (("fused_policy_kernel_cuda_graph", True, True), ("torch_policy_cuda_graph", True, False),
+                                       ("torch_policy_eager", False, False)):
+                col = RolloutCollector(e, pol, horizon=horizon, use_cuda_graph=graph, fused=fused)
                 col.collect()
                 torch.cuda.synchronize(dev)
                 f0 = e.episode_stats()["env_frames"]
@@ -391,11 +392,11 @@ def main():
                 torch.cuda.synchronize(dev)
                 ms = s0.elapsed_time(s1)
                 fr = e.episode_stats()["env_frames"] - f0
-                out["cuda_graph" if graph else "eager"] = {"env_frames_per_sec": fr / (ms * 1e-3),
-                                                           "ms_per_horizon": ms / reps}
+                out[name] = {"env_frames_per_sec": fr / (ms * 1e-3), "ms_per_horizon": ms / reps}
             e.close()
-            out.update(envs=n_envs, horizon=horizon, policy="torch MLP 8-64-64-8 fp32, multinomial sampling",
-                       note="per GPU; policy forward + sampling + rollout-buffer writes inside the timed region")
+            out.update(envs=n_envs, horizon=horizon, policy="MLP 8-64-64-8 tanh fp32, categorical sampling",
+                       note="per GPU; policy forward + sampling + rollout-buffer writes inside the timed region; the fused "
+                            "path is 2 launches per step (fg_policy_mlp_sample + fg_step) with zero-copy rollout buffers")
             return out
         extra["E_ppo_rollout_16384x128"] = ppo_rollout()
 

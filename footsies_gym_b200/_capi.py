@@ -64,7 +64,7 @@ _lib = None
 # every symbol include/footsies_b200.h declares
 EXPORTS = ["fg_abi_version", "fg_last_error", "fg_algorithmic_bytes_per_env_step", "fg_create", "fg_destroy",
            "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_get_state",
-           "fg_set_state", "fg_read_stats", "fg_launch_count"]
+           "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_last_error"]
 
 
 def load(build_if_missing=True):
@@ -107,6 +107,9 @@ def load(build_if_missing=True):
     L.fg_read_stats.argtypes = [vp, vp, vp]
     L.fg_launch_count.restype = i64
     L.fg_launch_count.argtypes = [vp]
+    L.fg_policy_mlp_sample.restype = i32
+    L.fg_policy_mlp_sample.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+    L.fg_policy_last_error.restype = C.c_char_p
     if L.fg_abi_version() != 1:
         raise FootsiesLibraryError("libfootsies_b200.so ABI version mismatch")
     _lib = L

@@ -29,7 +29,8 @@ def _nvcc():
 
 
 def sources():
-    return [os.path.join(CSRC, "footsies_kernels.cu"), os.path.join(CSRC, "step_instances.cu")]
+    return [os.path.join(CSRC, "footsies_kernels.cu"), os.path.join(CSRC, "step_instances.cu"),
+            os.path.join(CSRC, "policy_kernel.cu")]
 
 
 def deps():
@@ -48,7 +49,9 @@ def is_stale(lib_path=None):
 
 def translation_units():
     """(object name, source, extra defines)"""
-    units = [("abi.o", os.path.join(CSRC, "footsies_kernels.cu"), [])]
+    # the policy kernel is ordinary fp32 inference: FMA contraction allowed there
+    units = [("abi.o", os.path.join(CSRC, "footsies_kernels.cu"), []),
+             ("policy.o", os.path.join(CSRC, "policy_kernel.cu"), ["-fmad=true"])]
     for kf in (0, 1):
         for b1 in (0, 1):
             for b2 in (0, 1):

@@ -290,6 +290,26 @@ class FootsiesEnv:
             self.actions_p2 = actions_p2
         self._bind()
 
+    def bind_outputs(self, obs: Optional[torch.Tensor] = None, reward: Optional[torch.Tensor] = None,
+                     terminated: Optional[torch.Tensor] = None):
+        """Zero-copy outputs: make the kernel write its observations / rewards / termination flags straight into the
+        given device tensors from now on (e.g. slot t of a rollout buffer): obs float32 [N, 8], reward float32 [N],
+        terminated bool or uint8 [N], all contiguous.  `env.obs` and the observation dicts follow."""
+        n, dev = self.num_envs, self.device
+        for t, shape, dts in ((obs, (n, 8), (torch.float32,)), (reward, (n,), (torch.float32,)),
+                              (terminated, (n,), (torch.bool, torch.uint8))):
+            if t is not None and (t.dtype not in dts or tuple(t.shape) != shape or t.device != dev or not t.is_contiguous()):
+                raise ValueError(f"bound output tensors must be contiguous {dts} {shape} on the env's device")
+        if obs is not None:
+            self.obs = obs
+            self._obs_dict = self._make_obs_dict(self.obs)
+            self._info_dict = self._make_info_dict(self.info_frame, self.info_misc, self._obs_dict)
+        if reward is not None:
+            self.reward = reward
+        if terminated is not None:
+            self.terminated = terminated
+        self._bind()
+
     def step_bound(self):
         """step() without any action copy: the kernel reads the tensors given to bind_actions()."""
         if not self.has_reset:

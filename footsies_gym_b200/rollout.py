@@ -1,29 +1,38 @@
-"""On-device rollout collection (BASELINE.json configs[4]: a torch MLP policy consuming `env.obs` in place).
+"""On-device rollout collection (BASELINE.json configs[4]: an MLP policy consuming the observation tensor in place).
 
 The reference's training loops step one socket-connected game per process and move every observation through JSON
-(footsies.py:518-570).  Here a whole horizon of policy-forward -> sample -> FootsiesEnv.step for N battles is a
-sequence of device kernels with no host round trip: the policy reads the kernel's observation tensor directly, writes
-its sampled actions into the uint8 tensor the step kernel is bound to, and the per-step transition is appended to
-pre-allocated [horizon, N, ...] buffers.  With `use_cuda_graph=True` the horizon is captured once into a CUDA graph
-and replayed, which removes the per-step launch latency that dominates at 16k envs per GPU.
+(footsies.py:518-570, 633-661).  Here a whole horizon of policy-forward -> sample -> FootsiesEnv.step for N battles is
+a sequence of device kernels with no host round trip, captured once into a CUDA graph and replayed.
 
-PyTorch is plumbing here (the policy is the user's model); the simulator step inside the loop is fg_step.
+Two policy paths:
+  * any torch callable `policy(obs[N, 8]) -> logits[N, 8]` (a dozen small torch kernels per step);
+  * `MLPPolicy` with `fused=True` (default when the policy is an MLPPolicy): one hand-written kernel per step
+    (csrc/policy_kernel.cu, fg_policy_mlp_sample) does scale -> 8-H-H-8 tanh MLP -> log-softmax -> sample, and the
+    rollout needs no copies at all: the step kernel is re-bound, per captured launch, to write observation t + 1,
+    reward t and done t straight into the rollout buffers, and the policy kernel reads observation t from there.
+    Per step: 2 launches (policy, simulator step).
+
+PyTorch is plumbing here (parameters, buffers, CUDA graph); the simulator step inside the loop is fg_step.
 """
+import ctypes as C
 from typing import Callable, Optional
 
 import torch
 
+from . import _capi
 from .env import FootsiesEnv
 
-# FootsiesNormalized scales (wrappers/normalization.py:28-55): guard / 3, move index as is, move_frame / 55, position / 4.6
+# FootsiesNormalized scales (wrappers/normalization.py:28-55): guard / 3, move index / 14, move_frame / 55, position / 4.6
 _OBS_SCALE = (1 / 3.0, 1 / 3.0, 1 / 14.0, 1 / 14.0, 1 / 55.0, 1 / 55.0, 1 / 4.6, 1 / 4.6)
 
 
 class MLPPolicy(torch.nn.Module):
-    """8 -> hidden -> hidden -> 8 logits over the 2^3 input combinations (wrappers/action_comb_disc.py:13-18)."""
+    """8 -> hidden -> hidden -> 8 logits over the 2^3 input combinations (wrappers/action_comb_disc.py:13-18).
+    hidden in {32, 64, 128} can be run by the fused inference kernel."""
 
     def __init__(self, hidden: int = 64):
         super().__init__()
+        self.hidden = int(hidden)
         self.register_buffer("scale", torch.tensor(_OBS_SCALE, dtype=torch.float32))
         self.net = torch.nn.Sequential(torch.nn.Linear(8, hidden), torch.nn.Tanh(), torch.nn.Linear(hidden, hidden),
                                        torch.nn.Tanh(), torch.nn.Linear(hidden, 8))
@@ -31,59 +40,91 @@ class MLPPolicy(torch.nn.Module):
     def forward(self, obs: torch.Tensor) -> torch.Tensor:
         return self.net(obs * self.scale)
 
+    def fused_sample(self, obs: torch.Tensor, actions: torch.Tensor, logp: Optional[torch.Tensor], seed: int, counter: int,
+                     counter_base: Optional[torch.Tensor] = None, obs_copy: Optional[torch.Tensor] = None):
+        """One launch of fg_policy_mlp_sample on the current stream: actions (uint8 [N]) and logp (float32 [N]) are
+        written in place; sampling is a pure function of (seed, counter + counter_base[0], env index); counter_base
+        is an optional int64 device tensor (bumped between CUDA-graph replays)."""
+        lib = _capi.load()
+        l1, l2, l3 = self.net[0], self.net[2], self.net[4]
+        ts = [obs, self.scale, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
+        for t in ts:
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != obs.device:
+                raise ValueError("fused policy inference needs contiguous float32 tensors on one device")
+        if actions.dtype != torch.uint8 or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous uint8 tensor")
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        rc = lib.fg_policy_mlp_sample(*[ptr(t) for t in ts], self.hidden, obs.shape[0], int(seed) & (2**64 - 1),
+                                      int(counter), ptr(counter_base), ptr(actions), ptr(logp), ptr(obs_copy),
+                                      C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+        if rc != 0:
+            raise _capi.FootsiesLibraryError(lib.fg_policy_last_error().decode())
+
 
 class RolloutCollector:
-    """Collects `horizon` steps of (obs, action, log-prob, reward, done) for every env of one GPU, entirely on device."""
+    """Collects `horizon` steps of (obs, action, log-prob, reward, done) for every env of one GPU, entirely on device.
+
+    Buffers (overwritten by every collect()): obs [horizon + 1, N, 8] (obs[t] is what the policy saw at step t, obs[-1]
+    the observation after the last step), actions uint8 [horizon, N], logp / rewards float32 [horizon, N], dones bool."""
 
     def __init__(self, env: FootsiesEnv, policy: Callable[[torch.Tensor], torch.Tensor], horizon: int = 128,
-                 use_cuda_graph: bool = True, generator: Optional[torch.Generator] = None):
+                 use_cuda_graph: bool = True, fused: Optional[bool] = None, seed: int = 0):
         if env.by_example:
             raise ValueError("the policy drives P1: create the env with by_example=False")
+        if env.frame_delay:
+            raise ValueError("RolloutCollector binds the env's outputs directly: frame_delay must be 0")
         self.env, self.policy, self.horizon = env, policy, int(horizon)
-        n, dev = env.num_envs, env.device
-        self.obs = torch.zeros((horizon, n, 8), dtype=torch.float32, device=dev)
-        self.actions = torch.zeros((horizon, n), dtype=torch.uint8, device=dev)
-        self.logp = torch.zeros((horizon, n), dtype=torch.float32, device=dev)
-        self.rewards = torch.zeros((horizon, n), dtype=torch.float32, device=dev)
-        self.dones = torch.zeros((horizon, n), dtype=torch.bool, device=dev)
-        self._act = torch.zeros(n, dtype=torch.uint8, device=dev)     # the tensor the step kernel reads its actions from
-        env.bind_actions(self._act)
-        self._generator = generator
+        self.fused = isinstance(policy, MLPPolicy) and policy.hidden in (32, 64, 128) if fused is None else bool(fused)
+        if self.fused and not isinstance(policy, MLPPolicy):
+            raise ValueError("fused=True needs an MLPPolicy")
+        n, dev, h = env.num_envs, env.device, self.horizon
+        self.obs = torch.zeros((h + 1, n, 8), dtype=torch.float32, device=dev)
+        self.actions = torch.zeros((h, n), dtype=torch.uint8, device=dev)
+        self.logp = torch.zeros((h, n), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((h, n), dtype=torch.float32, device=dev)
+        self.dones = torch.zeros((h, n), dtype=torch.bool, device=dev)
+        self._seed = int(seed)
+        self._drawn = torch.zeros(1, dtype=torch.int64, device=dev)   # policy steps taken so far (device side: graph replays bump it)
         self._graph = None
         self.use_cuda_graph = bool(use_cuda_graph)
         if not env.has_reset:
             env.reset()
+        self.obs[h].copy_(env.obs)                                  # the observation the first step will act on
 
     @torch.no_grad()
     def _one_horizon(self):
-        env = self.env
-        for t in range(self.horizon):
-            self.obs[t].copy_(env.obs)                                 # the kernel overwrites env.obs in place next step
-            logits = self.policy(env.obs)
-            logp_all = torch.log_softmax(logits, dim=-1)
-            a = torch.multinomial(logp_all.exp(), 1, generator=self._generator).squeeze(1)
-            self.logp[t].copy_(logp_all.gather(1, a.unsqueeze(1)).squeeze(1))
-            self._act.copy_(a)                                         # int64 -> uint8 bitmask (Left 1 | Right 2 | Attack 4)
-            self.actions[t].copy_(self._act)
+        env, h = self.env, self.horizon
+        self.obs[0].copy_(self.obs[h])                              # carry the last observation over
+        for t in range(h):
+            if self.fused:
+                self.policy.fused_sample(self.obs[t], self.actions[t], self.logp[t], self._seed, t, self._drawn)
+            else:
+                logits = self.policy(self.obs[t])
+                logp_all = torch.log_softmax(logits, dim=-1)
+                a = torch.multinomial(logp_all.exp(), 1).squeeze(1)
+                self.logp[t].copy_(logp_all.gather(1, a.unsqueeze(1)).squeeze(1))
+                self.actions[t].copy_(a)                            # int64 -> uint8 bitmask (Left 1 | Right 2 | Attack 4)
+            env.bind_actions(self.actions[t])
+            env.bind_outputs(obs=self.obs[t + 1], reward=self.rewards[t], terminated=self.dones[t])
             env.step_bound()
-            self.rewards[t].copy_(env.reward)
-            self.dones[t].copy_(env.terminated)
+        self._drawn.add_(h)
 
     def collect(self):
         """Runs one horizon; returns the rollout buffers (views, overwritten by the next call)."""
+        dev = self.env.device
         if not self.use_cuda_graph:
             self._one_horizon()
         else:
             if self._graph is None:
-                stream = torch.cuda.Stream(device=self.env.device)
-                stream.wait_stream(torch.cuda.current_stream(self.env.device))
+                stream = torch.cuda.Stream(device=dev)
+                stream.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(stream):
-                    self._one_horizon()                                # warm-up outside the capture (lazy inits)
-                torch.cuda.current_stream(self.env.device).wait_stream(stream)
-                torch.cuda.synchronize(self.env.device)
+                    self._one_horizon()                             # warm-up outside the capture (lazy inits)
+                torch.cuda.current_stream(dev).wait_stream(stream)
+                torch.cuda.synchronize(dev)
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._one_horizon()
             self._graph.replay()
-        return {"obs": self.obs, "actions": self.actions, "logp": self.logp, "rewards": self.rewards,
-                "dones": self.dones, "last_obs": self.env.obs}
+        return {"obs": self.obs[:self.horizon], "actions": self.actions, "logp": self.logp, "rewards": self.rewards,
+                "dones": self.dones, "last_obs": self.obs[self.horizon]}

@@ -156,6 +156,21 @@ int32_t fg_read_stats(fg_handle *h, uint64_t *out /* FG_STAT_COUNT */, void *str
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches claim). */
 int64_t fg_launch_count(fg_handle *h);
 
+/* BASELINE.json configs[4] (PPO rollout with an MLP policy reading the observation tensor in place; the reference's
+ * agents run their policy in Python between two socket round trips, footsies.py:633-661): fused inference of
+ * obs * scale -> Linear(8, H) -> tanh -> Linear(H, H) -> tanh -> Linear(H, 8) -> log-softmax -> categorical sample
+ * for every env in one launch.  All pointers are DEVICE pointers; weights are row-major [out][in] like torch.nn.Linear.
+ * hidden must be 32, 64 or 128.  actions receives the sampled index 0..7 = the input bitmask of fg_buffers.actions_p1
+ * (wrappers/action_comb_disc.py:13-18); logp (optional) its log-probability; obs_copy (optional, [num_envs][8]) a copy
+ * of obs, e.g. the rollout-buffer slot of this step.  The sample is a pure function of (seed, counter + *counter_base,
+ * env index); counter_base is an optional DEVICE word, so that a captured CUDA graph draws fresh numbers on every
+ * replay by bumping it. */
+int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
+                             const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
+                             uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
+                             float *obs_copy, void *stream);
+const char *fg_policy_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

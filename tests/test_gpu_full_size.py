@@ -141,7 +141,7 @@ def test_config_e_rollout_16384_envs_128_steps_is_replayable():
     n, horizon = 16384, 128
     torch.manual_seed(1)
     env = FootsiesEnv(num_envs=n, device=dev, seed=3)
-    col = RolloutCollector(env, MLPPolicy().to(dev), horizon=horizon, use_cuda_graph=True)
+    col = RolloutCollector(env, MLPPolicy().to(dev), horizon=horizon, use_cuda_graph=True)   # fused policy kernel, zero-copy
     col.collect()
     before = env.get_state()
     out = col.collect()

@@ -8,8 +8,8 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_rollout_is_replayable(oracle, use_graph):
+@pytest.mark.parametrize("use_graph,fused", [(False, False), (True, False), (False, True), (True, True)])
+def test_rollout_is_replayable(oracle, use_graph, fused):
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
     if not torch.cuda.is_available():
@@ -19,7 +19,7 @@ def test_rollout_is_replayable(oracle, use_graph):
     dev = torch.device("cuda:0")
     env = FootsiesEnv(num_envs=n, device=dev, seed=11)
     policy = MLPPolicy().to(dev)
-    col = RolloutCollector(env, policy, horizon=horizon, use_cuda_graph=use_graph)
+    col = RolloutCollector(env, policy, horizon=horizon, use_cuda_graph=use_graph, fused=fused)
     # the graph path warms up and captures with real env steps, so the replay twin is driven from get_state snapshots
     ref = FootsiesEnv(num_envs=n, device=dev, seed=11)
     orc = oracle.OracleBatch(n, p2_bot=True, seed=11)
@@ -44,10 +44,62 @@ def test_rollout_is_replayable(oracle, use_graph):
         assert np.array_equal(out["last_obs"].cpu().numpy(), ref.obs.cpu().numpy())
     # the oracle agrees with the replay twin on a full replay from reset of the first horizon's actions
     env2 = FootsiesEnv(num_envs=n, device=dev, seed=11)
-    col2 = RolloutCollector(env2, policy, horizon=horizon, use_cuda_graph=False)
+    col2 = RolloutCollector(env2, policy, horizon=horizon, use_cuda_graph=False, fused=fused)
     out = col2.collect()
     orc.reset()
     for t in range(horizon):
         tr = orc.step(out["actions"][t].cpu().numpy())
         assert np.array_equal(out["rewards"][t].cpu().numpy(), tr["reward"])
         assert np.array_equal(out["dones"][t].cpu().numpy().astype(np.int32), tr["terminated"])
+
+
+@pytest.mark.parametrize("hidden", [32, 64, 128])
+def test_fused_policy_kernel_matches_torch(hidden):
+    """fg_policy_mlp_sample against the torch module it replaces: the log-probability it reports for the action it drew
+    equals torch's log_softmax there (tolerance 2e-5 absolute: __expf-based tanh / exp, FMA contraction), and the
+    actions it draws follow the policy's distribution."""
+    from footsies_gym_b200.rollout import MLPPolicy
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(hidden)
+    pol = MLPPolicy(hidden).to(dev)
+    with torch.no_grad():
+        for prm in pol.net.parameters():
+            prm.mul_(3.0)                                   # a peaky, non-uniform policy
+    n = 10007                                               # ragged: not a multiple of the 32 envs a CTA handles
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    obs = torch.stack([torch.randint(0, 4, (n,), generator=g, device=dev).float(), torch.randint(0, 4, (n,), generator=g, device=dev).float(),
+                       torch.randint(0, 15, (n,), generator=g, device=dev).float(), torch.randint(0, 15, (n,), generator=g, device=dev).float(),
+                       torch.randint(0, 56, (n,), generator=g, device=dev).float(), torch.randint(0, 56, (n,), generator=g, device=dev).float(),
+                       torch.rand(n, generator=g, device=dev) * 9.2 - 4.6, torch.rand(n, generator=g, device=dev) * 9.2 - 4.6], dim=1).contiguous()
+    actions = torch.zeros(n, dtype=torch.uint8, device=dev)
+    logp = torch.zeros(n, dtype=torch.float32, device=dev)
+    copy = torch.zeros_like(obs)
+    base = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.no_grad():
+        ref = torch.log_softmax(pol(obs), dim=-1)
+    pol.fused_sample(obs, actions, logp, seed=5, counter=0, counter_base=base, obs_copy=copy)
+    torch.cuda.synchronize()
+    assert torch.equal(copy, obs) and int(actions.max()) <= 7
+    got = ref.gather(1, actions.long().unsqueeze(1)).squeeze(1)
+    assert float((got - logp).abs().max()) < 2e-5
+    # determinism and the device-side counter: same (seed, counter) -> same draw; counter + base is what matters
+    a2 = torch.zeros_like(actions)
+    pol.fused_sample(obs, a2, None, seed=5, counter=0, counter_base=base)
+    assert torch.equal(a2, actions)
+    base.fill_(3)
+    a3 = torch.zeros_like(actions)
+    pol.fused_sample(obs, a3, None, seed=5, counter=0, counter_base=base)
+    a4 = torch.zeros_like(actions)
+    pol.fused_sample(obs, a4, None, seed=5, counter=3, counter_base=None)
+    assert torch.equal(a3, a4) and not torch.equal(a3, actions)
+    # distribution: one observation repeated, 200 000 draws, compared with the softmax probabilities
+    m = 200_000
+    one = obs[:1].expand(m, 8).contiguous()
+    acts = torch.zeros(m, dtype=torch.uint8, device=dev)
+    pol.fused_sample(one, acts, None, seed=9, counter=7)
+    freq = torch.bincount(acts.long(), minlength=8).double() / m
+    prob = ref[0].exp().double()
+    assert float((freq - prob).abs().max()) < 5e-3, (freq.tolist(), prob.tolist())
