@@ -19,6 +19,7 @@ namespace {
 
 constexpr int kPolThreads = 128;       // 32 envs x 4 threads per CTA
 constexpr int kMaxHidden = 128;
+constexpr int kEnvsPerThread = 2;
 
 __device__ __forceinline__ float fast_tanh(float x) {
     // tanh(x) = 1 - 2 / (exp(2x) + 1); __expf keeps the relative error ~1e-6, far below what PPO's ratios resolve
@@ -47,92 +48,159 @@ struct PolicyParams {
     int n, hidden;
 };
 
+// Shared-memory layout of one layer's weights for the "4 threads per env" mapping: thread `part` owns the output units
+// part * Q .. part * Q + Q - 1 and needs, for every input k, its Q weights as contiguous 128-bit words:
+//   ws[(k * 4 + part) * kPad + j] = W[part * Q + j][k]       (kPad = Q rounded up so that the 4 parts of a quarter-warp
+// hit disjoint banks: 16-float segments at a 20-float pitch start at banks 0, 20, 8, 28)
+template <int Q> struct Pitch { static constexpr int v = Q + 4; };
+
 template <int H>
 __global__ void __launch_bounds__(kPolThreads) policy_mlp_sample_kernel(const PolicyParams p) {
     static_assert(H % 16 == 0 && H <= kMaxHidden, "hidden size");
     constexpr int Q = H / 4;                       // hidden units owned by one of the 4 threads of an env
+    constexpr int P = Pitch<Q>::v;
     extern __shared__ __align__(16) float sm[];
-    float *w1 = sm;                                // [H][8]
-    float *w2 = w1 + H * 8;                        // [H][H]
-    float *w3 = w2 + H * H;                        // [8][H]
-    float *b1 = w3 + 8 * H, *b2 = b1 + H, *b3 = b2 + H, *sc = b3 + 8;
-    for (int i = threadIdx.x; i < H * 8; i += kPolThreads) { w1[i] = p.w1[i]; w3[i] = p.w3[i]; }
-    for (int i = threadIdx.x; i < H * H; i += kPolThreads) w2[i] = p.w2[i];
+    float *w1 = sm;                                // [8 inputs][4 parts][P]
+    float *w2 = w1 + 8 * 4 * P;                    // [H inputs][4 parts][P]
+    float *w3 = w2 + H * 4 * P;                    // [8 outputs][4 parts][P]: W3[o][part * Q + j]
+    float *b1 = w3 + 8 * 4 * P, *b2 = b1 + H, *b3 = b2 + H, *sc = b3 + 8;
+    for (int i = threadIdx.x; i < H * 8; i += kPolThreads) {
+        const int u = i / 8, k = i % 8;            // W1[u][k]
+        w1[(k * 4 + u / Q) * P + u % Q] = p.w1[i];
+        const int o = i / H, c = i % H;            // W3[o][c]
+        w3[(o * 4 + c / Q) * P + c % Q] = p.w3[i];
+    }
+    for (int i = threadIdx.x; i < H * H / 4; i += kPolThreads) {
+        const float4 v = reinterpret_cast<const float4 *>(p.w2)[i];   // W2[u][k .. k + 3]
+        const int u = (4 * i) / H, k = (4 * i) % H;
+        float *dst = w2 + (u / Q) * P + u % Q;
+        dst[(k + 0) * 4 * P] = v.x; dst[(k + 1) * 4 * P] = v.y; dst[(k + 2) * 4 * P] = v.z; dst[(k + 3) * 4 * P] = v.w;
+    }
     for (int i = threadIdx.x; i < H; i += kPolThreads) { b1[i] = p.b1[i]; b2[i] = p.b2[i]; }
     if (threadIdx.x < 8) { b3[threadIdx.x] = p.b3[threadIdx.x]; sc[threadIdx.x] = p.scale[threadIdx.x]; }
     __syncthreads();
     const unsigned long long counter = p.counter + (p.counter_base ? *p.counter_base : 0ull);
     const int part = threadIdx.x & 3;              // which quarter of the hidden units
-    const int envs_per_block = kPolThreads / 4;
+    // E envs per thread: every weight fetched from shared memory is used E times (the kernel is bound by those fetches)
+    constexpr int E = kEnvsPerThread;
+    constexpr int envs_per_block = (kPolThreads / 4) * E;
     for (int base = blockIdx.x * envs_per_block; base < p.n; base += gridDim.x * envs_per_block) {
-        const int env = base + (threadIdx.x >> 2);
-        const bool valid = env < p.n;
-        float x[8];
-        {
-            const float4 a = valid ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env] : make_float4(0, 0, 0, 0);
-            const float4 b = valid ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env + 1] : make_float4(0, 0, 0, 0);
-            if (valid && p.obs_copy && part == 0) {
-                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env] = a;
-                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env + 1] = b;
+        int env[E];
+        bool valid[E];
+        float x[E][8];
+#pragma unroll
+        for (int q = 0; q < E; q++) {
+            env[q] = base + q * (kPolThreads / 4) + (threadIdx.x >> 2);
+            valid[q] = env[q] < p.n;
+            const float4 a = valid[q] ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env[q]] : make_float4(0, 0, 0, 0);
+            const float4 b = valid[q] ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env[q] + 1] : make_float4(0, 0, 0, 0);
+            if (valid[q] && p.obs_copy && part == 0) {
+                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env[q]] = a;
+                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env[q] + 1] = b;
             }
-            x[0] = a.x * sc[0]; x[1] = a.y * sc[1]; x[2] = a.z * sc[2]; x[3] = a.w * sc[3];
-            x[4] = b.x * sc[4]; x[5] = b.y * sc[5]; x[6] = b.z * sc[6]; x[7] = b.w * sc[7];
+            x[q][0] = a.x * sc[0]; x[q][1] = a.y * sc[1]; x[q][2] = a.z * sc[2]; x[q][3] = a.w * sc[3];
+            x[q][4] = b.x * sc[4]; x[q][5] = b.y * sc[5]; x[q][6] = b.z * sc[6]; x[q][7] = b.w * sc[7];
         }
-        // layer 1: this thread's quarter of h1
-        float h1[Q];
+        // layer 1: this thread's quarter of h1 = tanh(b1 + W1 x)
+        float h1[E][Q];
 #pragma unroll
         for (int j = 0; j < Q; j++) {
-            const int u = part * Q + j;
-            const float4 wa = reinterpret_cast<const float4 *>(w1 + u * 8)[0], wb = reinterpret_cast<const float4 *>(w1 + u * 8)[1];
-            float s = b1[u];
-            s += wa.x * x[0]; s += wa.y * x[1]; s += wa.z * x[2]; s += wa.w * x[3];
-            s += wb.x * x[4]; s += wb.y * x[5]; s += wb.z * x[6]; s += wb.w * x[7];
-            h1[j] = fast_tanh(s);
-        }
-        // layer 2: h2[u] = tanh(b2[u] + sum_k w2[u][k] h1[k]); each thread owns Q outputs and needs all H inputs:
-        // the other quarters of h1 come over warp shuffles (the 4 threads of an env are adjacent lanes)
-        float acc2[Q];
 #pragma unroll
-        for (int j = 0; j < Q; j++) acc2[j] = b2[part * Q + j];
+            for (int q = 0; q < E; q++) h1[q][j] = b1[part * Q + j];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float4 *w = reinterpret_cast<const float4 *>(w1 + (k * 4 + part) * P);
+#pragma unroll
+            for (int j4 = 0; j4 < Q / 4; j4++) {
+                const float4 v = w[j4];
+#pragma unroll
+                for (int q = 0; q < E; q++) {
+                    h1[q][4 * j4] += v.x * x[q][k]; h1[q][4 * j4 + 1] += v.y * x[q][k];
+                    h1[q][4 * j4 + 2] += v.z * x[q][k]; h1[q][4 * j4 + 3] += v.w * x[q][k];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+#pragma unroll
+            for (int q = 0; q < E; q++) h1[q][j] = fast_tanh(h1[q][j]);
+        }
+        // layer 2: each thread owns Q outputs and needs all H inputs: the other quarters of h1 come over warp
+        // shuffles (the 4 threads of an env are adjacent lanes)
+        float h2[E][Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+#pragma unroll
+            for (int q = 0; q < E; q++) h2[q][j] = b2[part * Q + j];
+        }
 #pragma unroll
         for (int src = 0; src < 4; src++) {
 #pragma unroll
             for (int k = 0; k < Q; k++) {
-                const float hk = __shfl_sync(0xffffffffu, h1[k], (threadIdx.x & 28) | src, 32);   // h1[src * Q + k]
+                float hk[E];
 #pragma unroll
-                for (int j = 0; j < Q; j++) acc2[j] += w2[(part * Q + j) * H + src * Q + k] * hk;
+                for (int q = 0; q < E; q++) hk[q] = __shfl_sync(0xffffffffu, h1[q][k], (threadIdx.x & 28) | src, 32);   // h1[src * Q + k]
+                const float4 *w = reinterpret_cast<const float4 *>(w2 + ((src * Q + k) * 4 + part) * P);
+#pragma unroll
+                for (int j4 = 0; j4 < Q / 4; j4++) {
+                    const float4 v = w[j4];
+#pragma unroll
+                    for (int q = 0; q < E; q++) {
+                        h2[q][4 * j4] += v.x * hk[q]; h2[q][4 * j4 + 1] += v.y * hk[q];
+                        h2[q][4 * j4 + 2] += v.z * hk[q]; h2[q][4 * j4 + 3] += v.w * hk[q];
+                    }
+                }
             }
         }
-        float h2[Q];
 #pragma unroll
-        for (int j = 0; j < Q; j++) h2[j] = fast_tanh(acc2[j]);
+        for (int j = 0; j < Q; j++) {
+#pragma unroll
+            for (int q = 0; q < E; q++) h2[q][j] = fast_tanh(h2[q][j]);
+        }
         // layer 3: partial logits over this thread's quarter of h2, then a butterfly over the 4 lanes
-        float lg[8];
+        float lg[E][8];
 #pragma unroll
         for (int o = 0; o < 8; o++) {
-            float s = 0.0f;
+            const float4 *w = reinterpret_cast<const float4 *>(w3 + (o * 4 + part) * P);
+            float s[E];
 #pragma unroll
-            for (int j = 0; j < Q; j++) s += w3[o * H + part * Q + j] * h2[j];
-            s += __shfl_xor_sync(0xffffffffu, s, 1, 32);
-            s += __shfl_xor_sync(0xffffffffu, s, 2, 32);
-            lg[o] = s + b3[o];
+            for (int q = 0; q < E; q++) s[q] = 0.0f;
+#pragma unroll
+            for (int j4 = 0; j4 < Q / 4; j4++) {
+                const float4 v = w[j4];
+#pragma unroll
+                for (int q = 0; q < E; q++) {
+                    s[q] += v.x * h2[q][4 * j4]; s[q] += v.y * h2[q][4 * j4 + 1];
+                    s[q] += v.z * h2[q][4 * j4 + 2]; s[q] += v.w * h2[q][4 * j4 + 3];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < E; q++) {
+                s[q] += __shfl_xor_sync(0xffffffffu, s[q], 1, 32);
+                s[q] += __shfl_xor_sync(0xffffffffu, s[q], 2, 32);
+                lg[q][o] = s[q] + b3[o];
+            }
         }
         // log-softmax + inverse-CDF sample (identical on the 4 lanes; lane 0 of the group writes)
-        float m = lg[0];
 #pragma unroll
-        for (int o = 1; o < 8; o++) m = fmaxf(m, lg[o]);
-        float e[8], z = 0.0f;
+        for (int q = 0; q < E; q++) {
+            float m = lg[q][0];
 #pragma unroll
-        for (int o = 0; o < 8; o++) { e[o] = __expf(lg[o] - m); z += e[o]; }
-        const float u01 = (float)(hash3(p.seed, counter, (uint32_t)env) >> 8) * (1.0f / 16777216.0f);   // [0, 1)
-        const float target = u01 * z;
-        int a = 7;
-        float c = 0.0f;
+            for (int o = 1; o < 8; o++) m = fmaxf(m, lg[q][o]);
+            float e[8], z = 0.0f;
 #pragma unroll
-        for (int o = 0; o < 8; o++) { c += e[o]; if (a == 7 && target < c) a = o; }
-        if (valid && part == 0) {
-            p.actions[env] = (uint8_t)a;
-            if (p.logp) p.logp[env] = (lg[a] - m) - __logf(z);
+            for (int o = 0; o < 8; o++) { e[o] = __expf(lg[q][o] - m); z += e[o]; }
+            const float u01 = (float)(hash3(p.seed, counter, (uint32_t)env[q]) >> 8) * (1.0f / 16777216.0f);   // [0, 1)
+            const float target = u01 * z;
+            int a = 7;
+            float c = 0.0f, la = lg[q][7];
+#pragma unroll
+            for (int o = 0; o < 8; o++) { c += e[o]; if (a == 7 && target < c) { a = o; la = lg[q][o]; } }
+            if (valid[q] && part == 0) {
+                p.actions[env[q]] = (uint8_t)a;
+                if (p.logp) p.logp[env[q]] = (la - m) - __logf(z);
+            }
         }
     }
 }
@@ -162,10 +230,11 @@ int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int envs_per_block = kPolThreads / 4;
+    const int envs_per_block = (kPolThreads / 4) * kEnvsPerThread;
     int grid = (num_envs + envs_per_block - 1) / envs_per_block;
-    if (grid > sms * 8) grid = sms * 8;
-    const size_t bytes = sizeof(float) * ((size_t)hidden * 8 * 2 + (size_t)hidden * hidden + 2 * hidden + 16);
+    if (grid > sms * 4) grid = sms * 4;            // persistent: the weight staging is amortised over several env groups
+    const size_t pitch = (size_t)hidden / 4 + 4;   // Pitch<Q>
+    const size_t bytes = sizeof(float) * ((8 + (size_t)hidden + 8) * 4 * pitch + 2 * (size_t)hidden + 16);
     cudaError_t e = cudaSuccess;
     cudaStream_t s = (cudaStream_t)stream;
 #define FG_POLICY_LAUNCH(HH) do { \
