@@ -21,9 +21,7 @@ Output: tests/golden/ref_python_<name>.npz, one per scenario:
 import json
 import os
 import socket
-import struct
 import sys
-import threading
 import types
 
 import numpy as np

@@ -2,7 +2,6 @@
 
 TEST INFRASTRUCTURE ONLY: lets the batched wrappers (pure torch ops) be checked on a machine without a GPU.
 The product never imports this."""
-import numpy as np
 import torch
 
 import oracle_binding as ob

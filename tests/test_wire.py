@@ -7,7 +7,6 @@ cannot be imported on the GPU box); the goldens it recorded are replayed by test
 """
 import json
 import socket
-import struct
 
 import numpy as np
 import pytest
