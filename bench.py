@@ -50,6 +50,10 @@ def parse_args():
                     help="untimed steps before the warm-up so that episodes are desynchronised (steady state)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline leg")
+    ap.add_argument("--workload", default="step", choices=["step", "rollout"],
+                    help="step (default): the single-frame step kernel, BASELINE's headline metric; rollout: BASELINE "
+                         "configs[4], 16384 envs per GPU x 128-step horizon with the fused MLP policy kernel in the loop "
+                         "(one horizon = one bench step), weak scaling, one stats all-reduce at the end")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     return ap.parse_args()
@@ -199,6 +203,55 @@ def emit(line):
 _REAL_STDOUT = os.dup(1)
 
 
+def run_rollout(args, rank, world, dev, dist):
+    """--workload rollout: BASELINE configs[4] on N GPUs.  One bench step = one 128-step horizon for 16384 envs per
+    GPU: fused MLP policy inference + sampling (fg_policy_mlp_sample) and the simulator step (fg_step) alternate on
+    device, rollout buffers are written in place, the horizon is one CUDA-graph replay."""
+    import torch
+    from footsies_gym_b200 import FootsiesEnv
+    from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
+    n, horizon = 16384, 128
+    steps = min(args.steps, 200)
+    env = FootsiesEnv(num_envs=n, device=dev, opponent=None, seed=0, first_env_index=rank * n)
+    torch.manual_seed(0)
+    col = RolloutCollector(env, MLPPolicy(64).to(dev), horizon=horizon, use_cuda_graph=True, seed=rank)
+    for _ in range(max(args.warmup, 3)):
+        col.collect()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    f0 = env.episode_stats()["env_frames"]
+    l0 = env.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        col.collect()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    f = torch.tensor([env.episode_stats()["env_frames"] - f0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    stats = env.all_reduce_stats()
+    if rank == 0:
+        ms = float(t.item())
+        emit({"metric": METRIC, "value": int(f.item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+              "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
+              "config": {"workload": "E: PPO rollout, MLP 8-64-64-8 policy (fused inference + sampling kernel) reading the "
+                                     "observation tensor in place, 16384 envs per GPU x 128-step horizon per bench step, "
+                                     "vs in-game BattleAI, frame-skip 1 (BASELINE configs[4])",
+                         "envs_per_gpu": n, "horizon": horizon, "l2": "working set fits L2 (latency-bound regime); not the "
+                         "roofline workload"},
+              "gpu_launches": (env.launch_count() - l0) * 2, "episode_stats_all_ranks": stats})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     sys.stdout.flush()
     os.dup2(2, 1)
@@ -224,6 +277,9 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.workload == "rollout":
+        run_rollout(args, rank, world, dev, dist)
+        return
     if args.total_envs > 0:
         from footsies_gym_b200.distributed import shard_range
         first_index, n = shard_range(args.total_envs, rank, world)
