@@ -39,7 +39,7 @@ WORKLOAD = ("D-weak: random-action P1 vs in-game BattleAI, frame-skip 1, auto-re
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=DEFAULT_ENVS_PER_GPU)
