@@ -8,11 +8,13 @@
 //   -> in-game bot (BattleAI.cs:41-403, queried as TrainingManager.cs:59-77 does)
 //   -> observation, info, reward, termination (footsies.py:336-405, 518-570)
 //
-// The step kernel is bound by the integer (ALU) pipe, not by issue slots or HBM (profiles/: every ALU-pipe
-// instruction per env-frame costs ~0.26 us per 4 Mi-env launch), so this file is written to minimise LOP3 / SHF /
-// ISETP / SEL counts: fields are tested and updated in place in the packed words, table byte offsets are
-// pre-positioned inside the row words, multiplications by powers of two and adds of disjoint bit-fields go to the
-// FMA pipe (IMAD), and facts about (action, frame) are looked up once per fighter per frame.
+// The step kernel is bound by the integer (ALU) pipe before anything else (profiles/r01_summary.md: every ALU-pipe
+// instruction per env-frame cost ~0.26 us per 4 Mi-env launch; the fused-K kernels run that pipe at ~80 %), so this
+// file is written to minimise LOP3 / SHF / ISETP / SEL counts: fields are tested and updated in place in the packed
+// words, table byte offsets are pre-positioned inside the row words, input processing (Attack run length, dash
+// detection) and -- in the fused-K kernels -- the request decision are shared-memory table steps, multiplications by
+// powers of two and adds of disjoint bit-fields go to the FMA pipe (IMAD), and facts about (action, frame) are looked
+// up once per fighter per frame.
 //
 // fp32 discipline: compiled with -fmad=false; every add/mul rounds on its own exactly like the scalar C# expression
 // it restates.  Multiplications by the facing sign (+-1) and by 0.5 are exact.
