@@ -494,7 +494,7 @@ def main():
                          "algorithmic_bytes_per_env_frame": bytes_per_env, "peak_source": peak_src,
                          "kernel": "step_kernel<K=1, P2 bot, dense>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "FootsiesEnv.step_host -> fg_step_host (pinned host buffers)"},
+                    "steps": e2e_steps, "api": "FootsiesEnv.step_host -> fg_step_host_compact (pinned host buffers; compact 27-byte result layout, 1 Mi-env slices pipelined over two streams)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "episode_stats_all_ranks": stats,

@@ -29,6 +29,12 @@ class FgBuffers(C.Structure):
                 ("info_misc", C.c_void_p), ("step_mask", C.c_void_p)]
 
 
+class FgHostOutputs(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("reserved0", C.c_int32), ("position", C.c_void_p),
+                ("obs_u8", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
+                ("info_frame", C.c_void_p), ("info_misc", C.c_void_p)]
+
+
 class FgFighterState(C.Structure):
     _fields_ = [("pos_x", C.c_float), ("velocity_x", C.c_float), ("action_id", C.c_int32),
                 ("action_frame", C.c_int32), ("hitstun", C.c_int32), ("guard", C.c_int32), ("vital", C.c_int32),
@@ -63,7 +69,8 @@ _lib = None
 
 # every symbol include/footsies_b200.h declares
 EXPORTS = ["fg_abi_version", "fg_last_error", "fg_algorithmic_bytes_per_env_step", "fg_create", "fg_destroy",
-           "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_get_state",
+           "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_step_host_compact",
+           "fg_reset_host_compact", "fg_get_state",
            "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_last_error"]
 
 
@@ -99,6 +106,10 @@ def load(build_if_missing=True):
     L.fg_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fg_reset_host.restype = i32
     L.fg_reset_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.fg_step_host_compact.restype = i32
+    L.fg_step_host_compact.argtypes = [vp, vp, vp, C.POINTER(FgHostOutputs), vp]
+    L.fg_reset_host_compact.restype = i32
+    L.fg_reset_host_compact.argtypes = [vp, vp, C.POINTER(FgHostOutputs), vp]
     L.fg_get_state.restype = i32
     L.fg_get_state.argtypes = [vp, i32, i32, vp]
     L.fg_set_state.restype = i32

@@ -28,6 +28,14 @@ struct fg_handle {
     int64_t launches;
     uint8_t *d_mask;       // staging for fg_reset_host
     int large_shape_min_envs;
+    // host-buffer path (fg_step_host*): slices of host_chunk_envs battles are pipelined over two library-owned
+    // streams, so that the D2H copies of slice c run while slice c+1 is being simulated and its actions uploaded
+    int host_chunk_envs;
+    float2 *d_position;    // [num_envs] compact host layout: position p1,p2
+    uint8_t *d_obs_u8;     // [num_envs][6] compact host layout: guard p1,p2 | move p1,p2 | move_frame p1,p2
+    cudaStream_t s_compute, s_copy;
+    cudaEvent_t ev_fork, ev_join;
+    std::vector<cudaEvent_t> ev_slice;
 };
 
 namespace {
@@ -38,19 +46,22 @@ int grid_for(const fg_handle *h, int blocks_per_sm) {
     return want < cap ? (want > 0 ? want : 1) : cap;
 }
 
-Params make_params(const fg_handle *h) {
+// Kernel parameters for the envs [first, first + count) of the handle (count < 0: all of them).
+Params make_params(const fg_handle *h, int first = 0, int count = -1) {
     Params p;
     memset(&p, 0, sizeof p);
-    p.pl_f1 = (uint4 *)h->buf.state[FG_PLANE_F1]; p.pl_f2 = (uint4 *)h->buf.state[FG_PLANE_F2];
-    p.pl_env = (uint4 *)h->buf.state[FG_PLANE_ENV]; p.pl_rng = (uint4 *)h->buf.state[FG_PLANE_RNG];
+    const size_t o = (size_t)first;
+    p.pl_f1 = (uint4 *)h->buf.state[FG_PLANE_F1] + o; p.pl_f2 = (uint4 *)h->buf.state[FG_PLANE_F2] + o;
+    p.pl_env = (uint4 *)h->buf.state[FG_PLANE_ENV] + o; p.pl_rng = (uint4 *)h->buf.state[FG_PLANE_RNG] + o;
     p.stats = (unsigned long long *)h->buf.stats;
-    p.act1 = h->buf.actions_p1; p.act2 = h->buf.actions_p2;
-    p.obs = (float4 *)h->buf.obs; p.reward = h->buf.reward; p.terminated = h->buf.terminated;
-    p.info_frame = h->buf.info_frame; p.info_misc = (uint32_t *)h->buf.info_misc;
-    p.step_mask = h->buf.step_mask;
+    p.act1 = h->buf.actions_p1 ? h->buf.actions_p1 + o : nullptr;
+    p.act2 = h->buf.actions_p2 ? h->buf.actions_p2 + o : nullptr;
+    p.obs = (float4 *)h->buf.obs + 2 * o; p.reward = h->buf.reward + o; p.terminated = h->buf.terminated + o;
+    p.info_frame = h->buf.info_frame + o; p.info_misc = (uint32_t *)h->buf.info_misc + o;
+    p.step_mask = h->buf.step_mask ? h->buf.step_mask + o : nullptr;
     p.tables = h->d_tables;
-    p.first_env_index = h->cfg.first_env_index;
-    p.n = h->cfg.num_envs; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
+    p.first_env_index = h->cfg.first_env_index + first;
+    p.n = count < 0 ? h->cfg.num_envs - first : count; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
     p.stale_intro = h->cfg.stale_intro_input;
     p.large_shape_min_envs = h->large_shape_min_envs;
     return p;
@@ -85,6 +96,171 @@ int check_bound(const fg_handle *h) {
     return FG_OK;
 }
 
+// ---- host-buffer path -------------------------------------------------------------------------------------------
+// Where the results of a host-buffer call go.  obs_f32 is the device layout ([n][8] floats, 32 B); position + obs_u8 is
+// the compact host layout (8 + 6 B: the integer-valued observation fields travel as bytes), produced by pack_obs_kernel.
+struct HostOut {
+    float *obs_f32;
+    float *position;
+    uint8_t *obs_u8;
+    float *reward;
+    uint8_t *terminated;
+    int32_t *info_frame;
+    uint8_t *info_misc;
+};
+
+// obs [n][8] f32 -> position [n] float2 + obs_u8 [n][6].  Two envs per thread: 4 x 128-bit loads, one 128-bit and three
+// 32-bit stores, all coalesced.  The six integer-valued fields are exact in a byte (guard 0..3, move index 0..14,
+// move_frame 0..55: FootsiesEnv.observation_space, footsies.py:157-168).
+__global__ void __launch_bounds__(256) pack_obs_kernel(const float4 *__restrict__ obs, float2 *__restrict__ position,
+                                                        uint8_t *__restrict__ obs_u8, int n) {
+    const int pairs = n >> 1;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < pairs; j += gridDim.x * blockDim.x) {
+        const float4 a0 = obs[4 * (size_t)j], a1 = obs[4 * (size_t)j + 1], b0 = obs[4 * (size_t)j + 2], b1 = obs[4 * (size_t)j + 3];
+        reinterpret_cast<float4 *>(position)[j] = make_float4(a1.z, a1.w, b1.z, b1.w);
+        const uint32_t A[6] = { (uint32_t)a0.x, (uint32_t)a0.y, (uint32_t)a0.z, (uint32_t)a0.w, (uint32_t)a1.x, (uint32_t)a1.y };
+        const uint32_t B[6] = { (uint32_t)b0.x, (uint32_t)b0.y, (uint32_t)b0.z, (uint32_t)b0.w, (uint32_t)b1.x, (uint32_t)b1.y };
+        uint32_t *o = reinterpret_cast<uint32_t *>(obs_u8) + 3 * (size_t)j;
+        o[0] = A[0] | A[1] << 8 | A[2] << 16 | A[3] << 24;
+        o[1] = A[4] | A[5] << 8 | B[0] << 16 | B[1] << 24;
+        o[2] = B[2] | B[3] << 8 | B[4] << 16 | B[5] << 24;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = n - 1;
+        const float4 a0 = obs[2 * (size_t)i], a1 = obs[2 * (size_t)i + 1];
+        position[i] = make_float2(a1.z, a1.w);
+        const float v[6] = { a0.x, a0.y, a0.z, a0.w, a1.x, a1.y };
+        for (int k = 0; k < 6; k++) obs_u8[6 * (size_t)i + k] = (uint8_t)v[k];
+    }
+}
+
+int step_range(fg_handle *h, int first, int count, cudaStream_t s) {
+    const Params p = make_params(h, first, count);
+    CUDA_TRY(h->cfg.frame_skip == 1 ? launch_step_k<false>(h->cfg, h->sm_count, s, p) : launch_step_k<true>(h->cfg, h->sm_count, s, p));
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+// Library-owned resources of the host-buffer path, created on first use.
+int host_path_init(fg_handle *h, bool compact, int slices) {
+    if (compact && !h->d_position) {
+        CUDA_TRY(cudaMalloc(&h->d_position, sizeof(float2) * (size_t)h->cfg.num_envs));
+        CUDA_TRY(cudaMalloc(&h->d_obs_u8, 6 * (size_t)h->cfg.num_envs + 8));
+    }
+    if (slices > 1 && !h->s_compute) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    while (slices > 1 && (int)h->ev_slice.size() < slices) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_slice.push_back(e);
+    }
+    return FG_OK;
+}
+
+// Results of envs [first, first + m) -> host, on stream s (after the pack kernel when the compact layout is asked for).
+int copy_out(fg_handle *h, const HostOut &o, size_t first, size_t m, cudaStream_t s) {
+    const fg_buffers &b = h->buf;
+    if (o.obs_f32) CUDA_TRY(cudaMemcpyAsync(o.obs_f32 + 8 * first, b.obs + 8 * first, m * 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (o.position) CUDA_TRY(cudaMemcpyAsync(o.position + 2 * first, h->d_position + first, m * sizeof(float2), cudaMemcpyDeviceToHost, s));
+    if (o.obs_u8) CUDA_TRY(cudaMemcpyAsync(o.obs_u8 + 6 * first, h->d_obs_u8 + 6 * first, m * 6, cudaMemcpyDeviceToHost, s));
+    if (o.reward) CUDA_TRY(cudaMemcpyAsync(o.reward + first, b.reward + first, m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (o.terminated) CUDA_TRY(cudaMemcpyAsync(o.terminated + first, b.terminated + first, m, cudaMemcpyDeviceToHost, s));
+    if (o.info_frame) CUDA_TRY(cudaMemcpyAsync(o.info_frame + first, b.info_frame + first, m * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (o.info_misc) CUDA_TRY(cudaMemcpyAsync(o.info_misc + 4 * first, b.info_misc + 4 * first, m * 4, cudaMemcpyDeviceToHost, s));
+    return FG_OK;
+}
+
+int pack_range(fg_handle *h, size_t first, size_t m, cudaStream_t s) {
+    const int want = (int)((m / 2 + 255) / 256), cap = h->sm_count * 8;
+    pack_obs_kernel<<<want < cap ? (want > 0 ? want : 1) : cap, 256, 0, s>>>((const float4 *)h->buf.obs + 2 * first,
+                                                                             h->d_position + first, h->d_obs_u8 + 6 * first, (int)m);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+// FootsiesEnv.step with HOST buffers.  Small batches: H2D, step, (pack), D2H on the caller's stream.  Large batches are
+// cut into slices of host_chunk_envs battles (battles are independent, so a slice is just an offset into every buffer):
+// uploads + kernels run on one library stream, the D2H copies on another, and slice c's results cross PCIe while
+// slice c + 1 is simulated.  Ordered after prior work on `stream`; returns when every result is in host memory.
+int host_step(fg_handle *h, const uint8_t *a1, const uint8_t *a2, const HostOut &o, cudaStream_t user) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!h->cfg.p1_bot && !a1) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p1 is required unless p1_bot%s");
+    if (!h->cfg.p2_bot && !a2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
+    const bool compact = o.position || o.obs_u8;
+    if (compact && !(o.position && o.obs_u8)) return fail(FG_ERR_INVALID_ARGUMENT, "position and obs_u8 go together%s");
+    const size_t n = (size_t)h->cfg.num_envs, chunk = (size_t)h->host_chunk_envs;
+    const int slices = (int)((n + chunk - 1) / chunk);
+    if (int rc = host_path_init(h, compact, slices)) return rc;
+    cudaStream_t sc = user, sd = user;
+    if (slices > 1) {
+        sc = h->s_compute; sd = h->s_copy;
+        CUDA_TRY(cudaEventRecord(h->ev_fork, user));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_fork, 0));
+    }
+    for (int c = 0; c < slices; c++) {
+        const size_t first = (size_t)c * chunk, m = n - first < chunk ? n - first : chunk;
+        if (!h->cfg.p1_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p1 + first), a1 + first, m, cudaMemcpyHostToDevice, sc));
+        if (!h->cfg.p2_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p2 + first), a2 + first, m, cudaMemcpyHostToDevice, sc));
+        if (int rc = step_range(h, (int)first, (int)m, sc)) return rc;
+        if (compact) if (int rc = pack_range(h, first, m, sc)) return rc;
+        if (slices > 1) {
+            CUDA_TRY(cudaEventRecord(h->ev_slice[c], sc));
+            CUDA_TRY(cudaStreamWaitEvent(sd, h->ev_slice[c], 0));
+        }
+        if (int rc = copy_out(h, o, first, m, sd)) return rc;
+    }
+    if (slices > 1) {
+        CUDA_TRY(cudaEventRecord(h->ev_join, sd));
+        CUDA_TRY(cudaStreamWaitEvent(user, h->ev_join, 0));
+    }
+    CUDA_TRY(cudaStreamSynchronize(sd));
+    return FG_OK;
+}
+
+int reset_on(fg_handle *h, const uint8_t *dmask, cudaStream_t s) {
+    Params p = make_params(h);
+    p.mask = dmask;
+    const int grid = grid_for(h, 4);
+    cudaError_t le;
+    if (h->cfg.p1_bot && h->cfg.p2_bot) le = launch_reset<true, true>(grid, s, p);
+    else if (h->cfg.p1_bot) le = launch_reset<true, false>(grid, s, p);
+    else if (h->cfg.p2_bot) le = launch_reset<false, true>(grid, s, p);
+    else le = launch_reset<false, false>(grid, s, p);
+    CUDA_TRY(le);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+// FootsiesEnv.reset with HOST buffers (mask: host uint8[num_envs] or NULL); not a hot call, one stream.
+int host_reset(fg_handle *h, const uint8_t *mask, const HostOut &o, cudaStream_t s) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    const bool compact = o.position || o.obs_u8;
+    if (compact && !(o.position && o.obs_u8)) return fail(FG_ERR_INVALID_ARGUMENT, "position and obs_u8 go together%s");
+    const size_t n = (size_t)h->cfg.num_envs;
+    if (int rc = host_path_init(h, compact, 1)) return rc;
+    const uint8_t *dmask = nullptr;
+    if (mask) {
+        if (!h->d_mask) CUDA_TRY(cudaMalloc(&h->d_mask, n));
+        CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s));
+        dmask = h->d_mask;
+    }
+    if (int rc = reset_on(h, dmask, s)) return rc;
+    if (compact) if (int rc = pack_range(h, 0, n, s)) return rc;
+    if (int rc = copy_out(h, o, 0, n, s)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return FG_OK;
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -118,6 +294,16 @@ int32_t fg_create(const fg_config *cfg, fg_handle **out) {
     h->bound = false;
     h->launches = 0;
     h->d_mask = nullptr;
+    h->d_position = nullptr; h->d_obs_u8 = nullptr;
+    h->s_compute = h->s_copy = nullptr;
+    h->ev_fork = h->ev_join = nullptr;
+    // slice size of the pipelined host-buffer path (measured, tools/e2e_bench.py, 4 Mi battles: no slices 2.28 ms, 2 Mi 2.20, 1 Mi 2.21,
+    // 512 Ki 2.27, 256 Ki 2.45, 128 Ki 2.84: below 1 Mi the six copies per slice cost more than the overlap wins)
+    h->host_chunk_envs = 1024 * 1024;
+    if (const char *v = getenv("FOOTSIES_B200_HOST_CHUNK_ENVS")) {
+        const long long c = atoll(v);
+        if (c >= 256) h->host_chunk_envs = (int)((c > (1ll << 30) ? (1ll << 30) : c) / 256 * 256);
+    }
     // developer / test knob: force the large CTA shapes onto small batches (or the small shape onto large ones)
     h->large_shape_min_envs = kLargeShapeMinEnvs;
     if (const char *v = getenv("FOOTSIES_B200_LARGE_SHAPE_MIN_ENVS")) h->large_shape_min_envs = atoi(v);
@@ -139,6 +325,10 @@ void fg_destroy(fg_handle *h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->d_tables);
     if (h->d_mask) cudaFree(h->d_mask);
+    if (h->d_position) cudaFree(h->d_position);
+    if (h->d_obs_u8) cudaFree(h->d_obs_u8);
+    if (h->s_compute) { cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+    for (cudaEvent_t e : h->ev_slice) cudaEventDestroy(e);
     delete h;
 }
 
@@ -172,73 +362,38 @@ int32_t fg_seed(fg_handle *h, int64_t seed_base, const uint8_t *mask, void *stre
 int32_t fg_reset(fg_handle *h, const uint8_t *mask, void *stream) {
     if (int rc = check_bound(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    Params p = make_params(h);
-    p.mask = mask;
-    const int grid = grid_for(h, 4);
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t le;
-    if (h->cfg.p1_bot && h->cfg.p2_bot) le = launch_reset<true, true>(grid, s, p);
-    else if (h->cfg.p1_bot) le = launch_reset<true, false>(grid, s, p);
-    else if (h->cfg.p2_bot) le = launch_reset<false, true>(grid, s, p);
-    else le = launch_reset<false, false>(grid, s, p);
-    CUDA_TRY(le);
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return FG_OK;
+    return reset_on(h, mask, (cudaStream_t)stream);
 }
 
 int32_t fg_step(fg_handle *h, void *stream) {
     if (int rc = check_bound(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
-    const Params p = make_params(h);
-    CUDA_TRY(h->cfg.frame_skip == 1 ? launch_step_k<false>(h->cfg, h->sm_count, (cudaStream_t)stream, p)
-                                    : launch_step_k<true>(h->cfg, h->sm_count, (cudaStream_t)stream, p));
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return FG_OK;
+    return step_range(h, 0, -1, (cudaStream_t)stream);
 }
 
 int32_t fg_step_host(fg_handle *h, const uint8_t *a1, const uint8_t *a2, float *obs, float *reward,
                      uint8_t *terminated, int32_t *info_frame, uint8_t *info_misc, void *stream) {
-    if (int rc = check_bound(h)) return rc;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t n = (size_t)h->cfg.num_envs;
-    if (!h->cfg.p1_bot) {
-        if (!a1) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p1 is required unless p1_bot%s");
-        CUDA_TRY(cudaMemcpyAsync((void *)h->buf.actions_p1, a1, n, cudaMemcpyHostToDevice, s));
-    }
-    if (!h->cfg.p2_bot) {
-        if (!a2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
-        CUDA_TRY(cudaMemcpyAsync((void *)h->buf.actions_p2, a2, n, cudaMemcpyHostToDevice, s));
-    }
-    if (int rc = fg_step(h, stream)) return rc;
-    if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->buf.obs, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, h->buf.reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (terminated) CUDA_TRY(cudaMemcpyAsync(terminated, h->buf.terminated, n, cudaMemcpyDeviceToHost, s));
-    if (info_frame) CUDA_TRY(cudaMemcpyAsync(info_frame, h->buf.info_frame, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (info_misc) CUDA_TRY(cudaMemcpyAsync(info_misc, h->buf.info_misc, n * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return FG_OK;
+    HostOut o = { obs, nullptr, nullptr, reward, terminated, info_frame, info_misc };
+    return host_step(h, a1, a2, o, (cudaStream_t)stream);
+}
+
+int32_t fg_step_host_compact(fg_handle *h, const uint8_t *a1, const uint8_t *a2, const fg_host_outputs *out, void *stream) {
+    if (!out || out->struct_size != (int32_t)sizeof(fg_host_outputs))
+        return fail(FG_ERR_INVALID_ARGUMENT, "fg_host_outputs is null or its struct_size does not match%s");
+    HostOut o = { nullptr, out->position, out->obs_u8, out->reward, out->terminated, out->info_frame, out->info_misc };
+    return host_step(h, a1, a2, o, (cudaStream_t)stream);
 }
 
 int32_t fg_reset_host(fg_handle *h, const uint8_t *mask, float *obs, int32_t *info_frame, uint8_t *info_misc, void *stream) {
-    if (int rc = check_bound(h)) return rc;
-    CUDA_TRY(cudaSetDevice(h->cfg.device));
-    cudaStream_t s = (cudaStream_t)stream;
-    const size_t n = (size_t)h->cfg.num_envs;
-    const uint8_t *dmask = nullptr;
-    if (mask) {
-        if (!h->d_mask) CUDA_TRY(cudaMalloc(&h->d_mask, n));
-        CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s));
-        dmask = h->d_mask;
-    }
-    if (int rc = fg_reset(h, dmask, stream)) return rc;
-    if (obs) CUDA_TRY(cudaMemcpyAsync(obs, h->buf.obs, n * 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (info_frame) CUDA_TRY(cudaMemcpyAsync(info_frame, h->buf.info_frame, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (info_misc) CUDA_TRY(cudaMemcpyAsync(info_misc, h->buf.info_misc, n * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    return FG_OK;
+    HostOut o = { obs, nullptr, nullptr, nullptr, nullptr, info_frame, info_misc };
+    return host_reset(h, mask, o, (cudaStream_t)stream);
+}
+
+int32_t fg_reset_host_compact(fg_handle *h, const uint8_t *mask, const fg_host_outputs *out, void *stream) {
+    if (!out || out->struct_size != (int32_t)sizeof(fg_host_outputs))
+        return fail(FG_ERR_INVALID_ARGUMENT, "fg_host_outputs is null or its struct_size does not match%s");
+    HostOut o = { nullptr, out->position, out->obs_u8, nullptr, nullptr, out->info_frame, out->info_misc };
+    return host_reset(h, mask, o, (cudaStream_t)stream);
 }
 
 int32_t fg_get_state(fg_handle *h, int32_t first, int32_t count, fg_env_state *out) {

@@ -392,49 +392,86 @@ class FootsiesEnv:
 
     # ------------------------------------------------------------------ host-buffer (reference-facing) path
     def _host_buffers(self):
+        """Pinned host tensors of the host-buffer path, in the compact layout of fg_host_outputs (27 bytes per battle:
+        the call is PCIe-bound, so the integer-valued observation fields travel as bytes)."""
         if self._host is None:
             n = self.num_envs
             pin = dict(pin_memory=True)
-            self._host = dict(
+            hb = dict(
                 a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
-                obs=torch.zeros((n, 8), dtype=torch.float32, **pin), reward=torch.zeros(n, dtype=torch.float32, **pin),
-                terminated=torch.zeros(n, dtype=torch.bool, **pin), info_frame=torch.zeros(n, dtype=torch.int32, **pin),
-                info_misc=torch.zeros((n, 4), dtype=torch.uint8, **pin))
+                position=torch.zeros((n, 2), dtype=torch.float32, **pin), obs_u8=torch.zeros((n, 6), dtype=torch.uint8, **pin),
+                reward=torch.zeros(n, dtype=torch.float32, **pin), terminated=torch.zeros(n, dtype=torch.bool, **pin),
+                info_frame=torch.zeros(n, dtype=torch.int32, **pin), info_misc=torch.zeros((n, 4), dtype=torch.uint8, **pin),
+                truncated=torch.zeros(n, dtype=torch.bool))     # the reference never truncates (footsies.py:570)
+            out = _capi.FgHostOutputs(struct_size=C.sizeof(_capi.FgHostOutputs), reserved0=0)
+            for k in ("position", "obs_u8", "reward", "terminated", "info_frame", "info_misc"):
+                setattr(out, k, hb[k].data_ptr())
+            hb["out"] = out
+            u8 = hb["obs_u8"]
+            hb["obs"] = {"guard": u8[:, 0:2], "move": u8[:, 2:4], "move_frame": u8[:, 4:6], "position": hb["position"]}
+            hb["info"] = self._make_info_dict(hb["info_frame"], hb["info_misc"], hb["obs"])
+            self._host = hb
         return self._host
 
+    def _check_host_path(self):
+        if self.frame_delay > 0:
+            raise NotImplementedError("the host-buffer path delivers undelayed observations: use step() with frame_delay")
+
+    def reset_host(self, *, seed: Optional[int] = None, mask=None):
+        """reset() delivering (obs, info) to pinned host tensors (mask: host bool / uint8 [N] or None = all)."""
+        self._check_host_path()
+        hb = self._host_buffers()
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(device="cpu", dtype=torch.uint8).contiguous()
+            if m.numel() != self.num_envs:
+                raise ValueError("mask must have num_envs entries")
+        if seed is not None:
+            self.seed(seed, None if m is None else m.to(self.device))
+        _capi.check(self._lib.fg_reset_host_compact(self._handle, None if m is None else C.c_void_p(m.data_ptr()),
+                                                    C.byref(hb["out"]), self._stream()))
+        self.has_reset = True
+        return hb["obs"], hb["info"]
+
     def step_host(self, action=None, opponent_action=None):
-        """step() for callers that live on the CPU like the reference's agents: actions are read from host
-        memory and obs / reward / terminated / info are delivered to pinned host tensors (one C call:
-        H2D copy, kernel, D2H copies, sync).  Returns host tensors (reused between calls)."""
+        """step() for callers that live on the CPU like the reference's agents: actions are read from host memory and
+        obs / reward / terminated / info are delivered to pinned host tensors by one C call (fg_step_host_compact:
+        H2D copies, step kernel, pack kernel, D2H copies, pipelined in slices for large batches).  The observation
+        fields keep their natural types: guard, move, move_frame uint8 [N, 2], position float32 [N, 2] (the reference
+        returns Python ints and floats, footsies.py:362-367).  Returns host tensors that are reused between calls."""
         if not self.has_reset:
             raise RuntimeError("call reset() before step()")
+        self._check_host_path()
         hb = self._host_buffers()
         p1 = p2 = None
         if not self.by_example:
             a = _as_bitmask(action, self.num_envs, "cpu")
             if a.data_ptr() != hb["a1"].data_ptr():
-                hb["a1"].copy_(a)
-            p1 = C.c_void_p(hb["a1"].data_ptr())
+                if a.is_pinned() and a.is_contiguous():
+                    p1 = C.c_void_p(a.data_ptr())
+                else:
+                    hb["a1"].copy_(a)
+            if p1 is None:
+                p1 = C.c_void_p(hb["a1"].data_ptr())
         if self._opponent_mode != "bot":
             if opponent_action is None:
                 raise ValueError("opponent_action is required when the opponent is not the in-game bot")
             a = _as_bitmask(opponent_action, self.num_envs, "cpu")
             if a.data_ptr() != hb["a2"].data_ptr():
-                hb["a2"].copy_(a)
-            p2 = C.c_void_p(hb["a2"].data_ptr())
-        _capi.check(self._lib.fg_step_host(
-            self._handle, p1, p2, C.c_void_p(hb["obs"].data_ptr()), C.c_void_p(hb["reward"].data_ptr()),
-            C.c_void_p(hb["terminated"].data_ptr()), C.c_void_p(hb["info_frame"].data_ptr()),
-            C.c_void_p(hb["info_misc"].data_ptr()), self._stream()))
-        obs = self._make_obs_dict(hb["obs"])
-        info = self._make_info_dict(hb["info_frame"], hb["info_misc"], obs)
-        return obs, hb["reward"], hb["terminated"], torch.zeros_like(hb["terminated"]), info
+                if a.is_pinned() and a.is_contiguous():
+                    p2 = C.c_void_p(a.data_ptr())
+                else:
+                    hb["a2"].copy_(a)
+            if p2 is None:
+                p2 = C.c_void_p(hb["a2"].data_ptr())
+        _capi.check(self._lib.fg_step_host_compact(self._handle, p1, p2, C.byref(hb["out"]), self._stream()))
+        return hb["obs"], hb["reward"], hb["terminated"], hb["truncated"], hb["info"]
 
     def host_io_bytes_per_step(self):
         """(host->device, device->host) bytes moved by one step_host call."""
         n = self.num_envs
         h2d = n * ((0 if self.by_example else 1) + (0 if self._opponent_mode == "bot" else 1))
-        d2h = n * (32 + 4 + 1 + 4 + 4)
+        d2h = n * (8 + 6 + 4 + 1 + 4 + 4)
         return h2d, d2h
 
     # ------------------------------------------------------------------ state access, statistics

@@ -147,6 +147,28 @@ int32_t fg_step_host(fg_handle *h, const uint8_t *actions_p1, const uint8_t *act
 int32_t fg_reset_host(fg_handle *h, const uint8_t *mask, float *obs, int32_t *info_frame, uint8_t *info_misc,
                       void *stream);
 
+/* Compact host layout of one step's results: what FootsiesEnv.step returns (footsies.py:336-380, 555-570) with every
+ * field in its natural width -- the reference's guard / move / move_frame are Python ints, here bytes -- 27 bytes per
+ * battle instead of the 45 of the device layout, because the host-buffer call is bound by PCIe.  All pointers are HOST
+ * pointers (pinned memory for full PCIe speed); any pointer may be NULL to skip that field, except that position and
+ * obs_u8 go together. */
+typedef struct {
+    int32_t struct_size;
+    int32_t reserved0;
+    float *position;                /* [num_envs][2] obs["position"]                                           */
+    uint8_t *obs_u8;                /* [num_envs][6] obs["guard"] p1,p2 | obs["move"] index p1,p2 | obs["move_frame"] p1,p2 */
+    float *reward;                  /* [num_envs]                                                              */
+    uint8_t *terminated;            /* [num_envs]                                                              */
+    int32_t *info_frame;            /* [num_envs]                                                              */
+    uint8_t *info_misc;             /* [num_envs][4] as in fg_buffers                                          */
+} fg_host_outputs;
+/* fg_step_host / fg_reset_host delivering the compact layout.  Batches above 1 Mi battles are cut into slices that are
+ * pipelined over two library-owned streams (upload + simulate slice c+1 while slice c's results cross PCIe); the call
+ * is ordered after prior work on `stream` and returns when every result is in host memory. */
+int32_t fg_step_host_compact(fg_handle *h, const uint8_t *actions_p1, const uint8_t *actions_p2,
+                             const fg_host_outputs *out, void *stream);
+int32_t fg_reset_host_compact(fg_handle *h, const uint8_t *mask, const fg_host_outputs *out, void *stream);
+
 /* Replaces: remote-control STATE_SAVE / STATE_LOAD (footsies.py:432-444, BattleCore.cs:667-683) at the level
  * of the compact state.  out / in are HOST arrays of `count` entries starting at env `first`. Synchronous. */
 int32_t fg_get_state(fg_handle *h, int32_t first, int32_t count, fg_env_state *out);

@@ -85,24 +85,71 @@ def test_single_env_reference_style_loop(oracle):
     env.close()
 
 
-def test_host_buffer_step_matches_device_step(oracle):
+@pytest.mark.parametrize("chunk_envs", [None, 256])
+def test_host_buffer_step_matches_oracle(oracle, monkeypatch, chunk_envs):
+    """FootsiesEnv.step_host / reset_host (fg_step_host_compact: compact 27-byte host layout) against the oracle; with
+    chunk_envs = 256 the 1000 battles go through the sliced two-stream pipeline (3 whole slices + a ragged one)."""
     from footsies_gym_b200 import FootsiesEnv
     _require_cuda()
+    if chunk_envs:
+        monkeypatch.setenv("FOOTSIES_B200_HOST_CHUNK_ENVS", str(chunk_envs))
     n = 1000
     rng = np.random.default_rng(6)
     env = FootsiesEnv(num_envs=n, seed=5)
     orc = oracle.OracleBatch(n, p2_bot=True, seed=5)
-    env.reset()
-    orc.reset()
+    obs, info = env.reset_host()
+    tr = orc.reset()
+    keys = ("guard", "move", "move_frame", "position")
+    assert [obs[k].dtype for k in keys] == [torch.uint8] * 3 + [torch.float32]
+    assert np.array_equal(np.concatenate([obs[k].numpy() for k in keys], 1), tr["obs"])
+    assert np.array_equal(info["frame"].numpy(), tr["info_frame"])
     for t in range(200):
         a = rng.integers(0, 8, size=n, dtype=np.uint8)
+        if t % 2:
+            a = torch.from_numpy(a).pin_memory()      # pinned actions are uploaded from where they are
         obs, reward, term, trunc, info = env.step_host(a)
-        tr = orc.step(a)
-        assert np.array_equal(np.concatenate([obs[k].numpy() for k in ("guard", "move", "move_frame", "position")], 1),
-                              tr["obs"])
+        tr = orc.step(np.asarray(a))
+        assert np.array_equal(np.concatenate([obs[k].numpy() for k in keys], 1), tr["obs"])
         assert np.array_equal(reward.numpy(), tr["reward"])
         assert np.array_equal(term.numpy().astype(np.int32), tr["terminated"])
+        assert not trunc.any()
         assert np.array_equal(info["frame"].numpy(), tr["info_frame"])
+        assert np.array_equal(np.stack([info[k].numpy() for k in ("p1_action", "p2_action", "p1_hitstun", "p2_hitstun")], 1),
+                              np.concatenate([tr["info_action"], tr["info_hitstun"]], 1))
+        # the device-resident tensors hold the same step
+        assert np.array_equal(env.obs.cpu().numpy(), tr["obs"])
+    env.close()
+
+
+def test_host_buffer_f32_layout_and_self_play_slices(oracle, monkeypatch):
+    """fg_step_host (device layout: obs f32 [N][8]) through the sliced pipeline, self-play with an odd batch size."""
+    import ctypes as C
+    from footsies_gym_b200 import FootsiesEnv, _capi
+    _require_cuda()
+    monkeypatch.setenv("FOOTSIES_B200_HOST_CHUNK_ENVS", "512")
+    n = 1337
+    rng = np.random.default_rng(9)
+    env = FootsiesEnv(num_envs=n, opponent="self_play", seed=1)
+    orc = oracle.OracleBatch(n, p2_bot=False, seed=1)
+    env.reset()
+    orc.reset()
+    obs = np.zeros((n, 8), np.float32); reward = np.zeros(n, np.float32); term = np.zeros(n, np.uint8)
+    frame = np.zeros(n, np.int32); misc = np.zeros((n, 4), np.uint8)
+    ptr = lambda x: C.c_void_p(x.ctypes.data)
+    for t in range(150):
+        a1 = rng.integers(0, 8, size=n, dtype=np.uint8)
+        a2 = rng.integers(0, 8, size=n, dtype=np.uint8)
+        _capi.check(env._lib.fg_step_host(env._handle, ptr(a1), ptr(a2), ptr(obs), ptr(reward), ptr(term), ptr(frame),
+                                          ptr(misc), None))
+        tr = orc.step(a1, a2)
+        assert np.array_equal(obs, tr["obs"]) and np.array_equal(reward, tr["reward"])
+        assert np.array_equal(term.astype(np.int32), tr["terminated"]) and np.array_equal(frame, tr["info_frame"])
+        assert np.array_equal(misc, np.concatenate([tr["info_action"], tr["info_hitstun"]], 1))
+        # and the compact layout of the same state
+        o2, r2, t2, _, i2 = env.step_host(a1, a2)
+        tr = orc.step(a1, a2)
+        assert np.array_equal(np.concatenate([o2[k].numpy() for k in ("guard", "move", "move_frame", "position")], 1), tr["obs"])
+        assert np.array_equal(r2.numpy(), tr["reward"])
     env.close()
 
 
