@@ -205,8 +205,8 @@ _REAL_STDOUT = os.dup(1)
 
 def run_rollout(args, rank, world, dev, dist):
     """--workload rollout: BASELINE configs[4] on N GPUs.  One bench step = one 128-step horizon for 16384 envs per
-    GPU: fused MLP policy inference + sampling (fg_policy_mlp_sample) and the simulator step (fg_step) alternate on
-    device, rollout buffers are written in place, the horizon is one CUDA-graph replay."""
+    GPU, one launch of the whole-horizon rollout kernel (fg_rollout_mlp: MLP policy inference + sampling + simulator step,
+    battle state in registers for the whole horizon, rollout buffers written in place)."""
     import torch
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
@@ -215,6 +215,7 @@ def run_rollout(args, rank, world, dev, dist):
     env = FootsiesEnv(num_envs=n, device=dev, opponent=None, seed=0, first_env_index=rank * n)
     torch.manual_seed(0)
     col = RolloutCollector(env, MLPPolicy(64).to(dev), horizon=horizon, use_cuda_graph=True, seed=rank)
+    assert col.mode == "horizon", col.mode
     for _ in range(max(args.warmup, 3)):
         col.collect()
     torch.cuda.synchronize(dev)
@@ -241,12 +242,12 @@ def run_rollout(args, rank, world, dev, dist):
         emit({"metric": METRIC, "value": int(f.item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
               "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
               "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
-              "config": {"workload": "E: PPO rollout, MLP 8-64-64-8 policy (fused inference + sampling kernel) reading the "
-                                     "observation tensor in place, 16384 envs per GPU x 128-step horizon per bench step, "
+              "config": {"workload": "E: PPO rollout, MLP 8-64-64-8 policy fused with the simulator step into one launch per "
+                                     "horizon (fg_rollout_mlp), 16384 envs per GPU x 128-step horizon per bench step, "
                                      "vs in-game BattleAI, frame-skip 1 (BASELINE configs[4])",
                          "envs_per_gpu": n, "horizon": horizon, "l2": "working set fits L2 (latency-bound regime); not the "
                          "roofline workload"},
-              "gpu_launches": (env.launch_count() - l0) * 2, "episode_stats_all_ranks": stats})
+              "gpu_launches": env.launch_count() - l0, "episode_stats_all_ranks": stats})
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -434,8 +435,8 @@ def main():
             e = FootsiesEnv(num_envs=n_envs, device=dev, opponent=None, seed=0)
             pol = MLPPolicy().to(dev)
             out = {}
-            for name, graph, fused in (("fused_policy_kernel_cuda_graph", True, True), ("torch_policy_cuda_graph", True, False),
-                                       ("torch_policy_eager", False, False)):
+            for name, graph, fused in (("horizon_kernel", False, "horizon"), ("fused_policy_kernel_cuda_graph", True, "step"),
+                                       ("torch_policy_cuda_graph", True, False), ("torch_policy_eager", False, False)):
                 col = RolloutCollector(e, pol, horizon=horizon, use_cuda_graph=graph, fused=fused)
                 col.collect()
                 torch.cuda.synchronize(dev)
@@ -451,8 +452,10 @@ def main():
                 out[name] = {"env_frames_per_sec": fr / (ms * 1e-3), "ms_per_horizon": ms / reps}
             e.close()
             out.update(envs=n_envs, horizon=horizon, policy="MLP 8-64-64-8 tanh fp32, categorical sampling",
-                       note="per GPU; policy forward + sampling + rollout-buffer writes inside the timed region; the fused "
-                            "path is 2 launches per step (fg_policy_mlp_sample + fg_step) with zero-copy rollout buffers")
+                       note="per GPU; policy forward + sampling + rollout-buffer writes inside the timed region; horizon_kernel "
+                            "is one launch per horizon (fg_rollout_mlp, battle state in registers throughout); "
+                            "fused_policy_kernel is 2 launches per step (fg_policy_mlp_sample + fg_step) with zero-copy "
+                            "rollout buffers")
             return out
         extra["E_ppo_rollout_16384x128"] = ppo_rollout()
 

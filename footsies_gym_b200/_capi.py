@@ -35,6 +35,14 @@ class FgHostOutputs(C.Structure):
                 ("info_frame", C.c_void_p), ("info_misc", C.c_void_p)]
 
 
+class FgRolloutBuffers(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("hidden", C.c_int32), ("horizon", C.c_int32), ("reserved0", C.c_int32),
+                ("scale", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w3", C.c_void_p), ("b3", C.c_void_p), ("seed", C.c_uint64), ("counter_base", C.c_void_p),
+                ("obs", C.c_void_p), ("actions", C.c_void_p), ("logp", C.c_void_p), ("rewards", C.c_void_p),
+                ("dones", C.c_void_p)]
+
+
 class FgFighterState(C.Structure):
     _fields_ = [("pos_x", C.c_float), ("velocity_x", C.c_float), ("action_id", C.c_int32),
                 ("action_frame", C.c_int32), ("hitstun", C.c_int32), ("guard", C.c_int32), ("vital", C.c_int32),
@@ -71,7 +79,8 @@ _lib = None
 EXPORTS = ["fg_abi_version", "fg_last_error", "fg_algorithmic_bytes_per_env_step", "fg_create", "fg_destroy",
            "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_step_host_compact",
            "fg_reset_host_compact", "fg_get_state",
-           "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_last_error"]
+           "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_last_error",
+           "fg_rollout_mlp"]
 
 
 def load(build_if_missing=True):
@@ -121,6 +130,8 @@ def load(build_if_missing=True):
     L.fg_policy_mlp_sample.restype = i32
     L.fg_policy_mlp_sample.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
     L.fg_policy_last_error.restype = C.c_char_p
+    L.fg_rollout_mlp.restype = i32
+    L.fg_rollout_mlp.argtypes = [vp, C.POINTER(FgRolloutBuffers), vp]
     if L.fg_abi_version() != 1:
         raise FootsiesLibraryError("libfootsies_b200.so ABI version mismatch")
     _lib = L

@@ -30,13 +30,14 @@ def _nvcc():
 
 def sources():
     return [os.path.join(CSRC, "footsies_kernels.cu"), os.path.join(CSRC, "step_instances.cu"),
-            os.path.join(CSRC, "policy_kernel.cu")]
+            os.path.join(CSRC, "policy_kernel.cu"), os.path.join(CSRC, "rollout_kernel.cu")]
 
 
 def deps():
     inc = os.path.join(os.path.dirname(PKG_DIR), "include", "footsies_b200.h")
     return sources() + [os.path.join(CSRC, f) for f in ("state_codec.h", "frame_tables.h", "frame_logic.cuh",
-                                                        "tables_host.h", "step_kernel.cuh")] + [inc]
+                                                        "tables_host.h", "step_kernel.cuh", "policy_mlp.cuh",
+                                                        "rollout_kernel.h")] + [inc]
 
 
 def is_stale(lib_path=None):
@@ -49,9 +50,12 @@ def is_stale(lib_path=None):
 
 def translation_units():
     """(object name, source, extra defines)"""
-    # the policy kernel is ordinary fp32 inference: FMA contraction allowed there
+    # The policy arithmetic (policy_mlp.cuh) spells its multiply-adds as explicit fmaf; both translation units that use
+    # it are compiled with -fmad=false like everything else (the rollout kernel holds the simulator too), so that no
+    # other expression is contracted in one and not in the other: their logits and log-probabilities are bit-identical.
     units = [("abi.o", os.path.join(CSRC, "footsies_kernels.cu"), []),
-             ("policy.o", os.path.join(CSRC, "policy_kernel.cu"), ["-fmad=true"])]
+             ("policy.o", os.path.join(CSRC, "policy_kernel.cu"), []),
+             ("rollout.o", os.path.join(CSRC, "rollout_kernel.cu"), [])]
     for kf in (0, 1):
         for b1 in (0, 1):
             for b2 in (0, 1):

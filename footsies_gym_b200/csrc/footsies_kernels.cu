@@ -2,6 +2,7 @@
 // step_kernel.cuh.
 #include <stdlib.h>
 
+#include "rollout_kernel.h"
 #include "step_kernel.cuh"
 
 using namespace fg;
@@ -434,6 +435,31 @@ int32_t fg_read_stats(fg_handle *h, uint64_t *out, void *stream) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaMemcpyAsync(out, h->buf.stats, sizeof(uint64_t) * FG_STAT_COUNT, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return FG_OK;
+}
+
+int32_t fg_rollout_mlp(fg_handle *h, const fg_rollout_buffers *r, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    if (!r || r->struct_size != (int32_t)sizeof(fg_rollout_buffers))
+        return fail(FG_ERR_INVALID_ARGUMENT, "fg_rollout_buffers is null or its struct_size does not match%s");
+    if (h->cfg.p1_bot || !h->cfg.p2_bot || !h->cfg.autoreset || h->buf.step_mask)
+        return fail(FG_ERR_INVALID_STATE, "fg_rollout_mlp needs P1 = policy, P2 = in-game bot, autoreset on, no step mask "
+                                          "(use fg_policy_mlp_sample + fg_step for other configurations)%s");
+    if (r->hidden != 32 && r->hidden != 64 && r->hidden != 128) return fail(FG_ERR_INVALID_ARGUMENT, "hidden size must be 32, 64 or 128%s");
+    if (r->horizon < 1) return fail(FG_ERR_INVALID_ARGUMENT, "horizon must be positive%s");
+    if (!r->scale || !r->w1 || !r->b1 || !r->w2 || !r->b2 || !r->w3 || !r->b3 || !r->obs || !r->actions || !r->logp || !r->rewards || !r->dones)
+        return fail(FG_ERR_INVALID_ARGUMENT, "fg_rollout_buffers: null pointer%s");
+    if (((uintptr_t)r->obs & 15u) || ((uintptr_t)r->w2 & 15u)) return fail(FG_ERR_INVALID_ARGUMENT, "obs and w2 must be 16-byte aligned%s");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    RolloutParams rp;
+    rp.sim = make_params(h);
+    rp.w = { r->scale, r->w1, r->b1, r->w2, r->b2, r->w3, r->b3 };
+    rp.seed = r->seed; rp.counter_base = (const unsigned long long *)r->counter_base;
+    rp.hidden = r->hidden; rp.horizon = r->horizon;
+    rp.obs = (float4 *)r->obs; rp.actions = r->actions; rp.logp = r->logp; rp.rewards = r->rewards; rp.dones = r->dones;
+    CUDA_TRY(launch_rollout(h->cfg.dense_reward != 0, (cudaStream_t)stream, rp));
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
     return FG_OK;
 }
 

@@ -4,13 +4,16 @@ The reference's training loops step one socket-connected game per process and mo
 (footsies.py:518-570, 633-661).  Here a whole horizon of policy-forward -> sample -> FootsiesEnv.step for N battles is
 a sequence of device kernels with no host round trip, captured once into a CUDA graph and replayed.
 
-Two policy paths:
+Three policy paths:
   * any torch callable `policy(obs[N, 8]) -> logits[N, 8]` (a dozen small torch kernels per step);
-  * `MLPPolicy` with `fused=True` (default when the policy is an MLPPolicy): one hand-written kernel per step
-    (csrc/policy_kernel.cu, fg_policy_mlp_sample) does scale -> 8-H-H-8 tanh MLP -> log-softmax -> sample, and the
-    rollout needs no copies at all: the step kernel is re-bound, per captured launch, to write observation t + 1,
-    reward t and done t straight into the rollout buffers, and the policy kernel reads observation t from there.
-    Per step: 2 launches (policy, simulator step).
+  * `MLPPolicy`, fused="step": one hand-written kernel per step (csrc/policy_kernel.cu, fg_policy_mlp_sample) does
+    scale -> 8-H-H-8 tanh MLP -> log-softmax -> sample, and the rollout needs no copies at all: the step kernel is
+    re-bound, per captured launch, to write observation t + 1, reward t and done t straight into the rollout buffers,
+    and the policy kernel reads observation t from there.  Per step: 2 launches (policy, simulator step).
+  * `MLPPolicy`, fused="horizon" (the default whenever the env qualifies: P1 = policy, P2 = in-game bot, autoreset, no
+    step mask): ONE launch per horizon (csrc/rollout_kernel.cu, fg_rollout_mlp) -- a CTA keeps its 64 battles in
+    registers from the first step to the last and alternates policy inference and the frame update; bit-identical
+    to the per-step path.
 
 PyTorch is plumbing here (parameters, buffers, CUDA graph); the simulator step inside the loop is fg_step.
 """
@@ -68,15 +71,29 @@ class RolloutCollector:
     the observation after the last step), actions uint8 [horizon, N], logp / rewards float32 [horizon, N], dones bool."""
 
     def __init__(self, env: FootsiesEnv, policy: Callable[[torch.Tensor], torch.Tensor], horizon: int = 128,
-                 use_cuda_graph: bool = True, fused: Optional[bool] = None, seed: int = 0):
+                 use_cuda_graph: bool = True, fused=None, seed: int = 0):
+        """fused: None / True = the most fused path available ("horizon", else "step", else torch ops for a policy that
+        is not an MLPPolicy); False = torch ops; "step" / "horizon" = that path or an error."""
         if env.by_example:
             raise ValueError("the policy drives P1: create the env with by_example=False")
         if env.frame_delay:
             raise ValueError("RolloutCollector binds the env's outputs directly: frame_delay must be 0")
         self.env, self.policy, self.horizon = env, policy, int(horizon)
-        self.fused = isinstance(policy, MLPPolicy) and policy.hidden in (32, 64, 128) if fused is None else bool(fused)
-        if self.fused and not isinstance(policy, MLPPolicy):
-            raise ValueError("fused=True needs an MLPPolicy")
+        can_step = isinstance(policy, MLPPolicy) and policy.hidden in (32, 64, 128)
+        can_horizon = (can_step and env._opponent_mode == "bot" and env.autoreset and env._step_mask is None)
+        if fused is None or fused is True:
+            if fused and not can_step:
+                raise ValueError("fused=True needs an MLPPolicy with hidden in {32, 64, 128}")
+            self.mode = "horizon" if can_horizon else "step" if can_step else "torch"
+        elif fused is False:
+            self.mode = "torch"
+        elif fused in ("step", "horizon"):
+            if not (can_horizon if fused == "horizon" else can_step):
+                raise ValueError(f"fused={fused!r} is not available for this policy / env configuration")
+            self.mode = fused
+        else:
+            raise ValueError("fused must be None, a bool, 'step' or 'horizon'")
+        self.fused = self.mode != "torch"
         n, dev, h = env.num_envs, env.device, self.horizon
         self.obs = torch.zeros((h + 1, n, 8), dtype=torch.float32, device=dev)
         self.actions = torch.zeros((h, n), dtype=torch.uint8, device=dev)
@@ -91,12 +108,30 @@ class RolloutCollector:
             env.reset()
         self.obs[h].copy_(env.obs)                                  # the observation the first step will act on
 
+    def _horizon_launch(self):
+        """fg_rollout_mlp: the whole horizon in one launch on the current stream."""
+        env, pol = self.env, self.policy
+        l1, l2, l3 = pol.net[0], pol.net[2], pol.net[4]
+        r = _capi.FgRolloutBuffers(struct_size=C.sizeof(_capi.FgRolloutBuffers), hidden=pol.hidden, horizon=self.horizon,
+                                   reserved0=0, seed=self._seed & (2**64 - 1))
+        ts = dict(scale=pol.scale, w1=l1.weight, b1=l1.bias, w2=l2.weight, b2=l2.bias, w3=l3.weight, b3=l3.bias,
+                  counter_base=self._drawn, obs=self.obs, actions=self.actions, logp=self.logp, rewards=self.rewards,
+                  dones=self.dones)
+        for k, t in ts.items():
+            if not t.is_contiguous() or t.device != env.device:
+                raise ValueError(f"fused rollout needs contiguous tensors on the env's device ({k})")
+            setattr(r, k, t.data_ptr())
+        _capi.check(env._lib.fg_rollout_mlp(env._handle, C.byref(r), env._stream()))
+        self._drawn.add_(self.horizon)
+
     @torch.no_grad()
     def _one_horizon(self):
         env, h = self.env, self.horizon
+        if self.mode == "horizon":
+            return self._horizon_launch()
         self.obs[0].copy_(self.obs[h])                              # carry the last observation over
         for t in range(h):
-            if self.fused:
+            if self.mode == "step":
                 self.policy.fused_sample(self.obs[t], self.actions[t], self.logp[t], self._seed, t, self._drawn)
             else:
                 logits = self.policy(self.obs[t])
@@ -112,7 +147,7 @@ class RolloutCollector:
     def collect(self):
         """Runs one horizon; returns the rollout buffers (views, overwritten by the next call)."""
         dev = self.env.device
-        if not self.use_cuda_graph:
+        if not self.use_cuda_graph or self.mode == "horizon":      # one launch: nothing for a graph to save
             self._one_horizon()
         else:
             if self._graph is None:

@@ -193,6 +193,27 @@ int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *
                              float *obs_copy, void *stream);
 const char *fg_policy_last_error(void);
 
+/* BASELINE.json configs[4] as ONE launch per horizon: for t = 0 .. horizon - 1 { policy(obs[t]) -> sample -> actions[t],
+ * logp[t]; FootsiesEnv.step -> obs[t + 1], rewards[t], dones[t] } for every battle of the handle, with the battle state in
+ * registers throughout (csrc/rollout_kernel.cu).  obs[0] is first overwritten with obs[horizon] (the observation the
+ * previous horizon, or the reset, ended on).  Bit-identical to `horizon` rounds of fg_policy_mlp_sample(counter = t) +
+ * fg_step.  Needs p1_bot = 0, p2_bot = 1, autoreset = 1, no step mask.  All pointers are DEVICE pointers. */
+typedef struct {
+    int32_t struct_size;
+    int32_t hidden;                 /* 32, 64 or 128                                                           */
+    int32_t horizon;
+    int32_t reserved0;
+    const float *scale, *w1, *b1, *w2, *b2, *w3, *b3;   /* as in fg_policy_mlp_sample                          */
+    uint64_t seed;
+    const uint64_t *counter_base;   /* optional device word: policy steps drawn before this horizon            */
+    float *obs;                     /* [horizon + 1][num_envs][8]                                              */
+    uint8_t *actions;               /* [horizon][num_envs]                                                     */
+    float *logp;                    /* [horizon][num_envs]                                                     */
+    float *rewards;                 /* [horizon][num_envs]                                                     */
+    uint8_t *dones;                 /* [horizon][num_envs]                                                     */
+} fg_rollout_buffers;
+int32_t fg_rollout_mlp(fg_handle *h, const fg_rollout_buffers *r, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("use_graph,fused", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("use_graph,fused", [(False, False), (True, False), (False, "step"), (True, "step"),
+                                             (False, "horizon")])
 def test_rollout_is_replayable(oracle, use_graph, fused):
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
@@ -51,6 +52,57 @@ def test_rollout_is_replayable(oracle, use_graph, fused):
         tr = orc.step(out["actions"][t].cpu().numpy())
         assert np.array_equal(out["rewards"][t].cpu().numpy(), tr["reward"])
         assert np.array_equal(out["dones"][t].cpu().numpy().astype(np.int32), tr["terminated"])
+
+
+@pytest.mark.parametrize("hidden,n,dense,frame_skip", [(64, 1000, True, 1), (32, 64, False, 1), (128, 333, True, 3),
+                                                       (64, 16384, True, 1)])
+def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip):
+    """fg_rollout_mlp (one launch per horizon, state in registers) against fg_policy_mlp_sample + fg_step per step:
+    every rollout buffer, the final battle state and the episode statistics are bit-identical, over several horizons
+    (ragged batch sizes: 1000 and 333 are not multiples of the 64 battles a CTA owns)."""
+    from footsies_gym_b200 import FootsiesEnv
+    from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(hidden + n)
+    policy = MLPPolicy(hidden).to(dev)
+    with torch.no_grad():
+        for prm in policy.net.parameters():
+            prm.mul_(2.0)
+    horizon = 150                                           # > 120 frames: the statistics byte lanes are folded mid-horizon
+    envs, cols = [], []
+    for mode in ("step", "horizon"):
+        env = FootsiesEnv(num_envs=n, device=dev, seed=3, dense_reward=dense, frame_skip=frame_skip)
+        envs.append(env)
+        cols.append(RolloutCollector(env, policy, horizon=horizon, use_cuda_graph=False, fused=mode, seed=17))
+    assert [c.mode for c in cols] == ["step", "horizon"]
+    for r in range(3):
+        outs = [c.collect() for c in cols]
+        torch.cuda.synchronize()
+        for k in ("obs", "actions", "logp", "rewards", "dones", "last_obs"):
+            assert torch.equal(outs[0][k], outs[1][k]), (r, k)
+        assert outs[0]["dones"].any()
+        s0, s1 = envs[0].get_state(), envs[1].get_state()
+        assert s0.tobytes() == s1.tobytes(), r
+        assert envs[0].episode_stats() == envs[1].episode_stats(), r
+        assert torch.equal(envs[0].info_frame, envs[1].info_frame) and torch.equal(envs[0].info_misc, envs[1].info_misc)
+    launches = [e.launch_count() for e in envs]
+    assert launches[1] < launches[0] // 50                  # 1 launch per horizon instead of 1 per step (+ the policy's)
+
+
+def test_horizon_kernel_rejects_other_configurations():
+    from footsies_gym_b200 import FootsiesEnv
+    from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    dev = torch.device("cuda:0")
+    policy = MLPPolicy(64).to(dev)
+    env = FootsiesEnv(num_envs=64, device=dev, autoreset=False)
+    with pytest.raises(ValueError):
+        RolloutCollector(env, policy, horizon=8, fused="horizon")
+    assert RolloutCollector(env, policy, horizon=8).mode == "step"
+    assert RolloutCollector(FootsiesEnv(num_envs=64, device=dev), policy, horizon=8).mode == "horizon"
 
 
 @pytest.mark.parametrize("hidden", [32, 64, 128])
