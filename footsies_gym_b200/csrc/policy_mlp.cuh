@@ -26,9 +26,14 @@ struct PolicyWeights {
 };
 
 __device__ __forceinline__ float fast_tanh(float x) {
-    // tanh(x) = 1 - 2 / (exp(2x) + 1); __expf keeps the relative error ~1e-6, far below what PPO's ratios resolve
-    const float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    // tanh(x) = 1 - 2 / (exp(2x) + 1) on the two MUFU approximations (relative error ~1e-6, far below what PPO's
+    // ratios resolve): 5 instructions.  Same value as 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f), whose
+    // denormal fix-ups (12 instructions) can never fire here: the divisor is >= 1, and exp(2x) flushed to 0 or +inf
+    // saturates the result to -1 / +1 either way.
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900432586669921875f));   // 2 * log2(e), = 2 * the constant __expf uses
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
 }
 
 __device__ __forceinline__ uint32_t hash3(uint64_t seed, uint64_t counter, uint32_t idx) {
@@ -187,6 +192,159 @@ __device__ __forceinline__ int policy_sample(const float (&lg)[8], uint32_t rnd,
     for (int o = 0; o < 8; o++) { c += e[o]; if (a == 7 && target < c) { a = o; la = lg[o]; } }
     logp = (la - m) - __logf(z);
     return a;
+}
+
+// ---- second mapping of the same arithmetic: one warp per quarter of the hidden units, lanes = battles ----------------
+// Used by the whole-horizon rollout kernel.  In the mapping above the 4 threads of an env sit in one quarter-warp, so a
+// 128-bit weight fetch delivers only 4 distinct words per shared-memory wavefront (measured: 98 wavefronts per env-step,
+// shared-memory pipe 61 % busy at 16 384 envs).  Here warp w of a 4-warp CTA owns hidden units w * Q .. w * Q + Q - 1 for
+// all of the CTA's battles and every lane carries E battles (lane, lane + 32, ...): weight fetches are warp-wide
+// broadcasts (one wavefront serves 32 x E battles), activations cross between the warps through shared memory
+// ([unit][battle], conflict-free), and the layer-2 loop over the inputs stays a loop (small code: the fully unrolled
+// version thrashed the instruction cache).  Every output unit accumulates in the same order as above -- bias first,
+// inputs ascending, layer-3 quarters combined as (s0 + s1) + (s2 + s3) -- so the logits are bit-identical.
+template <int H, int NE>
+struct PolicySmemBcast {
+    static_assert(H % 16 == 0 && H <= kMaxHidden, "hidden size");
+    static constexpr int Q = H / 4;
+    static constexpr int kW1T = 0, kW2T = kW1T + 8 * H, kW3T = kW2T + H * H, kB1 = kW3T + 8 * H, kB2 = kB1 + H, kB3 = kB2 + H,
+                         kScale = kB3 + 8, kHid = kScale + 8, kPart = kHid + H * NE, kFloats = kPart + 4 * 8 * NE;
+    static constexpr size_t kBytes = sizeof(float) * kFloats;
+};
+
+// w1t[k][u] = W1[u][k], w2t[k][u] = W2[u][k], w3t[c][o] = W3[o][c] (input-major: the outputs of one input are contiguous).
+template <int H, int NE>
+__device__ __forceinline__ void policy_stage_bcast(float *sm, const PolicyWeights &p, int tid, int nthreads) {
+    using L = PolicySmemBcast<H, NE>;
+    for (int i = tid; i < H * 8; i += nthreads) {
+        const int u = i / 8, k = i % 8;            // W1[u][k]
+        sm[L::kW1T + k * H + u] = p.w1[i];
+        sm[L::kW3T + (i % H) * 8 + i / H] = p.w3[i];   // W3[o][c], i = o * H + c
+    }
+    for (int i = tid; i < H * H / 4; i += nthreads) {
+        const float4 v = reinterpret_cast<const float4 *>(p.w2)[i];   // W2[u][k .. k + 3]
+        const int u = (4 * i) / H, k = (4 * i) % H;
+        float *dst = sm + L::kW2T + u;
+        dst[(k + 0) * H] = v.x; dst[(k + 1) * H] = v.y; dst[(k + 2) * H] = v.z; dst[(k + 3) * H] = v.w;
+    }
+    for (int i = tid; i < H; i += nthreads) { sm[L::kB1 + i] = p.b1[i]; sm[L::kB2 + i] = p.b2[i]; }
+    if (tid < 8) { sm[L::kB3 + tid] = p.b3[tid]; sm[L::kScale + tid] = p.scale[tid]; }
+}
+
+// All 128 threads of the CTA.  x[e] = raw observation row of battle lane + 32 e.  On return (after the function's last
+// __syncthreads) the partial logits of every battle are in shared memory: policy_logits_of() assembles them.
+// The multiply-adds are issued as packed pairs (__ffma2_rn, Blackwell's FFMA2: two independent correctly rounded fp32
+// fmas per instruction, i.e. bit-identical to two fmaf) over adjacent output units: the policy phase is bound by the
+// FMA pipe (one warp instruction per 2 cycles per scheduler), so pairs halve its time.
+template <int H, int E>
+__device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int lane, float (&x)[E][8]) {
+    constexpr int NE = 32 * E;
+    using L = PolicySmemBcast<H, NE>;
+    constexpr int Q = L::Q;
+    const float *w1t = sm + L::kW1T + warp * Q, *w2t = sm + L::kW2T + warp * Q, *w3t = sm + L::kW3T + warp * Q * 8;
+    const float *b1 = sm + L::kB1 + warp * Q, *b2 = sm + L::kB2 + warp * Q, *sc = sm + L::kScale;
+    float *hid = sm + L::kHid, *part = sm + L::kPart;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[e][k] = x[e][k] * sc[k];
+    }
+    float2 acc[E][Q / 2];                           // acc[e][j2] = units 2 * j2, 2 * j2 + 1 of this warp's quarter
+    // layer 1
+#pragma unroll
+    for (int j2 = 0; j2 < Q / 2; j2++) {
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e][j2] = make_float2(b1[2 * j2], b1[2 * j2 + 1]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+#pragma unroll
+        for (int j4 = 0; j4 < Q / 4; j4++) {
+            const float4 v = *reinterpret_cast<const float4 *>(w1t + k * H + 4 * j4);
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const float2 xk = make_float2(x[e][k], x[e][k]);
+                acc[e][2 * j4] = __ffma2_rn(make_float2(v.x, v.y), xk, acc[e][2 * j4]);
+                acc[e][2 * j4 + 1] = __ffma2_rn(make_float2(v.z, v.w), xk, acc[e][2 * j4 + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j2 = 0; j2 < Q / 2; j2++) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            hid[(warp * Q + 2 * j2) * NE + lane + 32 * e] = fast_tanh(acc[e][j2].x);
+            hid[(warp * Q + 2 * j2 + 1) * NE + lane + 32 * e] = fast_tanh(acc[e][j2].y);
+        }
+    }
+    __syncthreads();
+    // layer 2: all H inputs from shared memory, this warp's Q outputs
+#pragma unroll
+    for (int j2 = 0; j2 < Q / 2; j2++) {
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e][j2] = make_float2(b2[2 * j2], b2[2 * j2 + 1]);
+    }
+#pragma unroll 4
+    for (int k = 0; k < H; k++) {
+        float2 hk[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) { const float h = hid[k * NE + lane + 32 * e]; hk[e] = make_float2(h, h); }
+#pragma unroll
+        for (int j4 = 0; j4 < Q / 4; j4++) {
+            const float4 v = *reinterpret_cast<const float4 *>(w2t + k * H + 4 * j4);
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                acc[e][2 * j4] = __ffma2_rn(make_float2(v.x, v.y), hk[e], acc[e][2 * j4]);
+                acc[e][2 * j4 + 1] = __ffma2_rn(make_float2(v.z, v.w), hk[e], acc[e][2 * j4 + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j2 = 0; j2 < Q / 2; j2++) {
+#pragma unroll
+        for (int e = 0; e < E; e++) acc[e][j2] = make_float2(fast_tanh(acc[e][j2].x), fast_tanh(acc[e][j2].y));
+    }
+    // layer 3: this warp's quarter of every logit; pairs run over adjacent outputs (w3t[j][o] = W3[o][j]), every logit
+    // still accumulates its quarter in ascending j from 0
+    float2 s[E][4];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+#pragma unroll
+        for (int o2 = 0; o2 < 4; o2++) s[e][o2] = make_float2(0.0f, 0.0f);
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        const float4 va = *reinterpret_cast<const float4 *>(w3t + j * 8), vb = *reinterpret_cast<const float4 *>(w3t + j * 8 + 4);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const float h = (j & 1) ? acc[e][j >> 1].y : acc[e][j >> 1].x;
+            const float2 hj = make_float2(h, h);
+            s[e][0] = __ffma2_rn(make_float2(va.x, va.y), hj, s[e][0]); s[e][1] = __ffma2_rn(make_float2(va.z, va.w), hj, s[e][1]);
+            s[e][2] = __ffma2_rn(make_float2(vb.x, vb.y), hj, s[e][2]); s[e][3] = __ffma2_rn(make_float2(vb.z, vb.w), hj, s[e][3]);
+        }
+    }
+#pragma unroll
+    for (int o2 = 0; o2 < 4; o2++) {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            part[(warp * 8 + 2 * o2) * NE + lane + 32 * e] = s[e][o2].x;
+            part[(warp * 8 + 2 * o2 + 1) * NE + lane + 32 * e] = s[e][o2].y;
+        }
+    }
+    __syncthreads();
+}
+
+// The 8 logits of battle `local` (0 .. NE - 1) from the partial sums left by policy_partials_bcast.
+template <int H, int NE>
+__device__ __forceinline__ void policy_logits_of(const float *sm, int local, float (&lg)[8]) {
+    using L = PolicySmemBcast<H, NE>;
+    const float *part = sm + L::kPart, *b3 = sm + L::kB3;
+#pragma unroll
+    for (int o = 0; o < 8; o++) {
+        const float s0 = part[(0 * 8 + o) * NE + local], s1 = part[(1 * 8 + o) * NE + local];
+        const float s2 = part[(2 * 8 + o) * NE + local], s3 = part[(3 * 8 + o) * NE + local];
+        lg[o] = ((s0 + s1) + (s2 + s3)) + b3[o];
+    }
 }
 
 }  // namespace fgp

@@ -2,17 +2,19 @@
 // `horizon` times, for every battle of the device, with the battle state held in registers for the whole horizon.
 //
 // Battles never interact and the policy only couples them through its (read-only) weights, so a horizon needs no
-// grid-wide synchronisation: a CTA owns 128 battles (64 at H = 128) from the first step to the last.  Per step and CTA:
-//   policy phase   all 128 threads: four threads per battle, four battles per thread (policy_mlp.cuh), observations read
-//                  from shared memory, sampled input bitmask handed to the simulator threads through shared memory and
-//                  written, with its log-probability, to slot t of the rollout buffers;
-//   simulator phase  one thread per battle: the reference frame update (frame_logic.cuh; autoreset, bot query,
-//                  reward and termination exactly as step_kernel does it), observation t + 1 / reward t / done t written
-//                  to the rollout buffers and observation t + 1 left in shared memory for the next policy phase.
+// grid-wide synchronisation: a CTA of 128 threads owns 32 x E battles from the first step to the last.  Per step and CTA:
+//   policy phase   all 4 warps: warp w computes hidden units w * H/4 .. of every battle of the CTA, lanes = battles
+//                  (policy_mlp.cuh, second mapping: weight fetches are warp-wide shared-memory broadcasts, activations
+//                  cross between warps through shared memory), ending with the partial logits in shared memory;
+//   simulator phase  one thread per battle: assemble the 8 logits, log-softmax, sample the input bitmask, then the
+//                  reference frame update (frame_logic.cuh; autoreset, bot query, reward and termination exactly as
+//                  step_kernel does it); action t / log-probability t / observation t + 1 / reward t / done t go to the
+//                  rollout buffers and observation t + 1 stays in shared memory for the next policy phase.
 // Against the two launches per step of the per-step path (policy kernel + step kernel in a CUDA graph) this removes
 // 2 x horizon launches, every state load / store but one, and the observation round trip through L2.  Several CTAs are
-// resident per SM (46 KB of shared memory each at H = 64), so one CTA's latency-bound simulator phase overlaps
-// another's FMA-bound policy phase.  Results are bit-identical to the per-step path (tests/test_rollout.py).
+// resident per SM.  (Tried: starting every second co-resident CTA half a step late so that simulator and policy phases
+// interleave -- no measurable effect, removed.)
+// Results are bit-identical to the per-step path (tests/test_rollout.py).
 // Compiled with -fmad=false like the step kernel; the policy arithmetic uses explicit fmaf.
 #include <stdlib.h>
 
@@ -24,44 +26,38 @@ using namespace fgp;
 
 constexpr int kRollThreads = 128;
 
-// E = battles per policy thread: every weight word fetched from shared memory (the policy phase is bound by those
-// fetches) is used E times, and E x 32 battles per CTA keep E warps busy in the simulator phase.  E = 4 where the
-// registers allow it (H <= 64: h1 / h2 are 2 x 4 x 16 floats), E = 2 for H = 128.
-template <int E_> struct RolloutShape { static constexpr int E = E_, kEnvs = (kRollThreads / 4) * E_; };
-
-template <int H, int E_>
+template <int H, int E>
 struct RolloutSmem {
-    static constexpr int kRollEnvs = RolloutShape<E_>::kEnvs;
+    static constexpr int kEnvs = 32 * E;
     static constexpr size_t kTables = 0;
-    static constexpr size_t kWeights = (sizeof(Tables) + 127) / 128 * 128;
-    static constexpr size_t kObs = kWeights + (PolicySmem<H>::kBytes + 15) / 16 * 16;      // float4 [kRollEnvs][2]
-    static constexpr size_t kAct = kObs + sizeof(float4) * 2 * kRollEnvs;                  // uint32 [kRollEnvs]
-    static constexpr size_t kStats = kAct + sizeof(uint32_t) * kRollEnvs;                  // u64 [FG_STAT_COUNT]
+    static constexpr size_t kPolicy = (sizeof(Tables) + 127) / 128 * 128;
+    static constexpr size_t kObs = kPolicy + (PolicySmemBcast<H, kEnvs>::kBytes + 15) / 16 * 16;   // float4 [kEnvs][2]
+    static constexpr size_t kStats = kObs + sizeof(float4) * 2 * kEnvs;                             // u64 [FG_STAT_COUNT]
     static constexpr size_t kBytes = kStats + sizeof(unsigned long long) * FG_STAT_COUNT;
 };
 
-template <int H, int E, bool ROLLED, bool DENSE>
+template <int H, int E, bool DENSE>
 __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutParams rp) {
     using SM = RolloutSmem<H, E>;
-    constexpr int kRollEnvs = RolloutShape<E>::kEnvs;
-    static_assert(kRollEnvs % 32 == 0 && kRollEnvs <= kRollThreads, "simulator threads are whole warps");
+    constexpr int kEnvs = SM::kEnvs;
+    static_assert(kEnvs <= kRollThreads, "one simulator thread per battle");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Tables &Tw = *reinterpret_cast<Tables *>(smem_raw + SM::kTables);
     const Tables &T = Tw;
-    float *pw = reinterpret_cast<float *>(smem_raw + SM::kWeights);
+    float *pw = reinterpret_cast<float *>(smem_raw + SM::kPolicy);
     float4 *obs_s = reinterpret_cast<float4 *>(smem_raw + SM::kObs);
-    uint32_t *act_s = reinterpret_cast<uint32_t *>(smem_raw + SM::kAct);
     unsigned long long *s_stats = reinterpret_cast<unsigned long long *>(smem_raw + SM::kStats);
     const Params &p = rp.sim;
-    const int tid = threadIdx.x, lane = tid & 31, part = tid & 3;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = p.n, horizon = rp.horizon;
-    const int base = blockIdx.x * kRollEnvs;
-    const bool sim_thread = tid < kRollEnvs;
-    const int i = base + tid;                                   // simulator mapping: one battle per thread
+    const int base = blockIdx.x * kEnvs;
+    const int stid = tid;                                       // simulator thread index = battle within the CTA
+    const bool sim_thread = stid < kEnvs;                       // whole warps: kEnvs is a multiple of 32
+    const int i = base + stid;                                  // simulator mapping: one battle per thread
     const bool valid = sim_thread && i < n;
 
     load_tables(&Tw, p.tables);
-    policy_stage<H>(pw, rp.w, tid, kRollThreads);
+    policy_stage_bcast<H, kEnvs>(pw, rp.w, tid, kRollThreads);
     if (tid < FG_STAT_COUNT) s_stats[tid] = 0ull;
     Env e;
     if (valid) load_env<true>(p, i, e);
@@ -73,7 +69,7 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
             a = rp.obs[src]; b = rp.obs[src + 1];
             rp.obs[(size_t)i * 2] = a; rp.obs[(size_t)i * 2 + 1] = b;
         }
-        obs_s[2 * tid] = a; obs_s[2 * tid + 1] = b;
+        obs_s[2 * stid] = a; obs_s[2 * stid + 1] = b;
     }
     __syncthreads();
     const unsigned long long drawn = rp.counter_base ? *rp.counter_base : 0ull;
@@ -82,40 +78,31 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
     const int K = p.frame_skip;
 
     for (int t = 0; t < horizon; t++) {
-        // ---- policy phase ----
+        // ---- policy phase (two CTA barriers inside) ----
         {
-            float x[E][8], lg[E][8];
+            float x[E][8];
 #pragma unroll
             for (int q = 0; q < E; q++) {
-                const int local = q * (kRollThreads / 4) + (tid >> 2);
-                const float4 a = obs_s[2 * local], b = obs_s[2 * local + 1];
+                const float4 a = obs_s[2 * (lane + 32 * q)], b = obs_s[2 * (lane + 32 * q) + 1];
                 x[q][0] = a.x; x[q][1] = a.y; x[q][2] = a.z; x[q][3] = a.w;
                 x[q][4] = b.x; x[q][5] = b.y; x[q][6] = b.z; x[q][7] = b.w;
             }
-            policy_logits<H, E, ROLLED>(pw, part, x, lg);
-#pragma unroll
-            for (int q = 0; q < E; q++) {
-                const int local = q * (kRollThreads / 4) + (tid >> 2), env = base + local;
-                float lp;
-                const int a = policy_sample(lg[q], hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)env), lp);
-                if (part == 0 && env < n) {
-                    act_s[local] = (uint32_t)a;
-                    rp.actions[(size_t)t * n + env] = (uint8_t)a;
-                    rp.logp[(size_t)t * n + env] = lp;
-                }
-            }
+            policy_partials_bcast<H, E>(pw, warp, lane, x);
         }
-        __syncthreads();
-        // ---- simulator phase: FootsiesEnv.step for the CTA's battles (same order of events as step_kernel) ----
+        // ---- sample + FootsiesEnv.step for the CTA's battles (same order of events as step_kernel) ----
         if (sim_thread) {
             if (valid) {
+                float lg[8], lp;
+                policy_logits_of<H, kEnvs>(pw, stid, lg);
+                const uint32_t in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)i), lp);
+                rp.actions[(size_t)t * n + i] = (uint8_t)in1;
+                rp.logp[(size_t)t * n + i] = lp;
                 double reward = 0.0;
                 bool terminal = false;
                 if ((e.misc >> FGM_DONE_SHIFT) & 1u) {                  // next-step autoreset: this step only resets
                     reset_env<false, true>(T, e, p.stale_intro != 0);
                     acc.s += 0x10000u;
                 } else {
-                    const uint32_t in1 = act_s[tid] & 7u;
                     uint32_t in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
                     for (int kk = 0; kk < K; kk++) {
                         if (!terminal) {
@@ -132,7 +119,7 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
                 rp.obs[dst] = a; rp.obs[dst + 1] = b;
                 rp.rewards[(size_t)t * n + i] = (float)reward;
                 rp.dones[(size_t)t * n + i] = terminal ? 1 : 0;
-                obs_s[2 * tid] = a; obs_s[2 * tid + 1] = b;
+                obs_s[2 * stid] = a; obs_s[2 * stid + 1] = b;
                 if (t == horizon - 1) { p.info_frame[i] = e.frame; p.info_misc[i] = o.info_misc; }
             }
             frames_since_flush += (uint32_t)K;                          // uniform across the warp
@@ -148,32 +135,33 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
     if (tid < FG_STAT_COUNT && s_stats[tid]) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
-template <int H, int E, bool ROLLED, bool DENSE>
+template <int H, int E, bool DENSE>
 static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
     constexpr size_t bytes = RolloutSmem<H, E>::kBytes;
     static bool configured[64] = {};                    // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, ROLLED, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    constexpr int kRollEnvs = RolloutShape<E>::kEnvs;
-    const int grid = (rp.sim.n + kRollEnvs - 1) / kRollEnvs;
-    rollout_kernel<H, E, ROLLED, DENSE><<<grid, kRollThreads, bytes, s>>>(rp);
+    constexpr int kEnvs = RolloutSmem<H, E>::kEnvs;
+    const int grid = (rp.sim.n + kEnvs - 1) / kEnvs;
+    rollout_kernel<H, E, DENSE><<<grid, kRollThreads, bytes, s>>>(rp);
     return cudaSuccess;
 }
 
 template <int H, bool DENSE>
 static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
-    // developer knobs (measured defaults below): battles per policy thread, rolled layer-2 loop
-    int e = 2, rolled = 0;
-    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);
-    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_ROLLED")) rolled = atoi(v);
-    if (H <= 64 && e == 4) return rolled ? launch_rollout_v<H, (H <= 64 ? 4 : 2), true, DENSE>(s, rp) : launch_rollout_v<H, (H <= 64 ? 4 : 2), false, DENSE>(s, rp);
-    if (e == 1) return rolled ? launch_rollout_v<H, 1, true, DENSE>(s, rp) : launch_rollout_v<H, 1, false, DENSE>(s, rp);
-    return rolled ? launch_rollout_v<H, 2, true, DENSE>(s, rp) : launch_rollout_v<H, 2, false, DENSE>(s, rp);
+    // battles per lane (measured, tools/rollout_sweep.py, H = 64): 16 384 battles E = 1 / 2 / 4: 10.6 / 6.9 / 8.6 us per
+    // step (too few CTAs for E = 4); 1 Mi battles: 446 / 314 / 290 us
+    int e = rp.sim.n >= 65536 ? 4 : 2;
+    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);   // developer knob
+    const RolloutParams &rp2 = rp;
+    if (e == 4 && H <= 64) return launch_rollout_v<H, (H <= 64 ? 4 : 2), DENSE>(s, rp2);
+    if (e == 1) return launch_rollout_v<H, 1, DENSE>(s, rp2);
+    return launch_rollout_v<H, 2, DENSE>(s, rp2);
 }
 
 cudaError_t launch_rollout(bool dense, cudaStream_t s, const RolloutParams &rp) {

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Whole-horizon rollout kernel (fg_rollout_mlp) variants: battles per policy thread x rolled layer-2 loop (developer
-tool; the variant is chosen per process by FOOTSIES_B200_ROLLOUT_E / FOOTSIES_B200_ROLLOUT_ROLLED).
+"""Whole-horizon rollout kernel (fg_rollout_mlp) variants: battles per lane (developer tool; the variant is chosen per
+process by FOOTSIES_B200_ROLLOUT_E).
 usage: python tools/rollout_sweep.py            # sweep
        python tools/rollout_sweep.py --one N H  # one configuration in this process (for ncu)"""
 import os
@@ -27,7 +27,7 @@ def one(n, hidden, reps=5):
     ms = e0.elapsed_time(e1) / reps
     fr = (env.episode_stats()["env_frames"] - f0) / reps
     print(f"n={n} hidden={hidden} E={os.environ.get('FOOTSIES_B200_ROLLOUT_E', 'default')} "
-          f"rolled={os.environ.get('FOOTSIES_B200_ROLLOUT_ROLLED', 'default')}: {ms * 1e3 / 128:.2f} us per step, "
+          f": {ms * 1e3 / 128:.2f} us per step, "
           f"{fr / (ms * 1e-3):.3e} env-frames/s", flush=True)
 
 
@@ -35,8 +35,7 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         one(int(sys.argv[2]), int(sys.argv[3]))
         sys.exit(0)
-    for n, hidden in ((16384, 64), (131072, 64), (16384, 32)):
-        for e in (1, 2, 4):
-            for rolled in (0, 1):
-                env = dict(os.environ, FOOTSIES_B200_ROLLOUT_E=str(e), FOOTSIES_B200_ROLLOUT_ROLLED=str(rolled))
-                subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(hidden)], env=env)
+    for n, hidden in ((16384, 64), (131072, 64), (1048576, 64), (16384, 32), (16384, 128)):
+        for e in (2, 4):
+            env = dict(os.environ, FOOTSIES_B200_ROLLOUT_E=str(e))
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(hidden)], env=env)
