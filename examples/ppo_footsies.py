@@ -6,7 +6,7 @@
 
 Rollouts come from footsies_gym_b200.rollout.RolloutCollector: the fused policy kernel samples actions from the
 observation tensor the step kernel wrote, the step kernel writes the next observation / reward / done flag straight
-into the rollout buffers, one CUDA-graph replay per horizon.  The update is ordinary torch (clipped PPO with GAE, a
+into the rollout buffers, one launch per horizon (fg_rollout_mlp keeps the battles in registers for all 128 steps).  The update is ordinary torch (clipped PPO with GAE, a
 separate value MLP); the policy's parameters are updated in place, so the next rollout reads the new weights.
 Prints the win rate against the bot per iteration (from the kernel's own episode statistics).
 """

@@ -4,11 +4,10 @@
 // BASELINE.json configs[4] (PPO rollout, a torch MLP policy consuming obs in place, 16 384 envs per GPU) is bound by
 // the dozen tiny torch kernels a policy step costs (~110 us per step, against ~6 us for the simulator step).  This
 // kernel replaces them for the 8-H-H-8 tanh MLP of footsies_gym_b200.rollout.MLPPolicy: weights are staged once per CTA
-// in shared memory (H = 64: 21 KB) and read as 128-bit broadcasts; four threads share one env (each owns a quarter of
-// the hidden units, partial sums are exchanged with warp shuffles) so that 16 384 envs still fill the machine; the
-// sampled action is written as the uint8 input bitmask the step kernel is bound to, next to its log-probability, and
-// (optionally) the observation row is copied into the rollout buffer on the way.  The arithmetic lives in policy_mlp.cuh
-// (shared with the whole-horizon rollout kernel, rollout_kernel.cu).
+// in shared memory; a CTA of 4 warps handles 64 battles at a time (warp = a quarter of the hidden units, lane = two
+// battles; policy_mlp.cuh); the sampled action is written as the uint8 input bitmask the step kernel is bound to, next
+// to its log-probability, and (optionally) the observation row is copied into the rollout buffer on the way.
+// The per-step path for configurations the whole-horizon kernel (rollout_kernel.cu) does not cover (self-play, masks).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -20,7 +19,9 @@ namespace {
 
 using namespace fgp;
 
-constexpr int kPolThreads = 128;       // 32 envs x 4 threads per CTA
+constexpr int kPolThreads = 32 * kPolicyWarps;
+constexpr int kPolE = 2;                       // battles per lane
+constexpr int kPolEnvs = 32 * kPolE;           // battles per CTA pass
 
 struct PolicyParams {
     const float *obs;          // [n, 8]
@@ -36,40 +37,36 @@ struct PolicyParams {
 template <int H>
 __global__ void __launch_bounds__(kPolThreads) policy_mlp_sample_kernel(const PolicyParams p) {
     extern __shared__ __align__(16) float sm[];
-    policy_stage<H>(sm, p.w, threadIdx.x, kPolThreads);
+    policy_stage_bcast<H, kPolEnvs, kPolicyWarps>(sm, p.w, threadIdx.x, kPolThreads);
     __syncthreads();
     const unsigned long long counter = p.counter + (p.counter_base ? *p.counter_base : 0ull);
-    const int part = threadIdx.x & 3;              // which quarter of the hidden units
-    constexpr int E = kEnvsPerThread;
-    constexpr int envs_per_block = (kPolThreads / 4) * E;
-    for (int base = blockIdx.x * envs_per_block; base < p.n; base += gridDim.x * envs_per_block) {
-        int env[E];
-        bool valid[E];
-        float x[E][8], lg[E][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int base = blockIdx.x * kPolEnvs; base < p.n; base += gridDim.x * kPolEnvs) {
+        float x[kPolE][8];
 #pragma unroll
-        for (int q = 0; q < E; q++) {
-            env[q] = base + q * (kPolThreads / 4) + (threadIdx.x >> 2);
-            valid[q] = env[q] < p.n;
-            const float4 a = valid[q] ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env[q]] : make_float4(0, 0, 0, 0);
-            const float4 b = valid[q] ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env[q] + 1] : make_float4(0, 0, 0, 0);
-            if (valid[q] && p.obs_copy && part == 0) {
-                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env[q]] = a;
-                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env[q] + 1] = b;
+        for (int q = 0; q < kPolE; q++) {
+            const int env = base + lane + 32 * q;
+            const bool valid = env < p.n;
+            const float4 a = valid ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env] : make_float4(0, 0, 0, 0);
+            const float4 b = valid ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env + 1] : make_float4(0, 0, 0, 0);
+            if (valid && p.obs_copy && warp == 0) {
+                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env] = a;
+                reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env + 1] = b;
             }
             x[q][0] = a.x; x[q][1] = a.y; x[q][2] = a.z; x[q][3] = a.w;
             x[q][4] = b.x; x[q][5] = b.y; x[q][6] = b.z; x[q][7] = b.w;
         }
-        policy_logits<H, E>(sm, part, x, lg);
-        // identical on the 4 lanes of an env; lane 0 of the group writes
-#pragma unroll
-        for (int q = 0; q < E; q++) {
-            float lp;
-            const int a = policy_sample(lg[q], hash3(p.seed, counter, (uint32_t)env[q]), lp);
-            if (valid[q] && part == 0) {
-                p.actions[env[q]] = (uint8_t)a;
-                if (p.logp) p.logp[env[q]] = lp;
-            }
+        policy_partials_bcast<H, kPolE, kPolicyWarps>(sm, warp, lane, x);     // two CTA barriers inside
+        const int env = base + tid;                             // one sampling thread per battle
+        if (tid < kPolEnvs && env < p.n) {
+            float lg[8], lp;
+            policy_logits_of<H, kPolEnvs, kPolicyWarps>(sm, tid, lg);
+            const int a = policy_sample(lg, hash3(p.seed, counter, (uint32_t)env), lp);
+            p.actions[env] = (uint8_t)a;
+            if (p.logp) p.logp[env] = lp;
         }
+        // no barrier needed here: the next pass writes the activations (nobody reads them any more) and only touches
+        // the partial sums after its first barrier, which the sampling threads reach after they are done reading
     }
 }
 
@@ -98,10 +95,10 @@ int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int envs_per_block = (kPolThreads / 4) * kEnvsPerThread;
-    int grid = (num_envs + envs_per_block - 1) / envs_per_block;
-    if (grid > sms * 4) grid = sms * 4;            // persistent: the weight staging is amortised over several env groups
-    const size_t bytes = hidden == 32 ? PolicySmem<32>::kBytes : hidden == 64 ? PolicySmem<64>::kBytes : PolicySmem<128>::kBytes;
+    int grid = (num_envs + kPolEnvs - 1) / kPolEnvs;
+    if (grid > sms * 4) grid = sms * 4;            // persistent: the weight staging is amortised over several passes
+    const size_t bytes = hidden == 32 ? PolicySmemBcast<32, kPolEnvs, kPolicyWarps>::kBytes : hidden == 64 ? PolicySmemBcast<64, kPolEnvs, kPolicyWarps>::kBytes
+                                      : PolicySmemBcast<128, kPolEnvs, kPolicyWarps>::kBytes;
     cudaError_t e = cudaSuccess;
     cudaStream_t s = (cudaStream_t)stream;
 #define FG_POLICY_LAUNCH(HH) do { \

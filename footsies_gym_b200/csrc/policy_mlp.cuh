@@ -4,11 +4,15 @@
 // per-step policy kernel (policy_kernel.cu) and the whole-horizon rollout kernel (rollout_kernel.cu):
 // scale -> Linear(8, H) -> tanh -> Linear(H, H) -> tanh -> Linear(H, 8) -> log-softmax -> categorical sample.
 //
-// Mapping: four threads share one env (each owns a quarter of the hidden units; partial sums travel by warp shuffles,
-// the 4 threads of an env are adjacent lanes) and every thread carries kEnvsPerThread envs, so that each weight word
-// fetched from shared memory is used for several envs (the inference is bound by those fetches).  Every multiply-add
-// is an explicit fmaf: the result does not depend on the translation unit's -fmad setting (the simulator half of the
-// rollout kernel must be compiled with -fmad=false), so both kernels produce bit-identical logits.
+// Mapping (CTA = W warps, W = 4 or 8): warp w owns hidden units w * H/W .. (w + 1) * H/W - 1 for all of the CTA's battles and every
+// lane carries E battles (lane, lane + 32, ...).  Weight fetches are warp-wide shared-memory broadcasts (one wavefront
+// serves 32 x E battles), activations cross between the warps through shared memory ([unit][battle], conflict-free),
+// and the layer-2 loop over the inputs stays a loop (small code).  History: the first version put the 4 threads of a
+// battle into one quarter-warp and exchanged activations by shuffles -- a 128-bit weight fetch then delivers only 4
+// distinct words per wavefront (measured: 98 wavefronts per env-step, shared-memory pipe 61 % busy) and its fully
+// unrolled layer 2 thrashed the instruction cache at 4 battles per thread.
+// Every multiply-add is an explicit fma (packed pairs, __ffma2_rn): the result does not depend on the translation
+// unit's -fmad setting, and both kernels produce bit-identical logits.
 // Randomness: a counter-based hash of (seed, step counter, env index) -- reproducible, no state to carry.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -16,7 +20,7 @@
 namespace fgp {
 
 constexpr int kMaxHidden = 128;
-constexpr int kEnvsPerThread = 2;
+constexpr int kPolicyWarps = 4;                    // W of both kernels (they must agree: the layer-3 partial sums are per warp)
 
 struct PolicyWeights {
     const float *scale;        // [8]
@@ -43,138 +47,6 @@ __device__ __forceinline__ uint32_t hash3(uint64_t seed, uint64_t counter, uint3
     return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 
-// Shared-memory layout of one layer's weights for the "4 threads per env" mapping: thread `part` owns the output units
-// part * Q .. part * Q + Q - 1 and needs, for every input k, its Q weights as contiguous 128-bit words:
-//   ws[(k * 4 + part) * P + j] = W[part * Q + j][k]       (P = Q + 4: the 4 parts of a quarter-warp hit disjoint banks,
-// e.g. Q = 16: 16-float segments at a 20-float pitch start at banks 0, 20, 8, 28)
-template <int H>
-struct PolicySmem {
-    static_assert(H % 16 == 0 && H <= kMaxHidden, "hidden size");
-    static constexpr int Q = H / 4, P = Q + 4;
-    static constexpr int kW1 = 0, kW2 = kW1 + 8 * 4 * P, kW3 = kW2 + H * 4 * P, kB1 = kW3 + 8 * 4 * P, kB2 = kB1 + H,
-                         kB3 = kB2 + H, kScale = kB3 + 8, kFloats = kScale + 8;
-    static constexpr size_t kBytes = sizeof(float) * kFloats;
-};
-
-// Stage the weights into shared memory (all threads of the CTA; the caller synchronises afterwards).
-template <int H>
-__device__ __forceinline__ void policy_stage(float *sm, const PolicyWeights &p, int tid, int nthreads) {
-    using L = PolicySmem<H>;
-    constexpr int Q = L::Q, P = L::P;
-    float *w1 = sm + L::kW1, *w2 = sm + L::kW2, *w3 = sm + L::kW3;
-    for (int i = tid; i < H * 8; i += nthreads) {
-        const int u = i / 8, k = i % 8;            // W1[u][k]
-        w1[(k * 4 + u / Q) * P + u % Q] = p.w1[i];
-        const int o = i / H, c = i % H;            // W3[o][c]
-        w3[(o * 4 + c / Q) * P + c % Q] = p.w3[i];
-    }
-    for (int i = tid; i < H * H / 4; i += nthreads) {
-        const float4 v = reinterpret_cast<const float4 *>(p.w2)[i];   // W2[u][k .. k + 3]
-        const int u = (4 * i) / H, k = (4 * i) % H;
-        float *dst = w2 + (u / Q) * P + u % Q;
-        dst[(k + 0) * 4 * P] = v.x; dst[(k + 1) * 4 * P] = v.y; dst[(k + 2) * 4 * P] = v.z; dst[(k + 3) * 4 * P] = v.w;
-    }
-    for (int i = tid; i < H; i += nthreads) { sm[L::kB1 + i] = p.b1[i]; sm[L::kB2 + i] = p.b2[i]; }
-    if (tid < 8) { sm[L::kB3 + tid] = p.b3[tid]; sm[L::kScale + tid] = p.scale[tid]; }
-}
-
-// Logits of this thread's E envs from their raw observation rows x[q][0..7] (scaled here).  Must be called by all 32
-// lanes of a warp; `part` = lane & 3; the 4 lanes of a group hold the same x and end up with the same logits.
-// ROLLED: the loop over the four source quarters of layer 2 stays a loop (the shuffle source lane and the weight
-// address are runtime values), which cuts the unrolled code of that layer four-fold; same arithmetic order either way.
-template <int H, int E, bool ROLLED = false>
-__device__ __forceinline__ void policy_logits(const float *sm, int part, float (&x)[E][8], float (&lg)[E][8]) {
-    using L = PolicySmem<H>;
-    constexpr int Q = L::Q, P = L::P;
-    const float *w1 = sm + L::kW1, *w2 = sm + L::kW2, *w3 = sm + L::kW3;
-    const float *b1 = sm + L::kB1, *b2 = sm + L::kB2, *b3 = sm + L::kB3, *sc = sm + L::kScale;
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int q = 0; q < E; q++) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) x[q][k] = x[q][k] * sc[k];
-    }
-    // layer 1: this thread's quarter of h1 = tanh(b1 + W1 x)
-    float h1[E][Q];
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-#pragma unroll
-        for (int q = 0; q < E; q++) h1[q][j] = b1[part * Q + j];
-    }
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float4 *w = reinterpret_cast<const float4 *>(w1 + (k * 4 + part) * P);
-#pragma unroll
-        for (int j4 = 0; j4 < Q / 4; j4++) {
-            const float4 v = w[j4];
-#pragma unroll
-            for (int q = 0; q < E; q++) {
-                h1[q][4 * j4] = fmaf(v.x, x[q][k], h1[q][4 * j4]); h1[q][4 * j4 + 1] = fmaf(v.y, x[q][k], h1[q][4 * j4 + 1]);
-                h1[q][4 * j4 + 2] = fmaf(v.z, x[q][k], h1[q][4 * j4 + 2]); h1[q][4 * j4 + 3] = fmaf(v.w, x[q][k], h1[q][4 * j4 + 3]);
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-#pragma unroll
-        for (int q = 0; q < E; q++) h1[q][j] = fast_tanh(h1[q][j]);
-    }
-    // layer 2: each thread owns Q outputs and needs all H inputs: the other quarters of h1 come over warp shuffles
-    float h2[E][Q];
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-#pragma unroll
-        for (int q = 0; q < E; q++) h2[q][j] = b2[part * Q + j];
-    }
-#pragma unroll(ROLLED ? 1 : 4)
-    for (int src = 0; src < 4; src++) {
-#pragma unroll
-        for (int k = 0; k < Q; k++) {
-            float hk[E];
-#pragma unroll
-            for (int q = 0; q < E; q++) hk[q] = __shfl_sync(0xffffffffu, h1[q][k], (lane & 28) | src, 32);   // h1[src * Q + k]
-            const float4 *w = reinterpret_cast<const float4 *>(w2 + ((src * Q + k) * 4 + part) * P);
-#pragma unroll
-            for (int j4 = 0; j4 < Q / 4; j4++) {
-                const float4 v = w[j4];
-#pragma unroll
-                for (int q = 0; q < E; q++) {
-                    h2[q][4 * j4] = fmaf(v.x, hk[q], h2[q][4 * j4]); h2[q][4 * j4 + 1] = fmaf(v.y, hk[q], h2[q][4 * j4 + 1]);
-                    h2[q][4 * j4 + 2] = fmaf(v.z, hk[q], h2[q][4 * j4 + 2]); h2[q][4 * j4 + 3] = fmaf(v.w, hk[q], h2[q][4 * j4 + 3]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < Q; j++) {
-#pragma unroll
-        for (int q = 0; q < E; q++) h2[q][j] = fast_tanh(h2[q][j]);
-    }
-    // layer 3: partial logits over this thread's quarter of h2, then a butterfly over the 4 lanes
-#pragma unroll
-    for (int o = 0; o < 8; o++) {
-        const float4 *w = reinterpret_cast<const float4 *>(w3 + (o * 4 + part) * P);
-        float s[E];
-#pragma unroll
-        for (int q = 0; q < E; q++) s[q] = 0.0f;
-#pragma unroll
-        for (int j4 = 0; j4 < Q / 4; j4++) {
-            const float4 v = w[j4];
-#pragma unroll
-            for (int q = 0; q < E; q++) {
-                s[q] = fmaf(v.x, h2[q][4 * j4], s[q]); s[q] = fmaf(v.y, h2[q][4 * j4 + 1], s[q]);
-                s[q] = fmaf(v.z, h2[q][4 * j4 + 2], s[q]); s[q] = fmaf(v.w, h2[q][4 * j4 + 3], s[q]);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < E; q++) {
-            s[q] += __shfl_xor_sync(0xffffffffu, s[q], 1, 32);
-            s[q] += __shfl_xor_sync(0xffffffffu, s[q], 2, 32);
-            lg[q][o] = s[q] + b3[o];
-        }
-    }
-}
-
 // log-softmax + inverse-CDF sample from 8 logits with the 32-bit random word `rnd`; returns the action index 0..7 (= the
 // input bitmask Left 1 | Right 2 | Attack 4, wrappers/action_comb_disc.py:13-18) and its log-probability.
 __device__ __forceinline__ int policy_sample(const float (&lg)[8], uint32_t rnd, float &logp) {
@@ -194,28 +66,21 @@ __device__ __forceinline__ int policy_sample(const float (&lg)[8], uint32_t rnd,
     return a;
 }
 
-// ---- second mapping of the same arithmetic: one warp per quarter of the hidden units, lanes = battles ----------------
-// Used by the whole-horizon rollout kernel.  In the mapping above the 4 threads of an env sit in one quarter-warp, so a
-// 128-bit weight fetch delivers only 4 distinct words per shared-memory wavefront (measured: 98 wavefronts per env-step,
-// shared-memory pipe 61 % busy at 16 384 envs).  Here warp w of a 4-warp CTA owns hidden units w * Q .. w * Q + Q - 1 for
-// all of the CTA's battles and every lane carries E battles (lane, lane + 32, ...): weight fetches are warp-wide
-// broadcasts (one wavefront serves 32 x E battles), activations cross between the warps through shared memory
-// ([unit][battle], conflict-free), and the layer-2 loop over the inputs stays a loop (small code: the fully unrolled
-// version thrashed the instruction cache).  Every output unit accumulates in the same order as above -- bias first,
-// inputs ascending, layer-3 quarters combined as (s0 + s1) + (s2 + s3) -- so the logits are bit-identical.
-template <int H, int NE>
+// Shared memory of one CTA: transposed weights, biases, observation scale, the hidden activations of NE battles and
+// the four partial logit sums per battle.
+template <int H, int NE, int W>
 struct PolicySmemBcast {
-    static_assert(H % 16 == 0 && H <= kMaxHidden, "hidden size");
-    static constexpr int Q = H / 4;
+    static_assert(H % 16 == 0 && H <= kMaxHidden && (W == 4 || W == 8) && (H / W) % 4 == 0, "hidden size / warps");
+    static constexpr int Q = H / W;                 // hidden units per warp
     static constexpr int kW1T = 0, kW2T = kW1T + 8 * H, kW3T = kW2T + H * H, kB1 = kW3T + 8 * H, kB2 = kB1 + H, kB3 = kB2 + H,
-                         kScale = kB3 + 8, kHid = kScale + 8, kPart = kHid + H * NE, kFloats = kPart + 4 * 8 * NE;
+                         kScale = kB3 + 8, kHid = kScale + 8, kPart = kHid + H * NE, kFloats = kPart + W * 8 * NE;
     static constexpr size_t kBytes = sizeof(float) * kFloats;
 };
 
 // w1t[k][u] = W1[u][k], w2t[k][u] = W2[u][k], w3t[c][o] = W3[o][c] (input-major: the outputs of one input are contiguous).
-template <int H, int NE>
+template <int H, int NE, int W>
 __device__ __forceinline__ void policy_stage_bcast(float *sm, const PolicyWeights &p, int tid, int nthreads) {
-    using L = PolicySmemBcast<H, NE>;
+    using L = PolicySmemBcast<H, NE, W>;
     for (int i = tid; i < H * 8; i += nthreads) {
         const int u = i / 8, k = i % 8;            // W1[u][k]
         sm[L::kW1T + k * H + u] = p.w1[i];
@@ -231,15 +96,15 @@ __device__ __forceinline__ void policy_stage_bcast(float *sm, const PolicyWeight
     if (tid < 8) { sm[L::kB3 + tid] = p.b3[tid]; sm[L::kScale + tid] = p.scale[tid]; }
 }
 
-// All 128 threads of the CTA.  x[e] = raw observation row of battle lane + 32 e.  On return (after the function's last
+// All 32 W threads of the CTA.  x[e] = raw observation row of battle lane + 32 e.  On return (after the function's last
 // __syncthreads) the partial logits of every battle are in shared memory: policy_logits_of() assembles them.
 // The multiply-adds are issued as packed pairs (__ffma2_rn, Blackwell's FFMA2: two independent correctly rounded fp32
 // fmas per instruction, i.e. bit-identical to two fmaf) over adjacent output units: the policy phase is bound by the
 // FMA pipe (one warp instruction per 2 cycles per scheduler), so pairs halve its time.
-template <int H, int E>
+template <int H, int E, int W>
 __device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int lane, float (&x)[E][8]) {
     constexpr int NE = 32 * E;
-    using L = PolicySmemBcast<H, NE>;
+    using L = PolicySmemBcast<H, NE, W>;
     constexpr int Q = L::Q;
     const float *w1t = sm + L::kW1T + warp * Q, *w2t = sm + L::kW2T + warp * Q, *w3t = sm + L::kW3T + warp * Q * 8;
     const float *b1 = sm + L::kB1 + warp * Q, *b2 = sm + L::kB2 + warp * Q, *sc = sm + L::kScale;
@@ -334,16 +199,23 @@ __device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int l
     __syncthreads();
 }
 
-// The 8 logits of battle `local` (0 .. NE - 1) from the partial sums left by policy_partials_bcast.
-template <int H, int NE>
+// The 8 logits of battle `local` (0 .. NE - 1) from the partial sums left by policy_partials_bcast: a fixed pairwise tree
+// over the warps' partial sums, then the bias.
+template <int H, int NE, int W>
 __device__ __forceinline__ void policy_logits_of(const float *sm, int local, float (&lg)[8]) {
-    using L = PolicySmemBcast<H, NE>;
+    using L = PolicySmemBcast<H, NE, W>;
     const float *part = sm + L::kPart, *b3 = sm + L::kB3;
 #pragma unroll
     for (int o = 0; o < 8; o++) {
-        const float s0 = part[(0 * 8 + o) * NE + local], s1 = part[(1 * 8 + o) * NE + local];
-        const float s2 = part[(2 * 8 + o) * NE + local], s3 = part[(3 * 8 + o) * NE + local];
-        lg[o] = ((s0 + s1) + (s2 + s3)) + b3[o];
+        float s[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) s[w] = part[(w * 8 + o) * NE + local];
+#pragma unroll
+        for (int span = 1; span < W; span *= 2) {
+#pragma unroll
+            for (int w = 0; w < W; w += 2 * span) s[w] = s[w] + s[w + span];
+        }
+        lg[o] = s[0] + b3[o];
     }
 }
 

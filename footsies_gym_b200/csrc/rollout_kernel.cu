@@ -2,8 +2,8 @@
 // `horizon` times, for every battle of the device, with the battle state held in registers for the whole horizon.
 //
 // Battles never interact and the policy only couples them through its (read-only) weights, so a horizon needs no
-// grid-wide synchronisation: a CTA of 128 threads owns 32 x E battles from the first step to the last.  Per step and CTA:
-//   policy phase   all 4 warps: warp w computes hidden units w * H/4 .. of every battle of the CTA, lanes = battles
+// grid-wide synchronisation: a CTA of W warps (W = 4) owns 32 x E battles from the first step to the last.  Per step and CTA:
+//   policy phase   all W warps: warp w computes hidden units w * H/W .. of every battle of the CTA, lanes = battles
 //                  (policy_mlp.cuh, second mapping: weight fetches are warp-wide shared-memory broadcasts, activations
 //                  cross between warps through shared memory), ending with the partial logits in shared memory;
 //   simulator phase  one thread per battle: assemble the 8 logits, log-softmax, sample the input bitmask, then the
@@ -24,22 +24,21 @@ namespace fgk {
 
 using namespace fgp;
 
-constexpr int kRollThreads = 128;
 
-template <int H, int E>
+template <int H, int E, int W>
 struct RolloutSmem {
     static constexpr int kEnvs = 32 * E;
     static constexpr size_t kTables = 0;
     static constexpr size_t kPolicy = (sizeof(Tables) + 127) / 128 * 128;
-    static constexpr size_t kObs = kPolicy + (PolicySmemBcast<H, kEnvs>::kBytes + 15) / 16 * 16;   // float4 [kEnvs][2]
+    static constexpr size_t kObs = kPolicy + (PolicySmemBcast<H, kEnvs, W>::kBytes + 15) / 16 * 16;   // float4 [kEnvs][2]
     static constexpr size_t kStats = kObs + sizeof(float4) * 2 * kEnvs;                             // u64 [FG_STAT_COUNT]
     static constexpr size_t kBytes = kStats + sizeof(unsigned long long) * FG_STAT_COUNT;
 };
 
-template <int H, int E, bool DENSE>
-__global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutParams rp) {
-    using SM = RolloutSmem<H, E>;
-    constexpr int kEnvs = SM::kEnvs;
+template <int H, int E, int W, bool DENSE>
+__global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp) {
+    using SM = RolloutSmem<H, E, W>;
+    constexpr int kEnvs = SM::kEnvs, kRollThreads = 32 * W;
     static_assert(kEnvs <= kRollThreads, "one simulator thread per battle");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Tables &Tw = *reinterpret_cast<Tables *>(smem_raw + SM::kTables);
@@ -57,7 +56,7 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
     const bool valid = sim_thread && i < n;
 
     load_tables(&Tw, p.tables);
-    policy_stage_bcast<H, kEnvs>(pw, rp.w, tid, kRollThreads);
+    policy_stage_bcast<H, kEnvs, W>(pw, rp.w, tid, kRollThreads);
     if (tid < FG_STAT_COUNT) s_stats[tid] = 0ull;
     Env e;
     if (valid) load_env<true>(p, i, e);
@@ -87,13 +86,13 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
                 x[q][0] = a.x; x[q][1] = a.y; x[q][2] = a.z; x[q][3] = a.w;
                 x[q][4] = b.x; x[q][5] = b.y; x[q][6] = b.z; x[q][7] = b.w;
             }
-            policy_partials_bcast<H, E>(pw, warp, lane, x);
+            policy_partials_bcast<H, E, W>(pw, warp, lane, x);
         }
         // ---- sample + FootsiesEnv.step for the CTA's battles (same order of events as step_kernel) ----
         if (sim_thread) {
             if (valid) {
                 float lg[8], lp;
-                policy_logits_of<H, kEnvs>(pw, stid, lg);
+                policy_logits_of<H, kEnvs, W>(pw, stid, lg);
                 const uint32_t in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)i), lp);
                 rp.actions[(size_t)t * n + i] = (uint8_t)in1;
                 rp.logp[(size_t)t * n + i] = lp;
@@ -135,20 +134,20 @@ __global__ void __launch_bounds__(kRollThreads) rollout_kernel(const RolloutPara
     if (tid < FG_STAT_COUNT && s_stats[tid]) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
-template <int H, int E, bool DENSE>
+template <int H, int E, int W, bool DENSE>
 static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
-    constexpr size_t bytes = RolloutSmem<H, E>::kBytes;
+    constexpr size_t bytes = RolloutSmem<H, E, W>::kBytes;
     static bool configured[64] = {};                    // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    constexpr int kEnvs = RolloutSmem<H, E>::kEnvs;
+    constexpr int kEnvs = RolloutSmem<H, E, W>::kEnvs;
     const int grid = (rp.sim.n + kEnvs - 1) / kEnvs;
-    rollout_kernel<H, E, DENSE><<<grid, kRollThreads, bytes, s>>>(rp);
+    rollout_kernel<H, E, W, DENSE><<<grid, 32 * W, bytes, s>>>(rp);
     return cudaSuccess;
 }
 
@@ -156,12 +155,12 @@ template <int H, bool DENSE>
 static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
     // battles per lane (measured, tools/rollout_sweep.py, H = 64): 16 384 battles E = 1 / 2 / 4: 10.6 / 6.9 / 8.6 us per
     // step (too few CTAs for E = 4); 1 Mi battles: 446 / 314 / 290 us
-    int e = rp.sim.n >= 65536 ? 4 : 2;
-    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);   // developer knob
-    const RolloutParams &rp2 = rp;
-    if (e == 4 && H <= 64) return launch_rollout_v<H, (H <= 64 ? 4 : 2), DENSE>(s, rp2);
-    if (e == 1) return launch_rollout_v<H, 1, DENSE>(s, rp2);
-    return launch_rollout_v<H, 2, DENSE>(s, rp2);
+    int e = rp.sim.n >= 65536 ? 4 : 2, w = kPolicyWarps;
+    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);   // developer knobs
+    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_W")) w = atoi(v);   // (W != kPolicyWarps: timing only, logits differ in the last bit from the per-step kernel)
+    constexpr int E4 = H <= 64 ? 4 : 2;
+    if (w == 8) return e == 4 ? launch_rollout_v<H, E4, 8, DENSE>(s, rp) : launch_rollout_v<H, 2, 8, DENSE>(s, rp);
+    return e == 4 ? launch_rollout_v<H, E4, 4, DENSE>(s, rp) : launch_rollout_v<H, 2, 4, DENSE>(s, rp);
 }
 
 cudaError_t launch_rollout(bool dense, cudaStream_t s, const RolloutParams &rp) {
