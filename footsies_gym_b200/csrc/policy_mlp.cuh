@@ -20,7 +20,8 @@
 namespace fgp {
 
 constexpr int kMaxHidden = 128;
-constexpr int kPolicyWarps = 4;                    // W of both kernels (they must agree: the layer-3 partial sums are per warp)
+constexpr int kPolicyWarps = 4;                    // W of both kernels (they must agree: the layer-3 partial sums are per warp);
+                                                   // measured W = 8: 16 384 envs 6.7 vs 6.5 us per step, 1 Mi envs 352 vs 264
 
 struct PolicyWeights {
     const float *scale;        // [8]
@@ -149,7 +150,7 @@ __device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int l
 #pragma unroll
         for (int e = 0; e < E; e++) acc[e][j2] = make_float2(b2[2 * j2], b2[2 * j2 + 1]);
     }
-#pragma unroll 4
+#pragma unroll 4                                    // measured: 2 / 4 / 8 / 16 within 2 % of each other
     for (int k = 0; k < H; k++) {
         float2 hk[E];
 #pragma unroll

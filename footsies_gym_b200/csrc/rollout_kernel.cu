@@ -2,9 +2,9 @@
 // `horizon` times, for every battle of the device, with the battle state held in registers for the whole horizon.
 //
 // Battles never interact and the policy only couples them through its (read-only) weights, so a horizon needs no
-// grid-wide synchronisation: a CTA of W warps (W = 4) owns 32 x E battles from the first step to the last.  Per step and CTA:
+// grid-wide synchronisation: a CTA of W = 4 warps owns 32 x E battles from the first step to the last.  Per step and CTA:
 //   policy phase   all W warps: warp w computes hidden units w * H/W .. of every battle of the CTA, lanes = battles
-//                  (policy_mlp.cuh, second mapping: weight fetches are warp-wide shared-memory broadcasts, activations
+//                  (policy_mlp.cuh: weight fetches are warp-wide shared-memory broadcasts, activations
 //                  cross between warps through shared memory), ending with the partial logits in shared memory;
 //   simulator phase  one thread per battle: assemble the 8 logits, log-softmax, sample the input bitmask, then the
 //                  reference frame update (frame_logic.cuh; autoreset, bot query, reward and termination exactly as
@@ -23,7 +23,6 @@
 namespace fgk {
 
 using namespace fgp;
-
 
 template <int H, int E, int W>
 struct RolloutSmem {
@@ -153,14 +152,12 @@ static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
 
 template <int H, bool DENSE>
 static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
-    // battles per lane (measured, tools/rollout_sweep.py, H = 64): 16 384 battles E = 1 / 2 / 4: 10.6 / 6.9 / 8.6 us per
-    // step (too few CTAs for E = 4); 1 Mi battles: 446 / 314 / 290 us
-    int e = rp.sim.n >= 65536 ? 4 : 2, w = kPolicyWarps;
-    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);   // developer knobs
-    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_W")) w = atoi(v);   // (W != kPolicyWarps: timing only, logits differ in the last bit from the per-step kernel)
-    constexpr int E4 = H <= 64 ? 4 : 2;
-    if (w == 8) return e == 4 ? launch_rollout_v<H, E4, 8, DENSE>(s, rp) : launch_rollout_v<H, 2, 8, DENSE>(s, rp);
-    return e == 4 ? launch_rollout_v<H, E4, 4, DENSE>(s, rp) : launch_rollout_v<H, 2, 4, DENSE>(s, rp);
+    // battles per lane (measured, tools/rollout_sweep.py, H = 64, us per step): 16 384 battles E = 2 / 4: 6.5 / 7.2 (too few
+    // CTAs for E = 4); 131 072: 37.5 / 34.6; 1 Mi: 288 / 264
+    int e = rp.sim.n >= 65536 ? 4 : 2;
+    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);   // developer knob
+    constexpr int E4 = H <= 64 ? 4 : 2;                                  // H = 128: 4 battles per lane do not fit the registers
+    return e == 4 ? launch_rollout_v<H, E4, kPolicyWarps, DENSE>(s, rp) : launch_rollout_v<H, 2, kPolicyWarps, DENSE>(s, rp);
 }
 
 cudaError_t launch_rollout(bool dense, cudaStream_t s, const RolloutParams &rp) {

@@ -413,14 +413,29 @@ class FootsiesEnv:
             self._host = hb
         return self._host
 
-    def _check_host_path(self):
-        if self.frame_delay > 0:
-            raise NotImplementedError("the host-buffer path delivers undelayed observations: use step() with frame_delay")
+    def _deliver_delayed_to_host(self):
+        """frame_delay > 0: the delayed observation / info lives in device tensors maintained by step() (the delay ring,
+        footsies.py:129-131, 533-535); pack it into the compact host layout on the device and copy it down.  Not the
+        fast path (a handful of torch ops per step)."""
+        hb = self._host_buffers()
+        obs, info = self._finish_obs()
+        u8 = torch.cat([obs["guard"], obs["move"], obs["move_frame"]], dim=1).to(torch.uint8)
+        hb["obs_u8"].copy_(u8, non_blocking=True)
+        hb["position"].copy_(obs["position"], non_blocking=True)
+        hb["info_frame"].copy_(info["frame"], non_blocking=True)
+        hb["info_misc"].copy_(torch.stack([info[k] for k in ("p1_action", "p2_action", "p1_hitstun", "p2_hitstun")], dim=1),
+                              non_blocking=True)
+        hb["reward"].copy_(self.reward, non_blocking=True)
+        hb["terminated"].copy_(self.terminated.to(torch.bool), non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def reset_host(self, *, seed: Optional[int] = None, mask=None):
         """reset() delivering (obs, info) to pinned host tensors (mask: host bool / uint8 [N] or None = all)."""
-        self._check_host_path()
         hb = self._host_buffers()
+        if self.frame_delay > 0:
+            self.reset(seed=seed, options=None if mask is None else {"mask": torch.as_tensor(mask)})
+            self._deliver_delayed_to_host()
+            return hb["obs"], hb["info"]
         m = None
         if mask is not None:
             m = torch.as_tensor(mask).to(device="cpu", dtype=torch.uint8).contiguous()
@@ -441,8 +456,11 @@ class FootsiesEnv:
         returns Python ints and floats, footsies.py:362-367).  Returns host tensors that are reused between calls."""
         if not self.has_reset:
             raise RuntimeError("call reset() before step()")
-        self._check_host_path()
         hb = self._host_buffers()
+        if self.frame_delay > 0:
+            self.step(action, opponent_action)
+            self._deliver_delayed_to_host()
+            return hb["obs"], hb["reward"], hb["terminated"], hb["truncated"], hb["info"]
         p1 = p2 = None
         if not self.by_example:
             a = _as_bitmask(action, self.num_envs, "cpu")

@@ -102,3 +102,29 @@ def test_frame_delay_queue_for_a_batch_with_automatic_restarts(oracle, delay):
         episodes += int(term.sum())
     assert episodes > n
     env.close()
+
+
+def test_frame_delay_on_the_host_buffer_path(oracle):
+    """step_host / reset_host with frame_delay: the delayed observation and info reach the pinned host tensors (compact
+    layout), reward and termination undelayed."""
+    from footsies_gym_b200 import FootsiesEnv
+    dev = _cuda()
+    n, steps, delay = 300, 400, 3
+    rng = np.random.default_rng(77)
+    env = FootsiesEnv(num_envs=n, device=dev, frame_delay=delay, seed=4)
+    orc = oracle.OracleBatch(n, p2_bot=True, frame_delay=delay, seed=4)
+    keys = ("guard", "move", "move_frame", "position")
+    obs, info = env.reset_host()
+    orc.reset()
+    assert not obs["position"].is_cuda and obs["guard"].dtype == torch.uint8
+    assert np.array_equal(np.concatenate([obs[k].numpy() for k in keys], 1), orc.trace["obs"])
+    for t in range(steps):
+        a = rng.integers(0, 8, size=n, dtype=np.uint8)
+        obs, reward, term, trunc, info = env.step_host(a)
+        orc.step(a)
+        assert np.array_equal(np.concatenate([obs[k].numpy() for k in keys], 1), orc.trace["obs"]), t
+        assert np.array_equal(info["frame"].numpy(), orc.trace["info_frame"]), t
+        assert np.array_equal(np.stack([info[k].numpy() for k in ("p1_action", "p2_action")], 1), orc.trace["info_action"]), t
+        assert np.array_equal(reward.numpy(), orc.trace["reward"]), t
+        assert np.array_equal(term.numpy().astype(np.int32), orc.trace["terminated"]), t
+    env.close()

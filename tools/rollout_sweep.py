@@ -27,7 +27,6 @@ def one(n, hidden, reps=5):
     ms = e0.elapsed_time(e1) / reps
     fr = (env.episode_stats()["env_frames"] - f0) / reps
     print(f"n={n} hidden={hidden} E={os.environ.get('FOOTSIES_B200_ROLLOUT_E', 'default')} "
-          f"W={os.environ.get('FOOTSIES_B200_ROLLOUT_W', 'default')} "
           f": {ms * 1e3 / 128:.2f} us per step, "
           f"{fr / (ms * 1e-3):.3e} env-frames/s", flush=True)
 
@@ -38,6 +37,5 @@ if __name__ == "__main__":
         sys.exit(0)
     for n, hidden in ((16384, 64), (131072, 64), (1048576, 64), (16384, 32), (16384, 128)):
         for e in (2, 4):
-            for w in (4, 8):
-                env = dict(os.environ, FOOTSIES_B200_ROLLOUT_E=str(e), FOOTSIES_B200_ROLLOUT_W=str(w))
-                subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(hidden)], env=env)
+            env = dict(os.environ, FOOTSIES_B200_ROLLOUT_E=str(e))
+            subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(n), str(hidden)], env=env)
