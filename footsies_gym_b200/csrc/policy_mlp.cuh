@@ -100,8 +100,10 @@ __device__ __forceinline__ void policy_stage_bcast(float *sm, const PolicyWeight
 // All 32 W threads of the CTA.  x[e] = raw observation row of battle lane + 32 e.  On return (after the function's last
 // __syncthreads) the partial logits of every battle are in shared memory: policy_logits_of() assembles them.
 // The multiply-adds are issued as packed pairs (__ffma2_rn, Blackwell's FFMA2: two independent correctly rounded fp32
-// fmas per instruction, i.e. bit-identical to two fmaf) over adjacent output units: the policy phase is bound by the
-// FMA pipe (one warp instruction per 2 cycles per scheduler), so pairs halve its time.
+// fmas per instruction, i.e. bit-identical to two fmaf) over adjacent output units.  Measured (tools/probes/
+// ffma2_probe.cu): FFMA2 does not raise the FMA pipe's rate -- 2.0 cycles per warp instruction per scheduler against 1.1
+// for FFMA, ~127 lane-fmas per cycle per SM either way -- it halves the ISSUE slots the fmas take, which is what this loop
+// is short of (weight and activation fetches share them): 7.6 -> 6.9 us per rollout step.
 template <int H, int E, int W>
 __device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int lane, float (&x)[E][8]) {
     constexpr int NE = 32 * E;
