@@ -105,8 +105,8 @@ def test_horizon_kernel_rejects_other_configurations():
     assert RolloutCollector(FootsiesEnv(num_envs=64, device=dev), policy, horizon=8).mode == "horizon"
 
 
-@pytest.mark.parametrize("hidden", [32, 64, 128])
-def test_fused_policy_kernel_matches_torch(hidden):
+@pytest.mark.parametrize("hidden,n", [(32, 10007), (64, 10007), (128, 10007), (64, 50001)])
+def test_fused_policy_kernel_matches_torch(hidden, n):
     """fg_policy_mlp_sample against the torch module it replaces: the log-probability it reports for the action it drew
     equals torch's log_softmax there (tolerance 2e-5 absolute: __expf-based tanh / exp, FMA contraction), and the
     actions it draws follow the policy's distribution."""
@@ -119,7 +119,8 @@ def test_fused_policy_kernel_matches_torch(hidden):
     with torch.no_grad():
         for prm in pol.net.parameters():
             prm.mul_(3.0)                                   # a peaky, non-uniform policy
-    n = 10007                                               # ragged: not a multiple of the 32 envs a CTA handles
+    # n is ragged (not a multiple of the 64 battles a CTA handles per pass); 50 001 battles make every CTA of the
+    # persistent grid run several passes over its shared-memory buffers
     g = torch.Generator(device=dev)
     g.manual_seed(1)
     obs = torch.stack([torch.randint(0, 4, (n,), generator=g, device=dev).float(), torch.randint(0, 4, (n,), generator=g, device=dev).float(),
