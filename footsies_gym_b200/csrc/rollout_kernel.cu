@@ -12,8 +12,9 @@
 //                  rollout buffers and observation t + 1 stays in shared memory for the next policy phase.
 // Against the two launches per step of the per-step path (policy kernel + step kernel in a CUDA graph) this removes
 // 2 x horizon launches, every state load / store but one, and the observation round trip through L2.  Several CTAs are
-// resident per SM.  (Tried: starting every second co-resident CTA half a step late so that simulator and policy phases
-// interleave -- no measurable effect, removed.)
+// resident per SM.  (Tried twice -- by blockIdx and by per-SM arrival order (%smid + atomic) -- starting every second
+// co-resident CTA half a step late so that simulator and policy phases interleave: no measurable effect for any delay;
+// one CTA per SM runs a step in 4.7 us, two in 6.5 us, so co-residency already overlaps most of the work.  Removed.)
 // Results are bit-identical to the per-step path (tests/test_rollout.py).
 // Compiled with -fmad=false like the step kernel; the policy arithmetic uses explicit fmaf.
 #include <stdlib.h>
