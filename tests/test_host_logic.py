@@ -34,6 +34,31 @@ def test_struct_layouts_match_header_sizes():
     assert _capi.env_state_dtype().itemsize == C.sizeof(_capi.FgEnvState)
 
 
+def test_ctypes_structs_match_the_header_as_gcc_sees_it(tmp_path):
+    """Every struct of include/footsies_b200.h, compiled as plain C: size and every field offset equal the ctypes mirror
+    in footsies_gym_b200/_capi.py (the header is the contract, the binding must not drift)."""
+    from footsies_gym_b200 import _capi
+    pairs = {"fg_config": _capi.FgConfig, "fg_buffers": _capi.FgBuffers, "fg_fighter_state": _capi.FgFighterState,
+             "fg_env_state": _capi.FgEnvState, "fg_host_outputs": _capi.FgHostOutputs,
+             "fg_rollout_buffers": _capi.FgRolloutBuffers}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "footsies_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     from footsies_gym_b200 import FootsiesEnv, _capi
