@@ -78,7 +78,7 @@ _lib = None
 # every symbol include/footsies_b200.h declares
 EXPORTS = ["fg_abi_version", "fg_last_error", "fg_algorithmic_bytes_per_env_step", "fg_create", "fg_destroy",
            "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_step_host_compact",
-           "fg_reset_host_compact", "fg_get_state",
+           "fg_reset_host_compact", "fg_delay_ring_step", "fg_get_state",
            "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_last_error",
            "fg_rollout_mlp"]
 
@@ -119,6 +119,8 @@ def load(build_if_missing=True):
     L.fg_step_host_compact.argtypes = [vp, vp, vp, C.POINTER(FgHostOutputs), vp]
     L.fg_reset_host_compact.restype = i32
     L.fg_reset_host_compact.argtypes = [vp, vp, C.POINTER(FgHostOutputs), vp]
+    L.fg_delay_ring_step.restype = i32
+    L.fg_delay_ring_step.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.fg_get_state.restype = i32
     L.fg_get_state.argtypes = [vp, i32, i32, vp]
     L.fg_set_state.restype = i32

@@ -135,6 +135,37 @@ __global__ void __launch_bounds__(256) pack_obs_kernel(const float4 *__restrict_
     }
 }
 
+// The frame_delay queue of FootsiesEnv (footsies.py:129-131: deque(maxlen = frame_delay + 1); :533-535: append the newest
+// state, emit the oldest; :502-504: a reset refills the queue with the first state) as a ring of `depth` slots per battle
+// in device memory: one thread per battle writes the state the step kernel just produced into slot `pos` (into every
+// slot when the battle was reset by this step: info frame == -1) and emits slot (pos + 1) % depth.  44 B read + 44 B
+// written + 44 B emitted per battle and step.
+__global__ void __launch_bounds__(256) delay_ring_kernel(const float4 *__restrict__ obs, const int32_t *__restrict__ frame,
+                                                         const uint32_t *__restrict__ misc, float4 *ring_obs, int32_t *ring_frame,
+                                                         uint32_t *ring_misc, float4 *__restrict__ out_obs, int32_t *__restrict__ out_frame,
+                                                         uint32_t *__restrict__ out_misc, int n, int depth, int pos) {
+    const int oldest = (pos + 1) % depth;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = obs[2 * (size_t)i], b = obs[2 * (size_t)i + 1];
+        const int32_t f = frame[i];
+        const uint32_t m = misc[i];
+        float4 oa = a, ob = b;
+        int32_t of = f;
+        uint32_t om = m;
+        if (f == -1) {
+            for (int s = 0; s < depth; s++) {
+                const size_t k = (size_t)s * n + i;
+                ring_obs[2 * k] = a; ring_obs[2 * k + 1] = b; ring_frame[k] = f; ring_misc[k] = m;
+            }
+        } else {
+            const size_t k = (size_t)pos * n + i, o = (size_t)oldest * n + i;
+            ring_obs[2 * k] = a; ring_obs[2 * k + 1] = b; ring_frame[k] = f; ring_misc[k] = m;
+            oa = ring_obs[2 * o]; ob = ring_obs[2 * o + 1]; of = ring_frame[o]; om = ring_misc[o];
+        }
+        out_obs[2 * (size_t)i] = oa; out_obs[2 * (size_t)i + 1] = ob; out_frame[i] = of; out_misc[i] = om;
+    }
+}
+
 int step_range(fg_handle *h, int first, int count, cudaStream_t s) {
     const Params p = make_params(h, first, count);
     CUDA_TRY(h->cfg.frame_skip == 1 ? launch_step_k<false>(h->cfg, h->sm_count, s, p) : launch_step_k<true>(h->cfg, h->sm_count, s, p));
@@ -435,6 +466,22 @@ int32_t fg_read_stats(fg_handle *h, uint64_t *out, void *stream) {
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     CUDA_TRY(cudaMemcpyAsync(out, h->buf.stats, sizeof(uint64_t) * FG_STAT_COUNT, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return FG_OK;
+}
+
+int32_t fg_delay_ring_step(fg_handle *h, int32_t depth, int32_t pos, float *ring_obs, int32_t *ring_frame, uint8_t *ring_misc,
+                           float *out_obs, int32_t *out_frame, uint8_t *out_misc, void *stream) {
+    if (int rc = check_bound(h)) return rc;
+    if (depth < 2 || pos < 0 || pos >= depth) return fail(FG_ERR_INVALID_ARGUMENT, "depth must be frame_delay + 1 >= 2 and 0 <= pos < depth%s");
+    if (!ring_obs || !ring_frame || !ring_misc || !out_obs || !out_frame || !out_misc) return fail(FG_ERR_INVALID_ARGUMENT, "null buffer%s");
+    if (((uintptr_t)ring_obs & 15u) || ((uintptr_t)out_obs & 15u) || ((uintptr_t)ring_misc & 3u) || ((uintptr_t)out_misc & 3u))
+        return fail(FG_ERR_INVALID_ARGUMENT, "obs buffers must be 16-byte, misc buffers 4-byte aligned%s");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    delay_ring_kernel<<<grid_for(h, 8), 256, 0, (cudaStream_t)stream>>>(
+        (const float4 *)h->buf.obs, h->buf.info_frame, (const uint32_t *)h->buf.info_misc, (float4 *)ring_obs, ring_frame,
+        (uint32_t *)ring_misc, (float4 *)out_obs, out_frame, (uint32_t *)out_misc, h->cfg.num_envs, depth, pos);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
     return FG_OK;
 }
 

@@ -333,24 +333,15 @@ class FootsiesEnv:
         self._bind()
 
     def _advance_delay_ring(self):
-        # footsies.py:533-535: append the newest state, pop the oldest (queue length frame_delay + 1);
-        # an env that was just auto-reset restarts with a queue full of its first state (footsies.py:502-504)
-        d = self.frame_delay + 1
-        was_reset = self.info_frame == -1       # no host sync: masked writes for every env, every step
-        self._ring_obs.copy_(torch.where(was_reset[None, :, None], self.obs[None], self._ring_obs))
-        self._ring_frame.copy_(torch.where(was_reset[None, :], self.info_frame[None], self._ring_frame))
-        self._ring_misc.copy_(torch.where(was_reset[None, :, None], self.info_misc[None], self._ring_misc))
-        p = self._ring_pos
-        self._ring_obs[p].copy_(self.obs)
-        self._ring_frame[p].copy_(self.info_frame)
-        self._ring_misc[p].copy_(self.info_misc)
-        self._ring_pos = (p + 1) % d
-        o = self._ring_pos                      # oldest entry
-        self._delayed_obs.copy_(self._ring_obs[o])
-        self._delayed_frame.copy_(self._ring_frame[o])
-        self._delayed_misc.copy_(self._ring_misc[o])
-        # the DEAD -> STAND remap is applied to the delayed state when it is emitted (footsies.py:538-552);
-        # the kernel already applied it to the undelayed observation it wrote, so nothing more to do here.
+        # footsies.py:533-535: append the newest state, pop the oldest (queue length frame_delay + 1); an env that was just
+        # auto-reset restarts with a queue full of its first state (footsies.py:502-504).  One kernel (fg_delay_ring_step).
+        # The DEAD -> STAND remap is applied to the delayed state when it is emitted (footsies.py:538-552); the step kernel
+        # already applied it to the observation it wrote, so the ring holds remapped states.
+        ptr = lambda t: C.c_void_p(t.data_ptr())   # noqa: E731
+        _capi.check(self._lib.fg_delay_ring_step(
+            self._handle, self.frame_delay + 1, self._ring_pos, ptr(self._ring_obs), ptr(self._ring_frame), ptr(self._ring_misc),
+            ptr(self._delayed_obs), ptr(self._delayed_frame), ptr(self._delayed_misc), self._stream()))
+        self._ring_pos = (self._ring_pos + 1) % (self.frame_delay + 1)
 
     def _finish_obs(self):
         if self.frame_delay > 0:

@@ -169,6 +169,14 @@ int32_t fg_step_host_compact(fg_handle *h, const uint8_t *actions_p1, const uint
                              const fg_host_outputs *out, void *stream);
 int32_t fg_reset_host_compact(fg_handle *h, const uint8_t *mask, const fg_host_outputs *out, void *stream);
 
+/* Replaces: the frame_delay queue of FootsiesEnv (footsies.py:129-131, 502-504, 533-535) for all envs: pushes the state
+ * the last fg_step / fg_reset wrote to the bound obs / info buffers into slot `pos` of a ring of depth = frame_delay + 1
+ * slots (into every slot for envs that step just reset) and emits the oldest slot, (pos + 1) % depth, to out_*.  The
+ * caller owns the ring (DEVICE memory: ring_obs [depth][num_envs][8] floats, ring_frame [depth][num_envs], ring_misc
+ * [depth][num_envs][4]) and advances pos by one (mod depth) per step.  Reward and termination are not delayed. */
+int32_t fg_delay_ring_step(fg_handle *h, int32_t depth, int32_t pos, float *ring_obs, int32_t *ring_frame, uint8_t *ring_misc,
+                           float *out_obs, int32_t *out_frame, uint8_t *out_misc, void *stream);
+
 /* Replaces: remote-control STATE_SAVE / STATE_LOAD (footsies.py:432-444, BattleCore.cs:667-683) at the level
  * of the compact state.  out / in are HOST arrays of `count` entries starting at env `first`. Synchronous. */
 int32_t fg_get_state(fg_handle *h, int32_t first, int32_t count, fg_env_state *out);
