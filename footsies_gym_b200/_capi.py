@@ -18,7 +18,7 @@ class FgConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("num_envs", C.c_int32), ("device", C.c_int32),
                 ("p1_bot", C.c_int32), ("p2_bot", C.c_int32), ("dense_reward", C.c_int32),
                 ("frame_skip", C.c_int32), ("autoreset", C.c_int32), ("stale_intro_input", C.c_int32),
-                ("reserved0", C.c_int32), ("first_env_index", C.c_int64)]
+                ("skip_unactionable", C.c_int32), ("first_env_index", C.c_int64)]
 
 
 class FgBuffers(C.Structure):

@@ -64,6 +64,7 @@ Params make_params(const fg_handle *h, int first = 0, int count = -1) {
     p.first_env_index = h->cfg.first_env_index + first;
     p.n = count < 0 ? h->cfg.num_envs - first : count; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
     p.stale_intro = h->cfg.stale_intro_input;
+    p.skip_unactionable = h->cfg.skip_unactionable;
     p.large_shape_min_envs = h->large_shape_min_envs;
     return p;
 }
@@ -168,7 +169,9 @@ __global__ void __launch_bounds__(256) delay_ring_kernel(const float4 *__restric
 
 int step_range(fg_handle *h, int first, int count, cudaStream_t s) {
     const Params p = make_params(h, first, count);
-    CUDA_TRY(h->cfg.frame_skip == 1 ? launch_step_k<false>(h->cfg, h->sm_count, s, p) : launch_step_k<true>(h->cfg, h->sm_count, s, p));
+    // the single-frame kernels carry neither the frame_skip loop nor the fused FootsiesFrameSkipped loop
+    const bool single = h->cfg.frame_skip == 1 && !h->cfg.skip_unactionable;
+    CUDA_TRY(single ? launch_step_k<false>(h->cfg, h->sm_count, s, p) : launch_step_k<true>(h->cfg, h->sm_count, s, p));
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FG_OK;
@@ -313,6 +316,7 @@ int32_t fg_create(const fg_config *cfg, fg_handle **out) {
     if (cfg->struct_size != (int32_t)sizeof(fg_config)) return fail(FG_ERR_INVALID_ARGUMENT, "fg_config.struct_size mismatch%s");
     if (cfg->num_envs <= 0) return fail(FG_ERR_INVALID_ARGUMENT, "num_envs must be positive%s");
     if (cfg->frame_skip < 1 || cfg->frame_skip > 64) return fail(FG_ERR_INVALID_ARGUMENT, "frame_skip must be in [1, 64]%s");
+    if (cfg->skip_unactionable && cfg->p1_bot) return fail(FG_ERR_INVALID_ARGUMENT, "skip_unactionable needs an agent-controlled P1%s");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

@@ -418,6 +418,18 @@ FG_DEV void make_outputs(const Env &e, StepOutputs &o) {
                 | ((e.pk1 >> FGP_STUN_SHIFT) & 31u) << 16 | ((e.pk2 >> FGP_STUN_SHIFT) & 31u) << 24;
 }
 
+// FootsiesFrameSkipped._is_obs_skippable (wrappers/frame_skip.py:56-66) on the state the observation is made from: P1 is
+// in the middle of a move (observed move_frame != 0, i.e. not STAND / FORWARD / BACKWARD and past frame 0) while P2 is not
+// in a hit / guard move, or P1 is in DAMAGE.  Same DEAD / WIN -> STAND remap as make_outputs.
+FG_DEV bool obs_is_skippable(const Env &e) {
+    uint32_t m1 = (e.pk1 >> FGP_ACT_SHIFT) & 31u, m2 = (e.pk2 >> FGP_ACT_SHIFT) & 31u;
+    if (m1 >= DEAD) m1 = STAND;
+    if (m2 >= DEAD) m2 = STAND;
+    const uint32_t f1 = m1 <= BACKWARD ? 0u : e.pk1 & 63u;
+    const bool p2_hit_guard = m2 == DAMAGE || m2 == FT_IDX_GUARD_STAND || m2 == FT_IDX_GUARD_CROUCH || m2 == FT_IDX_GUARD_M || m2 == GUARD_BREAK;
+    return (f1 != 0u && !p2_hit_guard) || m1 == DAMAGE;
+}
+
 // One fight frame for one env (everything between "inputs known" and "state after the frame").
 // Sets `terminal`, accumulates the Python float64 reward into `reward`, bumps the packed statistics.
 template <bool P1BOT, bool P2BOT, bool DENSE, bool LUT_REQUEST>

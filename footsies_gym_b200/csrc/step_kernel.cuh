@@ -74,6 +74,7 @@ struct Params {
     const uint8_t *step_mask;
     long long seed_base, first_env_index;
     int n, frame_skip, autoreset, stale_intro;
+    int skip_unactionable;      // fused FootsiesFrameSkipped (KFUSED kernels only)
     int large_shape_min_envs;   // host side only: batch size from which the large CTA shapes are launched
 };
 
@@ -276,11 +277,30 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
                 }
             }
         }
+        if (KFUSED && p.skip_unactionable) {
+            // FootsiesFrameSkipped.step (wrappers/frame_skip.py:68-80): while the observation is one P1 cannot act on and
+            // the battle is not over, take another env step (K frames) with P1's no-op input and add its reward.  The
+            // loop is warp-synchronous (every lane goes round until no lane of the warp needs another step) so that the
+            // statistics fold stays a warp-uniform decision.
+            bool more = run && !terminal && obs_is_skippable(e);
+            while (__any_sync(kFull, more)) {
+                for (int kk = 0; kk < K; kk++) {
+                    if (more && !terminal) {
+                        simulate_frame<P1BOT, P2BOT, DENSE, KFUSED>(T, e, 0u, in2, reward, terminal, acc);
+                        acc.s += 1u << 24;
+                        if (P2BOT) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                    }
+                }
+                more = more && !terminal && obs_is_skippable(e);
+                frames_since_flush += (uint32_t)K;
+                if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, S.stats, lane); frames_since_flush = 0u; }
+            }
+        }
         if (run) {
             store_env<kRng>(p, i, e);
             write_outputs(p, i, e, (float)reward, terminal);
         }
-        frames_since_flush += (uint32_t)K;                              // uniform across the group
+        frames_since_flush += (uint32_t)K;                              // uniform across the warp
         if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, S.stats, lane); frames_since_flush = 0u; }
     }
     flush_stats(acc, S.stats, lane);

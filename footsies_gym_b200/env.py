@@ -78,6 +78,7 @@ class FootsiesEnv:
         seed: Optional[int] = 0,
         first_env_index: int = 0,
         stale_intro_input: bool = True,
+        skip_unactionable: bool = False,
         **reference_kwargs,
     ):
         """
@@ -95,6 +96,9 @@ class FootsiesEnv:
         autoreset: see module docstring
         seed: per-env bot RNG = InitState(seed + first_env_index + i); None leaves the RNG planes zeroed
         first_env_index: global index of env 0 (multi-GPU sharding keeps results independent of the split)
+        skip_unactionable: FootsiesFrameSkipped (wrappers/frame_skip.py:46-80) fused into step(): an env whose new
+            observation P1 cannot act on keeps stepping with P1's no-op action inside the same kernel launch, rewards
+            summed (the FootsiesFrameSkipped wrapper switches this on; see set_skip_unactionable)
         reference_kwargs: game_path, game_address, game_port, fast_forward, sync_mode, ... are accepted
             and ignored (there is no game process to configure)
         """
@@ -131,6 +135,9 @@ class FootsiesEnv:
         self.autoreset = bool(autoreset)
         self.first_env_index = int(first_env_index)
         self.stale_intro_input = bool(stale_intro_input)
+        self.skip_unactionable = bool(skip_unactionable)
+        if self.skip_unactionable and self.by_example:
+            raise ValueError("skip_unactionable needs an agent-controlled P1 (by_example=False)")
         self.render_mode = None
 
         relevant = [m for m in FootsiesMove if m.name not in ("WIN", "DEAD")]
@@ -195,7 +202,8 @@ class FootsiesEnv:
             struct_size=C.sizeof(_capi.FgConfig), num_envs=self.num_envs, device=self.device.index,
             p1_bot=int(self.by_example), p2_bot=int(self._opponent_mode == "bot"),
             dense_reward=int(self.dense_reward), frame_skip=self.frame_skip, autoreset=int(self.autoreset),
-            stale_intro_input=int(self.stale_intro_input), reserved0=0, first_env_index=self.first_env_index)
+            stale_intro_input=int(self.stale_intro_input), skip_unactionable=int(self.skip_unactionable),
+            first_env_index=self.first_env_index)
 
     def _create_handle(self):
         if self._handle is not None:
@@ -319,6 +327,17 @@ class FootsiesEnv:
             self._advance_delay_ring()
         obs, info = self._finish_obs()
         return obs, self.reward, self.terminated, self.truncated, info
+
+    def set_skip_unactionable(self, flag: bool):
+        """Switch the fused FootsiesFrameSkipped stepping on or off (fg_config.skip_unactionable).  The battle state
+        lives in tensors this object owns, so only the library handle is re-created."""
+        flag = bool(flag)
+        if flag and self.by_example:
+            raise ValueError("skip_unactionable needs an agent-controlled P1 (by_example=False)")
+        if flag != self.skip_unactionable:
+            self.skip_unactionable = flag
+            torch.cuda.synchronize(self.device)
+            self._create_handle()
 
     def set_step_mask(self, mask: Optional[torch.Tensor]):
         """Only envs with mask[i] != 0 are advanced by the following step() calls (None = all); the others keep

@@ -115,11 +115,22 @@ _HIT_GUARD_MOVES = (FootsiesMove.DAMAGE, FootsiesMove.GUARD_STAND, FootsiesMove.
 
 class FootsiesFrameSkipped(_Wrapper):
     """Skip the time steps on which the agent cannot act (frame_skip.py:46-80): envs whose observation is
-    skippable keep stepping with the no-op action -- only those envs advance (the kernel's step mask) -- and
-    the rewards are accumulated.  P1's move_frame is dropped from the observation."""
+    skippable keep stepping with the no-op action and the rewards are accumulated.  P1's move_frame is dropped from the
+    observation.  With the CUDA env and an opponent that is not a Python callable the whole loop runs inside the step
+    kernel (fg_config.skip_unactionable: one launch per step, no host round trip); otherwise it is a loop of masked
+    steps here -- only the skippable envs advance (the kernel's step mask)."""
 
-    def __init__(self, env):
+    def __init__(self, env, fused: Optional[bool] = None):
         super().__init__(env)
+        base0 = self.unwrapped
+        can_fuse = hasattr(base0, "set_skip_unactionable") and getattr(base0, "opponent", None) is None \
+            and not getattr(base0, "by_example", False) and getattr(base0, "frame_delay", 0) == 0
+        if fused and not can_fuse:
+            raise ValueError("fused frame skipping needs the CUDA env, an agent-controlled P1, no frame_delay and an "
+                             "opponent that is not a Python callable")
+        self.fused = can_fuse if fused is None else bool(fused)
+        if self.fused:
+            base0.set_skip_unactionable(True)
         sp = dict(env.observation_space.spaces)
         mf = sp["move_frame"]
         sp["move_frame"] = Box(low=float(mf.low[1]), high=float(mf.high[1]), shape=(1,))
@@ -150,6 +161,8 @@ class FootsiesFrameSkipped(_Wrapper):
     def step(self, action, *args, **kw):
         base = self.unwrapped
         obs, reward, terminated, truncated, info = self.env.step(action, *args, **kw)
+        if self.fused:
+            return self._frame_skip_obs(obs), reward, terminated, truncated, info
         self._retained.copy_(reward)
         skip = self._is_obs_skippable(obs) & ~(terminated | truncated)
         while bool(skip.any()):

@@ -45,7 +45,9 @@ typedef struct {
     int32_t autoreset;          /* 0: finished battles freeze until fg_reset; 1: the step after a terminal
                                    one performs the reset and returns the frame -1 state                  */
     int32_t stale_intro_input;  /* 1 = reference behaviour: the Intro frame replays the actors' last input */
-    int32_t reserved0;
+    int32_t skip_unactionable;  /* 1: FootsiesFrameSkipped (wrappers/frame_skip.py:46-80) fused into fg_step: after the
+                                   step, a battle whose observation P1 cannot act on (frame_skip.py:56-66) keeps stepping
+                                   with P1's no-op input inside the same launch; rewards are summed                 */
     int64_t first_env_index;    /* global index of env 0 (multi-GPU sharding; seeds use global indices)   */
 } fg_config;
 

@@ -16,7 +16,7 @@
 using namespace fg;
 
 struct he_handle {
-    int n, p1_bot, p2_bot, dense, frame_skip, autoreset, stale;
+    int n, p1_bot, p2_bot, dense, frame_skip, autoreset, stale, skip_unactionable = 0;
     long long first_env_index;
     Tables T;
     std::vector<FgVec4> pl[4];
@@ -107,6 +107,18 @@ static void step_t(he_handle *h, const uint8_t *a1, const uint8_t *a2, const uin
                 if (B2) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
             }
         }
+        if (h->skip_unactionable) {                                     // fused FootsiesFrameSkipped, as in step_kernel
+            while (run && !terminal && obs_is_skippable(e)) {
+                for (int kk = 0; kk < h->frame_skip; kk++) {
+                    if (!terminal) {
+                        simulate_frame<B1, B2, DENSE, FUSED>(h->T, e, 0u, in2, reward, terminal, acc);
+                        acc.s += 1u << 24;
+                        if (B2) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                    }
+                }
+                flush(h, acc);
+            }
+        }
         if (run) {
             store_env(h, i, e);
             write_outputs(h, i, e, (float)reward, terminal);
@@ -129,6 +141,7 @@ he_handle *he_create(int n, int p1_bot, int p2_bot, int dense, int frame_skip, i
     return h;
 }
 void he_destroy(he_handle *h) { delete h; }
+void he_set_skip_unactionable(he_handle *h, int flag) { h->skip_unactionable = flag; }
 void he_seed(he_handle *h, long long seed_base, const uint8_t *mask) {
     for (int i = 0; i < h->n; i++) {
         if (mask && !mask[i]) continue;
@@ -145,7 +158,7 @@ void he_reset(he_handle *h, const uint8_t *mask) {
 }
 void he_step(he_handle *h, const uint8_t *a1, const uint8_t *a2, const uint8_t *step_mask) {
 #define GO(B1, B2) do { \
-        if (h->frame_skip > 1) { if (h->dense) step_t<B1, B2, true, true>(h, a1, a2, step_mask); else step_t<B1, B2, false, true>(h, a1, a2, step_mask); } \
+        if (h->frame_skip > 1 || h->skip_unactionable) { if (h->dense) step_t<B1, B2, true, true>(h, a1, a2, step_mask); else step_t<B1, B2, false, true>(h, a1, a2, step_mask); } \
         else { if (h->dense) step_t<B1, B2, true, false>(h, a1, a2, step_mask); else step_t<B1, B2, false, false>(h, a1, a2, step_mask); } \
     } while (0)
     if (h->p1_bot && h->p2_bot) GO(true, true);

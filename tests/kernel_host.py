@@ -35,6 +35,7 @@ def lib():
         L.he_create.restype = C.c_void_p
         L.he_create.argtypes = [C.c_int] * 7 + [C.c_longlong]
         L.he_destroy.argtypes = [C.c_void_p]
+        L.he_set_skip_unactionable.argtypes = [C.c_void_p, C.c_int]
         L.he_seed.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p]
         L.he_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.he_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -86,6 +87,9 @@ class HostKernelEnv:
         if seed is not None:
             self.seed(seed, m)
         lib().he_reset(self.h, _ptr(m))
+
+    def set_skip_unactionable(self, flag):
+        lib().he_set_skip_unactionable(self.h, int(bool(flag)))
 
     def set_step_mask(self, mask):
         self._mask = None if mask is None else np.ascontiguousarray(np.asarray(mask), dtype=np.uint8)

@@ -150,3 +150,55 @@ def case_input_personalities_vs_bot_sparse(make_env, oracle, scale=1.0):
 
 
 FUSED_PARAMS = [(4, False), (4, True), (3, True), (16, False), (2, False), (2, True)]
+
+
+def _obs_is_skippable(obs):
+    """FootsiesFrameSkipped._is_obs_skippable (wrappers/frame_skip.py:56-66) on the obs tensor [N, 8]."""
+    o = np.asarray(obs.cpu() if hasattr(obs, "cpu") else obs)
+    m1, m2, mf1 = o[:, 2].astype(np.int64), o[:, 3].astype(np.int64), o[:, 4]
+    hit_guard = np.zeros(17, dtype=bool)
+    hit_guard[[9, 10, 11, 12, 13]] = True          # DAMAGE, GUARD_M, GUARD_STAND, GUARD_CROUCH, GUARD_BREAK (moves.py order)
+    return ((mf1 != 0.0) & ~hit_guard[m2]) | (m1 == 9)
+
+
+def frame_skipped_fused_vs_masked_loop(make_env, frame_skip=1, p2_bot=True, n=400, steps=300, seed=3):
+    """fg_config.skip_unactionable (FootsiesFrameSkipped fused into the step) against the wrapper's own loop -- one env step,
+    then masked no-op steps for the envs whose observation P1 cannot act on (wrappers/frame_skip.py:68-80): identical
+    state, observation, termination and statistics after every wrapper step; summed reward to 1e-6 (the loop adds float32
+    step rewards, the kernel sums in float64 like the reference's Python floats)."""
+    rng = np.random.default_rng(seed)
+    kw = dict(num_envs=n, opponent=None if p2_bot else "self_play", frame_skip=frame_skip, seed=seed)
+    fused, plain = make_env(**kw), make_env(**kw)
+    fused.set_skip_unactionable(True)
+    fused.reset()
+    plain.reset()
+    tape1 = tape_sticky(rng, steps, n, p_change=0.3)
+    tape2 = tape_sticky(rng, steps, n, p_change=0.3)
+    zero = np.zeros(n, dtype=np.uint8)
+    skipped_steps = 0
+    for t in range(steps):
+        a2 = None if p2_bot else tape2[t]
+        fused.step(tape1[t], a2)
+        plain.step(tape1[t], a2)
+        total = np.asarray(plain.reward.cpu(), dtype=np.float64).copy()
+        done = np.asarray(plain.terminated.cpu()).astype(bool)
+        skip = _obs_is_skippable(plain.obs) & ~done
+        while skip.any():
+            plain.set_step_mask(torch.from_numpy(skip))
+            plain.step(zero, a2)
+            plain.set_step_mask(None)
+            total += np.where(skip, np.asarray(plain.reward.cpu(), dtype=np.float64), 0.0)
+            done = np.asarray(plain.terminated.cpu()).astype(bool)
+            skip = skip & _obs_is_skippable(plain.obs) & ~done
+            skipped_steps += 1
+        where = f"frame-skipped step {t}"
+        assert fused.get_state().tobytes() == plain.get_state().tobytes(), where
+        assert np.array_equal(np.asarray(fused.obs.cpu()), np.asarray(plain.obs.cpu())), where
+        assert np.array_equal(np.asarray(fused.terminated.cpu()).astype(bool), done), where
+        assert np.array_equal(np.asarray(fused.info_frame.cpu()), np.asarray(plain.info_frame.cpu())), where
+        assert np.abs(np.asarray(fused.reward.cpu(), dtype=np.float64) - total).max() <= 1e-6, where
+        assert not (_obs_is_skippable(fused.obs) & ~done).any(), where
+    assert skipped_steps > steps                      # the loop really had work to do
+    assert fused.episode_stats() == plain.episode_stats()
+    fused.close()
+    plain.close()

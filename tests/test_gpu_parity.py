@@ -85,6 +85,12 @@ def test_single_env_reference_style_loop(oracle):
     env.close()
 
 
+@pytest.mark.parametrize("frame_skip,p2_bot,n", [(1, True, 3000), (3, True, 1000), (1, False, 1000)])
+def test_frame_skipped_fused_into_the_step_kernel(frame_skip, p2_bot, n):
+    """fg_config.skip_unactionable against the FootsiesFrameSkipped loop of masked steps (wrappers/frame_skip.py:68-80)."""
+    pc.frame_skipped_fused_vs_masked_loop(make_env, frame_skip, p2_bot, n=n, steps=300)
+
+
 @pytest.mark.parametrize("chunk_envs", [None, 256])
 def test_host_buffer_step_matches_oracle(oracle, monkeypatch, chunk_envs):
     """FootsiesEnv.step_host / reset_host (fg_step_host_compact: compact 27-byte host layout) against the oracle; with

@@ -27,6 +27,11 @@ def test_fused_frame_skip_host_logic(oracle, k, p2_bot):
     pc.case_fused_frame_skip(make_env, oracle, k, p2_bot, scale=0.0625)
 
 
+@pytest.mark.parametrize("frame_skip,p2_bot", [(1, True), (3, True), (1, False)])
+def test_frame_skipped_fusion_host_logic(frame_skip, p2_bot):
+    pc.frame_skipped_fused_vs_masked_loop(make_env, frame_skip, p2_bot, n=120, steps=250)
+
+
 def test_masked_reset_and_state_round_trip_host_logic(oracle):
     from kernel_host import HostKernelEnv
     from parity import compare_state_and_outputs
