@@ -90,19 +90,21 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
         }
         // ---- sample + FootsiesEnv.step for the CTA's battles (same order of events as step_kernel) ----
         if (sim_thread) {
+            double reward = 0.0;
+            bool terminal = false, ran = false;
+            uint32_t in2 = 0u;
             if (valid) {
                 float lg[8], lp;
                 policy_logits_of<H, kEnvs, W>(pw, stid, lg);
                 const uint32_t in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)i), lp);
                 rp.actions[(size_t)t * n + i] = (uint8_t)in1;
                 rp.logp[(size_t)t * n + i] = lp;
-                double reward = 0.0;
-                bool terminal = false;
                 if ((e.misc >> FGM_DONE_SHIFT) & 1u) {                  // next-step autoreset: this step only resets
                     reset_env<false, true>(T, e, p.stale_intro != 0);
                     acc.s += 0x10000u;
                 } else {
-                    uint32_t in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                    ran = true;
+                    in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
                     for (int kk = 0; kk < K; kk++) {
                         if (!terminal) {
                             simulate_frame<false, true, DENSE, false>(T, e, in1, in2, reward, terminal, acc);
@@ -111,6 +113,25 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
                         }
                     }
                 }
+            }
+            if (p.skip_unactionable) {
+                // fused FootsiesFrameSkipped, exactly as in step_kernel: warp-synchronous so that the statistics fold
+                // stays a warp-uniform decision
+                bool more = ran && !terminal && obs_is_skippable(e);
+                while (__any_sync(kFull, more)) {
+                    for (int kk = 0; kk < K; kk++) {
+                        if (more && !terminal) {
+                            simulate_frame<false, true, DENSE, false>(T, e, 0u, in2, reward, terminal, acc);
+                            acc.s += 1u << 24;
+                            in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                        }
+                    }
+                    more = more && !terminal && obs_is_skippable(e);
+                    frames_since_flush += (uint32_t)K;
+                    if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, s_stats, lane); frames_since_flush = 0u; }
+                }
+            }
+            if (valid) {
                 StepOutputs o;
                 make_outputs(e, o);
                 const float4 a = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]), b = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);

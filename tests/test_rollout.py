@@ -54,12 +54,14 @@ def test_rollout_is_replayable(oracle, use_graph, fused):
         assert np.array_equal(out["dones"][t].cpu().numpy().astype(np.int32), tr["terminated"])
 
 
-@pytest.mark.parametrize("hidden,n,dense,frame_skip", [(64, 1000, True, 1), (32, 64, False, 1), (128, 333, True, 3),
-                                                       (64, 16384, True, 1)])
-def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip):
+@pytest.mark.parametrize("hidden,n,dense,frame_skip,skip", [(64, 1000, True, 1, False), (32, 64, False, 1, False),
+                                                            (128, 333, True, 3, False), (64, 16384, True, 1, False),
+                                                            (64, 700, True, 1, True), (32, 333, True, 2, True)])
+def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip, skip):
     """fg_rollout_mlp (one launch per horizon, state in registers) against fg_policy_mlp_sample + fg_step per step:
     every rollout buffer, the final battle state and the episode statistics are bit-identical, over several horizons
-    (ragged batch sizes: 1000 and 333 are not multiples of the 64 battles a CTA owns)."""
+    (ragged batch sizes: 1000 and 333 are not multiples of the 64 battles a CTA owns); skip = the fused
+    FootsiesFrameSkipped stepping (fg_config.skip_unactionable) inside both."""
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
     if not torch.cuda.is_available():
@@ -73,7 +75,7 @@ def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip):
     horizon = 150                                           # > 120 frames: the statistics byte lanes are folded mid-horizon
     envs, cols = [], []
     for mode in ("step", "horizon"):
-        env = FootsiesEnv(num_envs=n, device=dev, seed=3, dense_reward=dense, frame_skip=frame_skip)
+        env = FootsiesEnv(num_envs=n, device=dev, seed=3, dense_reward=dense, frame_skip=frame_skip, skip_unactionable=skip)
         envs.append(env)
         cols.append(RolloutCollector(env, policy, horizon=horizon, use_cuda_graph=False, fused=mode, seed=17))
     assert [c.mode for c in cols] == ["step", "horizon"]
