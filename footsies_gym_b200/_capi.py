@@ -40,7 +40,10 @@ class FgRolloutBuffers(C.Structure):
                 ("scale", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
                 ("w3", C.c_void_p), ("b3", C.c_void_p), ("seed", C.c_uint64), ("counter_base", C.c_void_p),
                 ("obs", C.c_void_p), ("actions", C.c_void_p), ("logp", C.c_void_p), ("rewards", C.c_void_p),
-                ("dones", C.c_void_p)]
+                ("dones", C.c_void_p),
+                ("p2_scale", C.c_void_p), ("p2_w1", C.c_void_p), ("p2_b1", C.c_void_p), ("p2_w2", C.c_void_p),
+                ("p2_b2", C.c_void_p), ("p2_w3", C.c_void_p), ("p2_b3", C.c_void_p), ("p2_seed", C.c_uint64),
+                ("actions_p2", C.c_void_p), ("logp_p2", C.c_void_p), ("p2_mirror", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class FgFighterState(C.Structure):
@@ -79,7 +82,7 @@ _lib = None
 EXPORTS = ["fg_abi_version", "fg_last_error", "fg_algorithmic_bytes_per_env_step", "fg_create", "fg_destroy",
            "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_step_host_compact",
            "fg_reset_host_compact", "fg_delay_ring_step", "fg_get_state",
-           "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_last_error",
+           "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_mlp_sample_p2", "fg_policy_last_error",
            "fg_rollout_mlp"]
 
 
@@ -131,6 +134,8 @@ def load(build_if_missing=True):
     L.fg_launch_count.argtypes = [vp]
     L.fg_policy_mlp_sample.restype = i32
     L.fg_policy_mlp_sample.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+    L.fg_policy_mlp_sample_p2.restype = i32
+    L.fg_policy_mlp_sample_p2.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, i32, vp]
     L.fg_policy_last_error.restype = C.c_char_p
     L.fg_rollout_mlp.restype = i32
     L.fg_rollout_mlp.argtypes = [vp, C.POINTER(FgRolloutBuffers), vp]

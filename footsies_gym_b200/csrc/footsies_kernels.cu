@@ -493,9 +493,14 @@ int32_t fg_rollout_mlp(fg_handle *h, const fg_rollout_buffers *r, void *stream) 
     if (int rc = check_bound(h)) return rc;
     if (!r || r->struct_size != (int32_t)sizeof(fg_rollout_buffers))
         return fail(FG_ERR_INVALID_ARGUMENT, "fg_rollout_buffers is null or its struct_size does not match%s");
-    if (h->cfg.p1_bot || !h->cfg.p2_bot || !h->cfg.autoreset || h->buf.step_mask)
-        return fail(FG_ERR_INVALID_STATE, "fg_rollout_mlp needs P1 = policy, P2 = in-game bot, autoreset on, no step mask "
+    if (h->cfg.p1_bot || !h->cfg.autoreset || h->buf.step_mask)
+        return fail(FG_ERR_INVALID_STATE, "fg_rollout_mlp needs P1 = policy, autoreset on, no step mask "
                                           "(use fg_policy_mlp_sample + fg_step for other configurations)%s");
+    const bool p2_policy = !h->cfg.p2_bot;
+    if (p2_policy && (!r->p2_scale || !r->p2_w1 || !r->p2_b1 || !r->p2_w2 || !r->p2_b2 || !r->p2_w3 || !r->p2_b3 || !r->actions_p2 ||
+                      !r->logp_p2 || ((uintptr_t)r->p2_w2 & 15u)))
+        return fail(FG_ERR_INVALID_ARGUMENT, "p2_bot = 0: fg_rollout_buffers needs the P2 policy (p2_* weights, 16-byte aligned p2_w2, "
+                                             "actions_p2, logp_p2)%s");
     if (r->hidden != 32 && r->hidden != 64 && r->hidden != 128) return fail(FG_ERR_INVALID_ARGUMENT, "hidden size must be 32, 64 or 128%s");
     if (r->horizon < 1) return fail(FG_ERR_INVALID_ARGUMENT, "horizon must be positive%s");
     if (!r->scale || !r->w1 || !r->b1 || !r->w2 || !r->b2 || !r->w3 || !r->b3 || !r->obs || !r->actions || !r->logp || !r->rewards || !r->dones)
@@ -508,6 +513,9 @@ int32_t fg_rollout_mlp(fg_handle *h, const fg_rollout_buffers *r, void *stream) 
     rp.seed = r->seed; rp.counter_base = (const unsigned long long *)r->counter_base;
     rp.hidden = r->hidden; rp.horizon = r->horizon;
     rp.obs = (float4 *)r->obs; rp.actions = r->actions; rp.logp = r->logp; rp.rewards = r->rewards; rp.dones = r->dones;
+    rp.p2_policy = p2_policy; rp.p2_mirror = p2_policy && r->p2_mirror;
+    rp.w_p2 = { r->p2_scale, r->p2_w1, r->p2_b1, r->p2_w2, r->p2_b2, r->p2_w3, r->p2_b3 };
+    rp.seed_p2 = r->p2_seed; rp.actions_p2 = r->actions_p2; rp.logp_p2 = r->logp_p2;
     CUDA_TRY(launch_rollout(h->cfg.dense_reward != 0, (cudaStream_t)stream, rp));
     h->launches++;
     CUDA_TRY(cudaGetLastError());

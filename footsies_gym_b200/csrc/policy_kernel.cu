@@ -32,6 +32,7 @@ struct PolicyParams {
     unsigned long long seed, counter;
     const unsigned long long *counter_base;   // optional device word added to `counter` (CUDA-graph replays bump it)
     int n, hidden;
+    int mirror;                // 1: the policy drives P2 from the mirrored observation, its action is mirrored back
 };
 
 template <int H>
@@ -55,13 +56,15 @@ __global__ void __launch_bounds__(kPolThreads) policy_mlp_sample_kernel(const Po
             }
             x[q][0] = a.x; x[q][1] = a.y; x[q][2] = a.z; x[q][3] = a.w;
             x[q][4] = b.x; x[q][5] = b.y; x[q][6] = b.z; x[q][7] = b.w;
+            if (p.mirror) policy_mirror_obs(x[q]);
         }
-        policy_partials_bcast<H, kPolE, kPolicyWarps>(sm, warp, lane, x);     // two CTA barriers inside
+        policy_partials_bcast<H, kPolE, kPolicyWarps>(sm, sm + PolicySmemBcast<H, kPolEnvs, kPolicyWarps>::kWeightFloats, warp, lane, x);     // two CTA barriers inside
         const int env = base + tid;                             // one sampling thread per battle
         if (tid < kPolEnvs && env < p.n) {
             float lg[8], lp;
-            policy_logits_of<H, kPolEnvs, kPolicyWarps>(sm, tid, lg);
-            const int a = policy_sample(lg, hash3(p.seed, counter, (uint32_t)env), lp);
+            policy_logits_of<H, kPolEnvs, kPolicyWarps>(sm, sm + PolicySmemBcast<H, kPolEnvs, kPolicyWarps>::kWeightFloats, tid, lg);
+            int a = policy_sample(lg, hash3(p.seed, counter, (uint32_t)env), lp);
+            if (p.mirror) a = policy_mirror_action(a);
             p.actions[env] = (uint8_t)a;
             if (p.logp) p.logp[env] = lp;
         }
@@ -78,10 +81,10 @@ extern "C" {
 
 const char *fg_policy_last_error(void) { return g_perr; }
 
-int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
-                             const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
-                             uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
-                             float *obs_copy, void *stream) {
+static int32_t policy_sample_impl(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
+                                  const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
+                                  uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
+                                  float *obs_copy, int32_t mirror, void *stream) {
     if (!obs || !scale || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !actions || num_envs <= 0) {
         snprintf(g_perr, sizeof g_perr, "fg_policy_mlp_sample: null argument or empty batch");
         return FG_ERR_INVALID_ARGUMENT;
@@ -91,7 +94,7 @@ int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *
         return FG_ERR_INVALID_ARGUMENT;
     }
     PolicyParams p = { obs, { scale, w1, b1, w2, b2, w3, b3 }, actions, logp, obs_copy, seed, counter,
-                       (const unsigned long long *)counter_base, num_envs, hidden };
+                       (const unsigned long long *)counter_base, num_envs, hidden, mirror };
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -115,6 +118,22 @@ int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *
         return FG_ERR_CUDA;
     }
     return FG_OK;
+}
+
+int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
+                             const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
+                             uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
+                             float *obs_copy, void *stream) {
+    return policy_sample_impl(obs, scale, w1, b1, w2, b2, w3, b3, hidden, num_envs, seed, counter, counter_base, actions, logp,
+                              obs_copy, 0, stream);
+}
+
+int32_t fg_policy_mlp_sample_p2(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
+                                const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
+                                uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
+                                int32_t mirror, void *stream) {
+    return policy_sample_impl(obs, scale, w1, b1, w2, b2, w3, b3, hidden, num_envs, seed, counter, counter_base, actions, logp,
+                              nullptr, mirror != 0, stream);
 }
 
 }  // extern "C"

@@ -48,6 +48,14 @@ __device__ __forceinline__ uint32_t hash3(uint64_t seed, uint64_t counter, uint3
     return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 
+// The observation as the other player sees it (for a policy that drives P2 the way it would drive P1): the per-player
+// fields swap and the positions change sign.  The action such a policy picks is mirrored back with policy_mirror_action.
+__device__ __forceinline__ void policy_mirror_obs(float (&x)[8]) {
+    const float g = x[0], m = x[2], f = x[4], p = x[6];
+    x[0] = x[1]; x[1] = g; x[2] = x[3]; x[3] = m; x[4] = x[5]; x[5] = f; x[6] = -x[7]; x[7] = -p;
+}
+__device__ __forceinline__ int policy_mirror_action(int a) { return (a & 4) | ((a & 1) << 1) | ((a >> 1) & 1); }   // Left <-> Right
+
 // log-softmax + inverse-CDF sample from 8 logits with the 32-bit random word `rnd`; returns the action index 0..7 (= the
 // input bitmask Left 1 | Right 2 | Attack 4, wrappers/action_comb_disc.py:13-18) and its log-probability.
 __device__ __forceinline__ int policy_sample(const float (&lg)[8], uint32_t rnd, float &logp) {
@@ -76,6 +84,9 @@ struct PolicySmemBcast {
     static constexpr int kW1T = 0, kW2T = kW1T + 8 * H, kW3T = kW2T + H * H, kB1 = kW3T + 8 * H, kB2 = kB1 + H, kB3 = kB2 + H,
                          kScale = kB3 + 8, kHid = kScale + 8, kPart = kHid + H * NE, kFloats = kPart + W * 8 * NE;
     static constexpr size_t kBytes = sizeof(float) * kFloats;
+    // the block splits into the weights [0, kWeightFloats) and the activations (hid, part) behind them, so that a second
+    // policy can bring its own weights and share the activation buffers
+    static constexpr int kWeightFloats = kHid, kActFloats = kFloats - kHid;
 };
 
 // w1t[k][u] = W1[u][k], w2t[k][u] = W2[u][k], w3t[c][o] = W3[o][c] (input-major: the outputs of one input are contiguous).
@@ -97,7 +108,8 @@ __device__ __forceinline__ void policy_stage_bcast(float *sm, const PolicyWeight
     if (tid < 8) { sm[L::kB3 + tid] = p.b3[tid]; sm[L::kScale + tid] = p.scale[tid]; }
 }
 
-// All 32 W threads of the CTA.  x[e] = raw observation row of battle lane + 32 e.  On return (after the function's last
+// All 32 W threads of the CTA.  sm = the policy's weight block, act = the activation block (shared between policies);
+// x[e] = raw observation row of battle lane + 32 e.  On return (after the function's last
 // __syncthreads) the partial logits of every battle are in shared memory: policy_logits_of() assembles them.
 // The multiply-adds are issued as packed pairs (__ffma2_rn, Blackwell's FFMA2: two independent correctly rounded fp32
 // fmas per instruction, i.e. bit-identical to two fmaf) over adjacent output units.  Measured (tools/probes/
@@ -105,13 +117,13 @@ __device__ __forceinline__ void policy_stage_bcast(float *sm, const PolicyWeight
 // for FFMA, ~127 lane-fmas per cycle per SM either way -- it halves the ISSUE slots the fmas take, which is what this loop
 // is short of (weight and activation fetches share them): 7.6 -> 6.9 us per rollout step.
 template <int H, int E, int W>
-__device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int lane, float (&x)[E][8]) {
+__device__ __forceinline__ void policy_partials_bcast(const float *sm, float *act, int warp, int lane, float (&x)[E][8]) {
     constexpr int NE = 32 * E;
     using L = PolicySmemBcast<H, NE, W>;
     constexpr int Q = L::Q;
     const float *w1t = sm + L::kW1T + warp * Q, *w2t = sm + L::kW2T + warp * Q, *w3t = sm + L::kW3T + warp * Q * 8;
     const float *b1 = sm + L::kB1 + warp * Q, *b2 = sm + L::kB2 + warp * Q, *sc = sm + L::kScale;
-    float *hid = sm + L::kHid, *part = sm + L::kPart;
+    float *hid = act, *part = act + (L::kPart - L::kHid);
 #pragma unroll
     for (int e = 0; e < E; e++) {
 #pragma unroll
@@ -205,9 +217,9 @@ __device__ __forceinline__ void policy_partials_bcast(float *sm, int warp, int l
 // The 8 logits of battle `local` (0 .. NE - 1) from the partial sums left by policy_partials_bcast: a fixed pairwise tree
 // over the warps' partial sums, then the bias.
 template <int H, int NE, int W>
-__device__ __forceinline__ void policy_logits_of(const float *sm, int local, float (&lg)[8]) {
+__device__ __forceinline__ void policy_logits_of(const float *sm, const float *act, int local, float (&lg)[8]) {
     using L = PolicySmemBcast<H, NE, W>;
-    const float *part = sm + L::kPart, *b3 = sm + L::kB3;
+    const float *part = act + (L::kPart - L::kHid), *b3 = sm + L::kB3;
 #pragma unroll
     for (int o = 0; o < 8; o++) {
         float s[W];

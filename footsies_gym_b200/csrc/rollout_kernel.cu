@@ -25,25 +25,31 @@ namespace fgk {
 
 using namespace fgp;
 
-template <int H, int E, int W>
+template <int H, int E, int W, bool P2POL>
 struct RolloutSmem {
     static constexpr int kEnvs = 32 * E;
+    using PL = PolicySmemBcast<H, kEnvs, W>;
     static constexpr size_t kTables = 0;
-    static constexpr size_t kPolicy = (sizeof(Tables) + 127) / 128 * 128;
-    static constexpr size_t kObs = kPolicy + (PolicySmemBcast<H, kEnvs, W>::kBytes + 15) / 16 * 16;   // float4 [kEnvs][2]
+    static constexpr size_t kPolicy = (sizeof(Tables) + 127) / 128 * 128;                             // P1 weights + activations
+    static constexpr size_t kPolicy2 = kPolicy + (PL::kBytes + 15) / 16 * 16;                         // P2 weights (P2POL)
+    static constexpr size_t kObs = kPolicy2 + (P2POL ? (sizeof(float) * PL::kWeightFloats + 15) / 16 * 16 : 0);   // float4 [kEnvs][2]
     static constexpr size_t kStats = kObs + sizeof(float4) * 2 * kEnvs;                             // u64 [FG_STAT_COUNT]
     static constexpr size_t kBytes = kStats + sizeof(unsigned long long) * FG_STAT_COUNT;
 };
 
-template <int H, int E, int W, bool DENSE>
+template <int H, int E, int W, bool DENSE, bool P2POL>
 __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp) {
-    using SM = RolloutSmem<H, E, W>;
+    using SM = RolloutSmem<H, E, W, P2POL>;
+    using PL = typename SM::PL;
+    constexpr bool kP2Bot = !P2POL;                             // P2 = in-game bot (needs the RNG plane) or the second policy
     constexpr int kEnvs = SM::kEnvs, kRollThreads = 32 * W;
     static_assert(kEnvs <= kRollThreads, "one simulator thread per battle");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Tables &Tw = *reinterpret_cast<Tables *>(smem_raw + SM::kTables);
     const Tables &T = Tw;
     float *pw = reinterpret_cast<float *>(smem_raw + SM::kPolicy);
+    float *pact = pw + PL::kWeightFloats;                       // activations, shared by both policies
+    float *pw2 = reinterpret_cast<float *>(smem_raw + SM::kPolicy2);
     float4 *obs_s = reinterpret_cast<float4 *>(smem_raw + SM::kObs);
     unsigned long long *s_stats = reinterpret_cast<unsigned long long *>(smem_raw + SM::kStats);
     const Params &p = rp.sim;
@@ -57,9 +63,10 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
 
     load_tables(&Tw, p.tables);
     policy_stage_bcast<H, kEnvs, W>(pw, rp.w, tid, kRollThreads);
+    if (P2POL) policy_stage_bcast<H, kEnvs, W>(pw2, rp.w_p2, tid, kRollThreads);
     if (tid < FG_STAT_COUNT) s_stats[tid] = 0ull;
     Env e;
-    if (valid) load_env<true>(p, i, e);
+    if (valid) load_env<kP2Bot>(p, i, e);
     if (sim_thread) {
         // the observation the first step acts on: the last one of the previous horizon, carried over into slot 0
         float4 a = make_float4(0, 0, 0, 0), b = a;
@@ -86,30 +93,54 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
                 x[q][0] = a.x; x[q][1] = a.y; x[q][2] = a.z; x[q][3] = a.w;
                 x[q][4] = b.x; x[q][5] = b.y; x[q][6] = b.z; x[q][7] = b.w;
             }
-            policy_partials_bcast<H, E, W>(pw, warp, lane, x);
+            policy_partials_bcast<H, E, W>(pw, pact, warp, lane, x);
+        }
+        uint32_t in1 = 0u, in2 = 0u;
+        if (valid) {
+            float lg[8], lp;
+            policy_logits_of<H, kEnvs, W>(pw, pact, stid, lg);
+            in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)i), lp);
+            rp.actions[(size_t)t * n + i] = (uint8_t)in1;
+            rp.logp[(size_t)t * n + i] = lp;
+        }
+        if (P2POL) {
+            // the second policy on the same observation rows (mirrored if asked): the sampling threads above have read
+            // P1's partial sums before they arrive at the barriers in here, so the activation buffers can be reused
+            float x[E][8];
+#pragma unroll
+            for (int q = 0; q < E; q++) {
+                const float4 a = obs_s[2 * (lane + 32 * q)], b = obs_s[2 * (lane + 32 * q) + 1];
+                x[q][0] = a.x; x[q][1] = a.y; x[q][2] = a.z; x[q][3] = a.w;
+                x[q][4] = b.x; x[q][5] = b.y; x[q][6] = b.z; x[q][7] = b.w;
+                if (rp.p2_mirror) policy_mirror_obs(x[q]);
+            }
+            policy_partials_bcast<H, E, W>(pw2, pact, warp, lane, x);
+            if (valid) {
+                float lg[8], lp;
+                policy_logits_of<H, kEnvs, W>(pw2, pact, stid, lg);
+                int a2 = policy_sample(lg, hash3(rp.seed_p2, drawn + (unsigned long long)t, (uint32_t)i), lp);
+                if (rp.p2_mirror) a2 = policy_mirror_action(a2);
+                in2 = (uint32_t)a2;
+                rp.actions_p2[(size_t)t * n + i] = (uint8_t)a2;
+                rp.logp_p2[(size_t)t * n + i] = lp;
+            }
         }
         // ---- sample + FootsiesEnv.step for the CTA's battles (same order of events as step_kernel) ----
         if (sim_thread) {
             double reward = 0.0;
             bool terminal = false, ran = false;
-            uint32_t in2 = 0u;
             if (valid) {
-                float lg[8], lp;
-                policy_logits_of<H, kEnvs, W>(pw, stid, lg);
-                const uint32_t in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)i), lp);
-                rp.actions[(size_t)t * n + i] = (uint8_t)in1;
-                rp.logp[(size_t)t * n + i] = lp;
                 if ((e.misc >> FGM_DONE_SHIFT) & 1u) {                  // next-step autoreset: this step only resets
-                    reset_env<false, true>(T, e, p.stale_intro != 0);
+                    reset_env<false, kP2Bot>(T, e, p.stale_intro != 0);
                     acc.s += 0x10000u;
                 } else {
                     ran = true;
-                    in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                    if (kP2Bot) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
                     for (int kk = 0; kk < K; kk++) {
                         if (!terminal) {
-                            simulate_frame<false, true, DENSE, false>(T, e, in1, in2, reward, terminal, acc);
+                            simulate_frame<false, kP2Bot, DENSE, false>(T, e, in1, in2, reward, terminal, acc);
                             acc.s += 1u << 24;
-                            in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                            if (kP2Bot) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
                         }
                     }
                 }
@@ -121,9 +152,9 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
                 while (__any_sync(kFull, more)) {
                     for (int kk = 0; kk < K; kk++) {
                         if (more && !terminal) {
-                            simulate_frame<false, true, DENSE, false>(T, e, 0u, in2, reward, terminal, acc);
+                            simulate_frame<false, kP2Bot, DENSE, false>(T, e, 0u, in2, reward, terminal, acc);
                             acc.s += 1u << 24;
-                            in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                            if (kP2Bot) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
                         }
                     }
                     more = more && !terminal && obs_is_skippable(e);
@@ -148,27 +179,27 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
         __syncthreads();
     }
     if (sim_thread) {
-        if (valid) store_env<true>(p, i, e);
+        if (valid) store_env<kP2Bot>(p, i, e);
         flush_stats(acc, s_stats, lane);
     }
     __syncthreads();
     if (tid < FG_STAT_COUNT && s_stats[tid]) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
-template <int H, int E, int W, bool DENSE>
+template <int H, int E, int W, bool DENSE, bool P2POL>
 static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
-    constexpr size_t bytes = RolloutSmem<H, E, W>::kBytes;
+    constexpr size_t bytes = RolloutSmem<H, E, W, P2POL>::kBytes;
     static bool configured[64] = {};                    // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE, P2POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    constexpr int kEnvs = RolloutSmem<H, E, W>::kEnvs;
+    constexpr int kEnvs = RolloutSmem<H, E, W, P2POL>::kEnvs;
     const int grid = (rp.sim.n + kEnvs - 1) / kEnvs;
-    rollout_kernel<H, E, W, DENSE><<<grid, 32 * W, bytes, s>>>(rp);
+    rollout_kernel<H, E, W, DENSE, P2POL><<<grid, 32 * W, bytes, s>>>(rp);
     return cudaSuccess;
 }
 
@@ -179,7 +210,9 @@ static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
     int e = rp.sim.n >= 65536 ? 4 : 2;
     if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_E")) e = atoi(v);   // developer knob
     constexpr int E4 = H <= 64 ? 4 : 2;                                  // H = 128: 4 battles per lane do not fit the registers
-    return e == 4 ? launch_rollout_v<H, E4, kPolicyWarps, DENSE>(s, rp) : launch_rollout_v<H, 2, kPolicyWarps, DENSE>(s, rp);
+    if (rp.p2_policy)       // two weight sets in shared memory: always 2 battles per lane
+        return launch_rollout_v<H, 2, kPolicyWarps, DENSE, true>(s, rp);
+    return e == 4 ? launch_rollout_v<H, E4, kPolicyWarps, DENSE, false>(s, rp) : launch_rollout_v<H, 2, kPolicyWarps, DENSE, false>(s, rp);
 }
 
 cudaError_t launch_rollout(bool dense, cudaStream_t s, const RolloutParams &rp) {

@@ -17,9 +17,17 @@ struct RolloutParams {
     float *logp;                // [horizon][n]
     float *rewards;             // [horizon][n]
     uint8_t *dones;             // [horizon][n]
+    // P2 driven by a second policy instead of the in-game bot (self-play rollouts): same observation rows, optionally
+    // mirrored; its own weights, seed and output slots
+    int p2_policy, p2_mirror;
+    fgp::PolicyWeights w_p2;
+    unsigned long long seed_p2;
+    uint8_t *actions_p2;        // [horizon][n]
+    float *logp_p2;             // [horizon][n]
 };
 
-// P1 = the MLP policy, P2 = the in-game BattleAI, autoreset on.  Returns cudaErrorInvalidValue for other hidden sizes.
+// P1 = the MLP policy, P2 = the in-game BattleAI or a second MLP policy (p2_policy), autoreset on.  Returns
+// cudaErrorInvalidValue for other hidden sizes.
 cudaError_t launch_rollout(bool dense, cudaStream_t s, const RolloutParams &rp);
 
 }  // namespace fgk

@@ -10,8 +10,8 @@ Three policy paths:
     scale -> 8-H-H-8 tanh MLP -> log-softmax -> sample, and the rollout needs no copies at all: the step kernel is
     re-bound, per captured launch, to write observation t + 1, reward t and done t straight into the rollout buffers,
     and the policy kernel reads observation t from there.  Per step: 2 launches (policy, simulator step).
-  * `MLPPolicy`, fused="horizon" (the default whenever the env qualifies: P1 = policy, P2 = in-game bot, autoreset, no
-    step mask): ONE launch per horizon (csrc/rollout_kernel.cu, fg_rollout_mlp) -- a CTA keeps its 64 battles in
+  * `MLPPolicy`, fused="horizon" (the default whenever the env qualifies: P1 = policy, P2 = in-game bot or a second
+    MLPPolicy given as `opponent_policy` (self-play), autoreset, no step mask): ONE launch per horizon (csrc/rollout_kernel.cu, fg_rollout_mlp) -- a CTA keeps its 64 battles in
     registers from the first step to the last and alternates policy inference and the frame update; bit-identical
     to the per-step path.
 
@@ -63,6 +63,37 @@ class MLPPolicy(torch.nn.Module):
         if rc != 0:
             raise _capi.FootsiesLibraryError(lib.fg_policy_last_error().decode())
 
+    def fused_sample_p2(self, obs: torch.Tensor, actions: torch.Tensor, logp: Optional[torch.Tensor], seed: int, counter: int,
+                        counter_base: Optional[torch.Tensor] = None, mirror: bool = False):
+        """fused_sample for a policy that drives P2 (fg_policy_mlp_sample_p2): with mirror=True it is fed the mirrored
+        observation (per-player fields swapped, positions negated) and its Left / Right bits are mirrored back, so that
+        the network that plays P1 can play P2 as well."""
+        lib = _capi.load()
+        l1, l2, l3 = self.net[0], self.net[2], self.net[4]
+        ts = [obs, self.scale, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
+        for t in ts:
+            if t.dtype != torch.float32 or not t.is_contiguous() or t.device != obs.device:
+                raise ValueError("fused policy inference needs contiguous float32 tensors on one device")
+        if actions.dtype != torch.uint8 or not actions.is_contiguous():
+            raise ValueError("actions must be a contiguous uint8 tensor")
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
+        rc = lib.fg_policy_mlp_sample_p2(*[ptr(t) for t in ts], self.hidden, obs.shape[0], int(seed) & (2**64 - 1),
+                                         int(counter), ptr(counter_base), ptr(actions), ptr(logp), int(bool(mirror)),
+                                         C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+        if rc != 0:
+            raise _capi.FootsiesLibraryError(lib.fg_policy_last_error().decode())
+
+
+def mirror_obs(obs: torch.Tensor) -> torch.Tensor:
+    """The observation [N, 8] as P2 sees it: per-player fields swapped, positions negated."""
+    m = obs[:, [1, 0, 3, 2, 5, 4, 7, 6]].clone()
+    m[:, 6:8] = -m[:, 6:8]
+    return m
+
+
+_MIRROR_ACTION = (0, 2, 1, 3, 4, 6, 5, 7)      # Left (1) <-> Right (2)
+_P2_SEED_SALT = 0x5DEECE66D2F1A3B7
+
 
 class RolloutCollector:
     """Collects `horizon` steps of (obs, action, log-prob, reward, done) for every env of one GPU, entirely on device.
@@ -71,16 +102,27 @@ class RolloutCollector:
     the observation after the last step), actions uint8 [horizon, N], logp / rewards float32 [horizon, N], dones bool."""
 
     def __init__(self, env: FootsiesEnv, policy: Callable[[torch.Tensor], torch.Tensor], horizon: int = 128,
-                 use_cuda_graph: bool = True, fused=None, seed: int = 0):
+                 use_cuda_graph: bool = True, fused=None, seed: int = 0,
+                 opponent_policy: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, mirror_opponent: bool = False):
         """fused: None / True = the most fused path available ("horizon", else "step", else torch ops for a policy that
-        is not an MLPPolicy); False = torch ops; "step" / "horizon" = that path or an error."""
+        is not an MLPPolicy); False = torch ops; "step" / "horizon" = that path or an error.
+        opponent_policy: a second policy for P2 (self-play rollouts; the env must take P2's actions from step(), i.e.
+        opponent="self_play" / "remote").  It sees the same observation as the reference's `opponent(obs, info)`
+        callable (footsies.py:522-527), or its mirror image with mirror_opponent=True (then `policy` itself can be passed
+        again: one network plays both sides).  Its actions / log-probabilities are collected in actions_p2 / logp_p2."""
         if env.by_example:
             raise ValueError("the policy drives P1: create the env with by_example=False")
         if env.frame_delay:
             raise ValueError("RolloutCollector binds the env's outputs directly: frame_delay must be 0")
         self.env, self.policy, self.horizon = env, policy, int(horizon)
+        self.opponent_policy, self.mirror_opponent = opponent_policy, bool(mirror_opponent)
+        if opponent_policy is not None and (env._opponent_mode == "bot" or env.opponent is not None):
+            raise ValueError("opponent_policy needs an env whose P2 actions come from step(): opponent='self_play'")
         can_step = isinstance(policy, MLPPolicy) and policy.hidden in (32, 64, 128)
-        can_horizon = (can_step and env._opponent_mode == "bot" and env.autoreset and env._step_mask is None)
+        if opponent_policy is not None:
+            can_step = can_step and isinstance(opponent_policy, MLPPolicy) and opponent_policy.hidden == policy.hidden
+        can_horizon = (can_step and env.autoreset and env._step_mask is None
+                       and (env._opponent_mode == "bot" or opponent_policy is not None))
         if fused is None or fused is True:
             if fused and not can_step:
                 raise ValueError("fused=True needs an MLPPolicy with hidden in {32, 64, 128}")
@@ -100,6 +142,11 @@ class RolloutCollector:
         self.logp = torch.zeros((h, n), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((h, n), dtype=torch.float32, device=dev)
         self.dones = torch.zeros((h, n), dtype=torch.bool, device=dev)
+        self.actions_p2 = self.logp_p2 = None
+        if opponent_policy is not None:
+            self.actions_p2 = torch.zeros((h, n), dtype=torch.uint8, device=dev)
+            self.logp_p2 = torch.zeros((h, n), dtype=torch.float32, device=dev)
+            self._mirror_action = torch.tensor(_MIRROR_ACTION, dtype=torch.uint8, device=dev)
         self._seed = int(seed)
         self._drawn = torch.zeros(1, dtype=torch.int64, device=dev)   # policy steps taken so far (device side: graph replays bump it)
         self._graph = None
@@ -117,6 +164,13 @@ class RolloutCollector:
         ts = dict(scale=pol.scale, w1=l1.weight, b1=l1.bias, w2=l2.weight, b2=l2.bias, w3=l3.weight, b3=l3.bias,
                   counter_base=self._drawn, obs=self.obs, actions=self.actions, logp=self.logp, rewards=self.rewards,
                   dones=self.dones)
+        if self.opponent_policy is not None:
+            o = self.opponent_policy
+            m1, m2, m3 = o.net[0], o.net[2], o.net[4]
+            ts.update(p2_scale=o.scale, p2_w1=m1.weight, p2_b1=m1.bias, p2_w2=m2.weight, p2_b2=m2.bias, p2_w3=m3.weight,
+                      p2_b3=m3.bias, actions_p2=self.actions_p2, logp_p2=self.logp_p2)
+            r.p2_seed = (self._seed ^ _P2_SEED_SALT) & (2**64 - 1)
+            r.p2_mirror = int(self.mirror_opponent)
         for k, t in ts.items():
             if not t.is_contiguous() or t.device != env.device:
                 raise ValueError(f"fused rollout needs contiguous tensors on the env's device ({k})")
@@ -139,7 +193,19 @@ class RolloutCollector:
                 a = torch.multinomial(logp_all.exp(), 1).squeeze(1)
                 self.logp[t].copy_(logp_all.gather(1, a.unsqueeze(1)).squeeze(1))
                 self.actions[t].copy_(a)                            # int64 -> uint8 bitmask (Left 1 | Right 2 | Attack 4)
-            env.bind_actions(self.actions[t])
+            if self.opponent_policy is None:
+                env.bind_actions(self.actions[t])
+            else:
+                if self.mode == "step":
+                    self.opponent_policy.fused_sample_p2(self.obs[t], self.actions_p2[t], self.logp_p2[t],
+                                                         self._seed ^ _P2_SEED_SALT, t, self._drawn, self.mirror_opponent)
+                else:
+                    o = mirror_obs(self.obs[t]) if self.mirror_opponent else self.obs[t]
+                    logp_all = torch.log_softmax(self.opponent_policy(o), dim=-1)
+                    a = torch.multinomial(logp_all.exp(), 1).squeeze(1)
+                    self.logp_p2[t].copy_(logp_all.gather(1, a.unsqueeze(1)).squeeze(1))
+                    self.actions_p2[t].copy_(self._mirror_action[a] if self.mirror_opponent else a)
+                env.bind_actions(self.actions[t], self.actions_p2[t])
             env.bind_outputs(obs=self.obs[t + 1], reward=self.rewards[t], terminated=self.dones[t])
             env.step_bound()
         self._drawn.add_(h)
@@ -161,5 +227,8 @@ class RolloutCollector:
                 with torch.cuda.graph(self._graph):
                     self._one_horizon()
             self._graph.replay()
-        return {"obs": self.obs[:self.horizon], "actions": self.actions, "logp": self.logp, "rewards": self.rewards,
-                "dones": self.dones, "last_obs": self.obs[self.horizon]}
+        out = {"obs": self.obs[:self.horizon], "actions": self.actions, "logp": self.logp, "rewards": self.rewards,
+               "dones": self.dones, "last_obs": self.obs[self.horizon]}
+        if self.opponent_policy is not None:
+            out.update(actions_p2=self.actions_p2, logp_p2=self.logp_p2)
+        return out

@@ -201,13 +201,20 @@ int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *
                              const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
                              uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
                              float *obs_copy, void *stream);
+/* The same for a policy that drives P2: writes fg_buffers.actions_p2-style bitmasks; mirror = 1 feeds it the mirrored
+ * observation and mirrors its action back (see fg_rollout_buffers.p2_mirror). */
+int32_t fg_policy_mlp_sample_p2(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
+                                const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
+                                uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
+                                int32_t mirror, void *stream);
 const char *fg_policy_last_error(void);
 
 /* BASELINE.json configs[4] as ONE launch per horizon: for t = 0 .. horizon - 1 { policy(obs[t]) -> sample -> actions[t],
  * logp[t]; FootsiesEnv.step -> obs[t + 1], rewards[t], dones[t] } for every battle of the handle, with the battle state in
  * registers throughout (csrc/rollout_kernel.cu).  obs[0] is first overwritten with obs[horizon] (the observation the
  * previous horizon, or the reset, ended on).  Bit-identical to `horizon` rounds of fg_policy_mlp_sample(counter = t) +
- * fg_step.  Needs p1_bot = 0, p2_bot = 1, autoreset = 1, no step mask.  All pointers are DEVICE pointers. */
+ * fg_step (+ fg_policy_mlp_sample_p2 for a policy-driven P2).  Needs p1_bot = 0, autoreset = 1, no step mask.  All pointers
+ * are DEVICE pointers. */
 typedef struct {
     int32_t struct_size;
     int32_t hidden;                 /* 32, 64 or 128                                                           */
@@ -221,6 +228,16 @@ typedef struct {
     float *logp;                    /* [horizon][num_envs]                                                     */
     float *rewards;                 /* [horizon][num_envs]                                                     */
     uint8_t *dones;                 /* [horizon][num_envs]                                                     */
+    /* P2 driven by a second MLP policy (self-play rollouts; required when p2_bot = 0, ignored otherwise): it reads the
+     * same observation rows -- as the reference's `opponent(obs, info)` callable does, footsies.py:522-527 -- or, with
+     * p2_mirror = 1, their mirror image (per-player fields swapped, positions negated; the sampled Left / Right bits are
+     * mirrored back), so that one network can play both sides.  Same hidden size as P1's policy. */
+    const float *p2_scale, *p2_w1, *p2_b1, *p2_w2, *p2_b2, *p2_w3, *p2_b3;
+    uint64_t p2_seed;
+    uint8_t *actions_p2;            /* [horizon][num_envs]                                                     */
+    float *logp_p2;                 /* [horizon][num_envs]                                                     */
+    int32_t p2_mirror;
+    int32_t reserved1;
 } fg_rollout_buffers;
 int32_t fg_rollout_mlp(fg_handle *h, const fg_rollout_buffers *r, void *stream);
 

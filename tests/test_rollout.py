@@ -93,6 +93,60 @@ def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip, skip)
     assert launches[1] < launches[0] // 50                  # 1 launch per horizon instead of 1 per step (+ the policy's)
 
 
+@pytest.mark.parametrize("hidden,n,mirror,shared", [(64, 1000, False, False), (64, 777, True, True), (32, 130, True, False),
+                                                    (128, 200, False, False)])
+def test_self_play_rollout_with_a_policy_for_p2(hidden, n, mirror, shared):
+    """P2 driven by a second MLP policy (optionally on the mirrored observation, optionally the same network): the
+    whole-horizon kernel equals the per-step path (fg_policy_mlp_sample + fg_policy_mlp_sample_p2 + fg_step) bit for bit,
+    P2's log-probabilities equal torch's for the (mirrored) observation, and the collected actions replay."""
+    from footsies_gym_b200 import FootsiesEnv
+    from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector, mirror_obs, _MIRROR_ACTION
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(hidden + n)
+    p1 = MLPPolicy(hidden).to(dev)
+    p2 = p1 if shared else MLPPolicy(hidden).to(dev)
+    with torch.no_grad():
+        for prm in list(p1.net.parameters()) + ([] if shared else list(p2.net.parameters())):
+            prm.mul_(2.0)
+    horizon = 130
+    envs, cols = [], []
+    for mode in ("step", "horizon"):
+        env = FootsiesEnv(num_envs=n, device=dev, seed=3, opponent="self_play")
+        envs.append(env)
+        cols.append(RolloutCollector(env, p1, horizon=horizon, use_cuda_graph=False, fused=mode, seed=17, opponent_policy=p2,
+                                     mirror_opponent=mirror))
+    assert [c.mode for c in cols] == ["step", "horizon"]
+    keys = ("obs", "actions", "logp", "rewards", "dones", "last_obs", "actions_p2", "logp_p2")
+    for r in range(2):
+        before = envs[0].get_state()
+        outs = [c.collect() for c in cols]
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(outs[0][k], outs[1][k]), (r, k)
+        assert envs[0].get_state().tobytes() == envs[1].get_state().tobytes(), r
+        assert envs[0].episode_stats() == envs[1].episode_stats(), r
+    out = outs[1]
+    assert out["dones"].any() and len(torch.unique(out["actions_p2"])) > 4
+    # P2's log-probability is torch's log-softmax of its policy on the observation it was shown, at the action it chose
+    mir = torch.tensor(_MIRROR_ACTION, device=dev)
+    with torch.no_grad():
+        for t in (0, horizon // 2, horizon - 1):
+            o = mirror_obs(out["obs"][t]) if mirror else out["obs"][t]
+            ref = torch.log_softmax(p2(o), dim=-1)
+            chosen = mir[out["actions_p2"][t].long()] if mirror else out["actions_p2"][t].long()   # un-mirror: the policy's own pick
+            assert float((ref.gather(1, chosen.unsqueeze(1)).squeeze(1) - out["logp_p2"][t]).abs().max()) < 2e-5
+    # replay of the last horizon's actions from the state it started in
+    twin = FootsiesEnv(num_envs=n, device=dev, seed=3, opponent="self_play")
+    twin.reset()
+    twin.set_state(before)
+    for t in range(horizon):
+        twin.step(out["actions"][t], out["actions_p2"][t])
+        assert torch.equal(twin.reward, out["rewards"][t]) and torch.equal(twin.terminated, out["dones"][t]), t
+    assert torch.equal(twin.obs, out["last_obs"])
+
+
 def test_horizon_kernel_rejects_other_configurations():
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
