@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """PPO against the in-game bot, entirely on the GPU (BASELINE.json configs[4] in use).
 
-    python examples/ppo_footsies.py [--envs 16384] [--horizon 128] [--iters 40] [--frame-skip 1]
+    python examples/ppo_footsies.py [--envs 16384] [--horizon 128] [--iters 40] [--frame-skip 1] [--self-play]
     torchrun --nproc-per-node 8 examples/ppo_footsies.py          # one process per GPU, gradients all-reduced
 
 Rollouts come from footsies_gym_b200.rollout.RolloutCollector: the fused policy kernel samples actions from the
@@ -9,6 +9,8 @@ observation tensor the step kernel wrote, the step kernel writes the next observ
 into the rollout buffers, one launch per horizon (fg_rollout_mlp keeps the battles in registers for all 128 steps).  The update is ordinary torch (clipped PPO with GAE, a
 separate value MLP); the policy's parameters are updated in place, so the next rollout reads the new weights.
 Prints the win rate against the bot per iteration (from the kernel's own episode statistics).
+With --self-play the training rollouts are played against the same network on the mirrored observation (still one
+launch per horizon) and the win rate against the in-game bot comes from a separate evaluation rollout per iteration.
 """
 import argparse
 import os
@@ -37,6 +39,7 @@ def main():
     ap.add_argument("--lam", type=float, default=0.95)
     ap.add_argument("--clip", type=float, default=0.2)
     ap.add_argument("--entropy", type=float, default=0.01)
+    ap.add_argument("--self-play", action="store_true", help="train against the same network playing the mirrored side")
     a = ap.parse_args()
 
     rank, local_rank, world = env_rank_world()
@@ -46,7 +49,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
 
-    env = make_sharded_env(a.envs * world, frame_skip=a.frame_skip, seed=0)
+    env = make_sharded_env(a.envs * world, frame_skip=a.frame_skip, seed=0, opponent="self_play" if a.self_play else None)
     policy = MLPPolicy(64).to(dev)
     value = torch.nn.Sequential(torch.nn.Linear(8, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
                                 torch.nn.Linear(64, 1)).to(dev)
@@ -55,9 +58,15 @@ def main():
         for p in params:
             dist.broadcast(p.data, 0)
     opt = torch.optim.Adam(params, lr=a.lr)
-    col = RolloutCollector(env, policy, horizon=a.horizon, use_cuda_graph=True, seed=rank)
+    col = RolloutCollector(env, policy, horizon=a.horizon, use_cuda_graph=True, seed=rank,
+                           opponent_policy=policy if a.self_play else None, mirror_opponent=a.self_play)
+    eval_env = eval_col = None
+    if a.self_play:                       # the yardstick stays the in-game bot
+        eval_env = make_sharded_env(a.envs * world, frame_skip=a.frame_skip, seed=1)
+        eval_col = RolloutCollector(eval_env, policy, horizon=a.horizon, seed=1000 + rank)
     n, h = env.num_envs, a.horizon
-    prev = env.episode_stats()
+    stat_env = eval_env if a.self_play else env
+    prev = stat_env.episode_stats()
     t_roll = t_upd = 0.0
     for it in range(a.iters):
         t0 = time.perf_counter()
@@ -103,10 +112,17 @@ def main():
         t2 = time.perf_counter()
         t_roll += t1 - t0
         t_upd += t2 - t1
-        st = env.all_reduce_stats()
+        frames = env.episode_stats()["env_frames"] - (0 if it == 0 else frames_seen)
+        frames_seen = env.episode_stats()["env_frames"]
+        if world > 1:
+            ft = torch.tensor([frames], dtype=torch.int64, device=dev)
+            dist.all_reduce(ft)
+            frames = int(ft.item())
+        if a.self_play:
+            eval_col.collect()
+        st = stat_env.all_reduce_stats()
         ep = st["episodes"] - prev["episodes"]
         wins = st["p1_wins"] - prev["p1_wins"]
-        frames = st["env_frames"] - prev["env_frames"]
         prev = st
         if rank == 0:
             print(f"iter {it:3d}  episodes {ep:8d}  win rate vs bot {wins / max(ep, 1):.3f}  mean reward/step {float(rew.mean()):+.4f}  "
