@@ -37,7 +37,7 @@ struct RolloutSmem {
     static constexpr size_t kBytes = kStats + sizeof(unsigned long long) * FG_STAT_COUNT;
 };
 
-template <int H, int E, int W, bool DENSE, bool P2POL>
+template <int H, int E, int W, bool DENSE, bool P2POL, bool SKIP>
 __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp) {
     using SM = RolloutSmem<H, E, W, P2POL>;
     using PL = typename SM::PL;
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
                     }
                 }
             }
-            if (p.skip_unactionable) {
-                // fused FootsiesFrameSkipped, exactly as in step_kernel: warp-synchronous so that the statistics fold
+            if (SKIP) {
+                // fused FootsiesFrameSkipped (fg_config.skip_unactionable), exactly as in step_kernel: warp-synchronous so that the statistics fold
                 // stays a warp-uniform decision
                 bool more = ran && !terminal && obs_is_skippable(e);
                 while (__any_sync(kFull, more)) {
@@ -186,21 +186,25 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
     if (tid < FG_STAT_COUNT && s_stats[tid]) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
-template <int H, int E, int W, bool DENSE, bool P2POL>
-static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
+template <int H, int E, int W, bool DENSE, bool P2POL, bool SKIP>
+static cudaError_t launch_rollout_s(cudaStream_t s, const RolloutParams &rp) {
     constexpr size_t bytes = RolloutSmem<H, E, W, P2POL>::kBytes;
     static bool configured[64] = {};                    // per device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE, P2POL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE, P2POL, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
     constexpr int kEnvs = RolloutSmem<H, E, W, P2POL>::kEnvs;
     const int grid = (rp.sim.n + kEnvs - 1) / kEnvs;
-    rollout_kernel<H, E, W, DENSE, P2POL><<<grid, 32 * W, bytes, s>>>(rp);
+    rollout_kernel<H, E, W, DENSE, P2POL, SKIP><<<grid, 32 * W, bytes, s>>>(rp);
     return cudaSuccess;
+}
+template <int H, int E, int W, bool DENSE, bool P2POL>
+static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
+    return rp.sim.skip_unactionable ? launch_rollout_s<H, E, W, DENSE, P2POL, true>(s, rp) : launch_rollout_s<H, E, W, DENSE, P2POL, false>(s, rp);
 }
 
 template <int H, bool DENSE>
