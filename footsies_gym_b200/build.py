@@ -55,7 +55,11 @@ def translation_units():
     # other expression is contracted in one and not in the other: their logits and log-probabilities are bit-identical.
     units = [("abi.o", os.path.join(CSRC, "footsies_kernels.cu"), []),
              ("policy.o", os.path.join(CSRC, "policy_kernel.cu"), []),
-             ("rollout.o", os.path.join(CSRC, "rollout_kernel.cu"), [])]
+             ("rollout.o", os.path.join(CSRC, "rollout_kernel.cu"), [])]           # the dispatcher
+    for hidden in (32, 64, 128):
+        for dense in (0, 1):
+            units.append((f"rollout_h{hidden}_d{dense}.o", os.path.join(CSRC, "rollout_kernel.cu"),
+                          [f"-DFG_ROLLOUT_H={hidden}", f"-DFG_ROLLOUT_DENSE={dense}"]))
     for kf in (0, 1):
         for b1 in (0, 1):
             for b2 in (0, 1):

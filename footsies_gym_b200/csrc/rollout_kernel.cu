@@ -219,13 +219,23 @@ static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
     return e == 4 ? launch_rollout_v<H, E4, kPolicyWarps, DENSE, false>(s, rp) : launch_rollout_v<H, 2, kPolicyWarps, DENSE, false>(s, rp);
 }
 
+// One translation unit per hidden size and reward mode (build.py compiles this file with -DFG_ROLLOUT_H=.. -DFG_ROLLOUT_DENSE=..
+// so that the kernels compile in parallel) plus one without the defines that holds the dispatcher.
+#define FG_ROLLOUT_DECL(H, D) cudaError_t launch_rollout_##H##_##D(cudaStream_t s, const RolloutParams &rp)
+FG_ROLLOUT_DECL(32, 0); FG_ROLLOUT_DECL(32, 1); FG_ROLLOUT_DECL(64, 0); FG_ROLLOUT_DECL(64, 1); FG_ROLLOUT_DECL(128, 0); FG_ROLLOUT_DECL(128, 1);
+#ifdef FG_ROLLOUT_H
+#define FG_ROLLOUT_DEF2(H, D) FG_ROLLOUT_DECL(H, D) { return launch_rollout_h<H, (D != 0)>(s, rp); }
+#define FG_ROLLOUT_DEF(H, D) FG_ROLLOUT_DEF2(H, D)
+FG_ROLLOUT_DEF(FG_ROLLOUT_H, FG_ROLLOUT_DENSE)
+#else
 cudaError_t launch_rollout(bool dense, cudaStream_t s, const RolloutParams &rp) {
     switch (rp.hidden) {
-    case 32: return dense ? launch_rollout_h<32, true>(s, rp) : launch_rollout_h<32, false>(s, rp);
-    case 64: return dense ? launch_rollout_h<64, true>(s, rp) : launch_rollout_h<64, false>(s, rp);
-    case 128: return dense ? launch_rollout_h<128, true>(s, rp) : launch_rollout_h<128, false>(s, rp);
+    case 32: return dense ? launch_rollout_32_1(s, rp) : launch_rollout_32_0(s, rp);
+    case 64: return dense ? launch_rollout_64_1(s, rp) : launch_rollout_64_0(s, rp);
+    case 128: return dense ? launch_rollout_128_1(s, rp) : launch_rollout_128_0(s, rp);
     default: return cudaErrorInvalidValue;
     }
 }
+#endif
 
 }  // namespace fgk
