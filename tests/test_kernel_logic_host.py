@@ -27,9 +27,11 @@ def test_fused_frame_skip_host_logic(oracle, k, p2_bot):
     pc.case_fused_frame_skip(make_env, oracle, k, p2_bot, scale=0.0625)
 
 
-@pytest.mark.parametrize("frame_skip,p2_bot", [(1, True), (3, True), (1, False)])
-def test_frame_skipped_fusion_host_logic(frame_skip, p2_bot):
-    pc.frame_skipped_fused_vs_masked_loop(make_env, frame_skip, p2_bot, n=120, steps=250)
+@pytest.mark.parametrize("frame_skip,p2_bot,dense,autoreset", [(1, True, True, True), (3, True, True, True),
+                                                               (1, False, True, True), (2, True, False, True),
+                                                               (1, True, True, False)])
+def test_frame_skipped_fusion_host_logic(frame_skip, p2_bot, dense, autoreset):
+    pc.frame_skipped_fused_vs_masked_loop(make_env, frame_skip, p2_bot, n=120, steps=250, dense=dense, autoreset=autoreset)
 
 
 def test_masked_reset_and_state_round_trip_host_logic(oracle):
