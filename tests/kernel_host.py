@@ -125,3 +125,52 @@ class HostKernelEnv:
         if self.h:
             lib().he_destroy(self.h)
             self.h = None
+
+
+class HostKernelTorchEnv:
+    """HostKernelEnv behind the FootsiesEnv surface the wrappers use (reset / step returning the observation dicts,
+    set_step_mask, set_skip_unactionable), so that the batched wrappers -- including the fused FootsiesFrameSkipped path,
+    which lives in the frame logic -- replay the reference wrappers' golden vectors without a GPU."""
+    is_base_footsies_env = True
+    opponent = None
+    by_example = False
+    frame_delay = 0
+
+    def __init__(self, num_envs=1, dense_reward=True, autoreset=False, seed=0):
+        from footsies_gym_b200.env import FootsiesEnv
+        from footsies_gym_b200.moves import FootsiesMove
+        from footsies_gym_b200.spaces import footsies_action_space, footsies_observation_space
+        self.k = HostKernelEnv(num_envs=num_envs, dense_reward=dense_reward, autoreset=autoreset, seed=seed)
+        self.num_envs, self.device = num_envs, torch.device("cpu")
+        relevant = [m for m in FootsiesMove if m.name not in ("WIN", "DEAD")]
+        self.observation_space = footsies_observation_space(len(relevant), max(m.value.duration for m in relevant))
+        self.action_space = footsies_action_space()
+        self.obs, self.reward, self.info_frame = self.k.obs, self.k.reward, self.k.info_frame
+        self.truncated = torch.zeros(num_envs, dtype=torch.bool)
+        self._obs_dict = FootsiesEnv._make_obs_dict(self.obs)
+
+    @property
+    def terminated(self):
+        return self.k.terminated.bool()
+
+    def _out(self):
+        return self._obs_dict, {"frame": self.info_frame, **self._obs_dict}
+
+    def reset(self, *, seed=None, options=None):
+        self.k.reset(seed=seed, options=options)
+        return self._out()
+
+    def set_step_mask(self, mask):
+        self.k.set_step_mask(None if mask is None else mask.numpy())
+
+    def set_skip_unactionable(self, flag):
+        self.k.set_skip_unactionable(flag)
+
+    def step(self, action):
+        from footsies_gym_b200.env import _as_bitmask
+        self.k.step(_as_bitmask(action, self.num_envs, "cpu").numpy())
+        obs, info = self._out()
+        return obs, self.reward, self.terminated, self.truncated, info
+
+    def close(self):
+        self.k.close()

@@ -72,6 +72,18 @@ def test_wrappers_on_cpu_stand_in(oracle, path):
     assert replay(path, OracleTorchEnv(num_envs=1, autoreset=False, seed=0)) > 1000
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[13:-4] for p in GOLDEN])
+def test_wrappers_on_host_compiled_kernel_logic(path):
+    """The same goldens through the device frame logic compiled for the host: FootsiesFrameSkipped takes its fused path
+    there (the skip loop of step_kernel, mirrored by tests/host_emulation), so the reference wrapper's own outputs pin it."""
+    from kernel_host import HostKernelTorchEnv
+    from footsies_gym_b200.wrappers import FootsiesFrameSkipped
+    base = HostKernelTorchEnv(num_envs=1, autoreset=False, seed=0)
+    assert FootsiesFrameSkipped(base).fused
+    base.set_skip_unactionable(False)
+    assert replay(path, base) > 1000
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[13:-4] for p in GOLDEN])
 def test_wrappers_on_gpu(path):
