@@ -147,6 +147,34 @@ def test_self_play_rollout_with_a_policy_for_p2(hidden, n, mirror, shared):
     assert torch.equal(twin.obs, out["last_obs"])
 
 
+def test_self_play_rollout_with_torch_policies_is_replayable():
+    """The torch-op path (any callable policy) with an opponent policy on the mirrored observation: the collected actions
+    replay into a fresh self-play env."""
+    from footsies_gym_b200 import FootsiesEnv
+    from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    n, horizon = 300, 90
+    pol = MLPPolicy(64).to(dev)
+    env = FootsiesEnv(num_envs=n, device=dev, seed=3, opponent="self_play")
+    col = RolloutCollector(env, pol, horizon=horizon, use_cuda_graph=False, fused=False, opponent_policy=pol, mirror_opponent=True)
+    assert col.mode == "torch"
+    before = env.get_state()
+    out = col.collect()
+    assert int(out["actions_p2"].max()) <= 7 and len(torch.unique(out["actions_p2"])) > 4
+    twin = FootsiesEnv(num_envs=n, device=dev, seed=3, opponent="self_play")
+    twin.reset()
+    twin.set_state(before)
+    for t in range(horizon):
+        if t > 0:
+            assert torch.equal(twin.obs, out["obs"][t]), t
+        twin.step(out["actions"][t], out["actions_p2"][t])
+        assert torch.equal(twin.reward, out["rewards"][t]) and torch.equal(twin.terminated, out["dones"][t]), t
+    assert torch.equal(twin.obs, out["last_obs"])
+
+
 def test_horizon_kernel_rejects_other_configurations():
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
