@@ -12,6 +12,22 @@ f32 = np.float32
 DT = f32(0.02)
 
 
+@pytest.fixture(params=["oracle", "reference_transliteration"])
+def oracle(request):
+    """Every known answer is asked of BOTH checkers: the hand-written restatement (oracle/) and the reference's own C#
+    transliterated by tools/cs2cpp.py (oracle/_ref/) -- a known answer derived from a misreading of the C# fails the second."""
+    import oracle_binding
+    if request.param == "oracle":
+        oracle_binding.build()
+        return oracle_binding
+    import types
+    import ref_binding
+    if not ref_binding.available():
+        pytest.skip("oracle/_ref not built and /root/reference not present")
+    ref_binding.build()
+    return types.SimpleNamespace(OracleBatch=ref_binding.RefBatch)
+
+
 def make(oracle, n=1, **kw):
     kw.setdefault("p2_bot", False)
     kw.setdefault("autoreset", False)
@@ -309,7 +325,8 @@ def test_proximity_guard(oracle):
     b = make(oracle)
     place(b, -1.5, 1.5)                           # distance 3.0: prox box reaches x+3.0, base hurtbox half 0.75
     tr = run(b, [A] + [0] * 10, [R] * 11)
-    assert tr[0]["events"] >> 7 & 1              # P2 notified on the first frame
+    if hasattr(oracle, "lib"):                    # the notification itself is instrumentation of the hand-written oracle;
+        assert tr[0]["events"] >> 7 & 1          # the transliterated engine shows only its effect (next line)
     assert tr[0]["f"]["is_reserve_prox"][1] == 1
     assert tr[1]["f"]["action_id"][1] == 350
     x = tr[1]["f"]["pos_x"][1]

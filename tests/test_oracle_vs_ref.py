@@ -1,0 +1,174 @@
+"""The CPU oracle (oracle/footsies_oracle.c, the hand-written restatement every GPU parity test is judged by) against
+the REFERENCE'S OWN battle code: /root/reference/Assets/Script/*.cs transliterated mechanically by tools/cs2cpp.py and
+compiled into oracle/_ref/libfootsies_ref.so (oracle/Makefile.ref; harness oracle/ref_shim/ref_harness.cpp).
+
+Every tape of tests/parity_cases.py -- the same seeded action sequences the CUDA path replays on the B200 -- goes through
+both engines; after reset and after every step EVERY field of the trace must be byte-identical: fighter state incl. the
+Left / Right history and the Attack run length read from the real 180-entry arrays, frame counter, recorded inputs,
+hit / block / guard-break events, battle_over, the xorshift128 state and draw count, the bots' held inputs, observation,
+info, reward (float64 and float32), termination.  Bar: bit-exact, floats compared as bytes (0 ulp).
+
+This is the pin SURVEY.md section 8(c) asks for: a shared misreading of the C# between the oracle and the known-answer
+tests can no longer pass, because the second engine is the C# text itself.  What stays unpinned is only what is NOT in
+/root/reference (closed-source UnityEngine.Random / Rect / Time and Mono's fp32 evaluation), restated in
+oracle/ref_shim/unity_shim.h and stated as such in DESIGN.md."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+import parity_cases as pc
+import ref_binding as rb
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref not built and /root/reference not present")
+
+EVENT_MASK = 0x3F      # bits 6-7 (proximity notification) are instrumentation inside the hand-written oracle only
+
+
+def assert_traces_equal(o, r, where):
+    for name in ob.TRACE_DTYPE.names:
+        a, b = o[name], r[name]
+        if name == "events":
+            a, b = a & EVENT_MASK, b & EVENT_MASK
+        if a.tobytes() == b.tobytes():
+            continue
+        if a.dtype.names:
+            for f in a.dtype.names:
+                if a[f].tobytes() != b[f].tobytes():
+                    i = tuple(np.argwhere(a[f] != b[f])[0])
+                    raise AssertionError(f"[{where}] f.{f} differs at (env, player) {i}: oracle={a[f][i]!r} reference={b[f][i]!r}")
+        i = tuple(np.argwhere(a != b)[0])
+        raise AssertionError(f"[{where}] {name} differs at {i}: oracle={a[i]!r} reference={b[i]!r}")
+
+
+def run_pair(make_env, oracle, n, steps, *, p1_bot=False, p2_bot=True, dense=True, frame_skip=1, autoreset=True, stale=True,
+             seed=0, tape1=None, tape2=None, first_env_index=0, check_every=1, frame_delay=0):
+    """Drop-in for parity_cases.run_case: same tapes, but the two implementations under comparison are the two CPU engines."""
+    kw = dict(p1_bot=p1_bot, p2_bot=p2_bot, dense_reward=dense, autoreset=autoreset, stale_intro_input=stale,
+              first_env_index=first_env_index, seed=seed, threads=8, frame_delay=frame_delay)
+    o, r = ob.OracleBatch(n, **kw), rb.RefBatch(n, **kw)
+    o.reset()
+    r.reset()
+    assert_traces_equal(o.trace, r.trace, "reset")
+    zero = np.zeros(n, np.uint8)
+    for t in range(steps):
+        a1 = zero if p1_bot else tape1[t]
+        a2 = None if p2_bot else tape2[t]
+        o.step(a1, a2, repeat=frame_skip)
+        r.step(a1, a2, repeat=frame_skip)
+        assert_traces_equal(o.trace, r.trace, f"step {t}")
+    so, sr = o.stats(), r.stats()
+    assert so == sr, (so, sr)
+    assert o.frames_simulated() == r.frames_simulated()
+    st = dict(so)
+    st["episode_frames"] = st.pop("frames")
+    return st
+
+
+CASES = [name for name in dir(pc) if name.startswith("case_") and name != "case_fused_frame_skip"]
+
+
+# FOUND BY THIS TEST (round 2): by_example launches the game with --p1-bot --p1-spectator, and the spectator wrapper makes
+# `actorP1 is TrainingBattleAIActor` false (BattleCore.cs:274), so P1's BattleAI is never Reset() at a round start.  The
+# oracle (and the kernel) reset it.  Being fixed in oracle + kernel; strict xfail so that the fix has to remove this.
+KNOWN_OPEN = {"case_both_bots_by_example", "case_p1_bot_vs_remote_p2"}
+
+
+@pytest.mark.parametrize("name", [pytest.param(c, marks=pytest.mark.xfail(strict=True)) if c in KNOWN_OPEN else c
+                                  for c in CASES], ids=[c[5:] for c in CASES])
+def test_every_parity_tape_oracle_equals_transliterated_reference(monkeypatch, name):
+    monkeypatch.setattr(pc, "run_case", run_pair)
+    # config B (the trace bit-exactness gate) at 512 battles x 2048 frames; the others at 1/16 of their GPU size
+    getattr(pc, name)(None, None, scale=0.125 if name.startswith("case_config_b") else 0.0625)
+
+
+@pytest.mark.parametrize("k,p2_bot", pc.FUSED_PARAMS)
+def test_frame_skip_tapes_oracle_equals_transliterated_reference(monkeypatch, k, p2_bot):
+    monkeypatch.setattr(pc, "run_case", run_pair)
+    pc.case_fused_frame_skip(None, None, k, p2_bot, scale=0.03125)
+
+
+@pytest.mark.parametrize("frame_delay,dense", [(3, True), (1, False)])
+def test_frame_delay_queue(frame_delay, dense):
+    rng = np.random.default_rng(17)
+    n, steps = 96, 900
+    run_pair(None, None, n, steps, dense=dense, frame_delay=frame_delay, tape1=pc.tape_sticky(rng, steps, n), seed=5)
+
+
+def test_masked_hard_reset_and_reseed_mid_episode():
+    """RESET command in the middle of an episode (BattleCore.cs:143-146) and SEED (:170-173) on a subset of the battles."""
+    rng = np.random.default_rng(8)
+    n = 128
+    kw = dict(p2_bot=True, seed=1, threads=8)
+    o, r = ob.OracleBatch(n, **kw), rb.RefBatch(n, **kw)
+    o.reset()
+    r.reset()
+    for t in range(700):
+        a = rng.integers(0, 8, size=n, dtype=np.uint8)
+        o.step(a)
+        r.step(a)
+        if t % 50 == 25:
+            mask = rng.random(n) < 0.3
+            for b in (o, r):
+                b.seed(1000 + t, mask)
+                b.reset(mask)
+        assert_traces_equal(o.trace, r.trace, f"step {t}")
+
+
+def test_bot_decisions_on_injected_draw_tapes():
+    """The bot's decision tree on a chosen draw sequence (tests of BattleAI.SelectMovement / SelectAttack branches that a
+    seeded stream visits rarely): both engines consume the same raw 32-bit draws."""
+    rng = np.random.default_rng(99)
+    n, steps = 64, 1200
+    kw = dict(p1_bot=False, p2_bot=True, seed=0, threads=1)
+    o, r = ob.OracleBatch(n, **kw), rb.RefBatch(n, **kw)
+    for e in range(n):
+        raw = rng.integers(0, 2 ** 32, size=4000, dtype=np.uint64).astype(np.uint32)
+        o.set_rng_tape(e, raw)
+        r.set_rng_tape(e, raw)
+    o.reset()
+    r.reset()
+    tape = pc.tape_sticky(rng, steps, n)
+    for t in range(steps):
+        o.step(tape[t])
+        r.step(tape[t])
+        assert_traces_equal(o.trace[["f", "frame", "bot_input", "rng_draws", "obs", "reward", "terminated"]],
+                            r.trace[["f", "frame", "bot_input", "rng_draws", "obs", "reward", "terminated"]], f"step {t}") \
+            if False else None
+        for name in ("f", "frame", "bot_input", "rng_draws", "obs", "reward", "terminated"):
+            assert o.trace[name].tobytes() == r.trace[name].tobytes(), (t, name)
+
+
+def test_save_load_battle_state_through_the_games_own_commands():
+    """STATE_SAVE / STATE_LOAD (BattleCore.SaveState / LoadState, Fighter.SaveState / LoadState, FighterState ctor --
+    all transliterated): saved states are identical, and a state saved by one engine continues identically in the other."""
+    rng = np.random.default_rng(23)
+    n, steps = 48, 400
+    kw = dict(p2_bot=False, seed=0, threads=1)
+    o, r = ob.OracleBatch(n, **kw), rb.RefBatch(n, **kw)
+    o.reset()
+    r.reset()
+    t1, t2 = pc.tape_sticky(rng, steps, n), pc.tape_sticky(rng, steps, n)
+    saved = {}
+    for t in range(steps):
+        o.step(t1[t], t2[t])
+        r.step(t1[t], t2[t])
+        if t % 37 == 5:
+            for e in range(0, n, 5):
+                so, sr = o.save_battle_state(e), r.save_battle_state(e)
+                so.pop("roundStartTime"), sr.pop("roundStartTime")      # wall-clock bookkeeping, not battle state
+                assert so == sr, (t, e)
+                if not (o.trace["terminated"][e] or e in saved):
+                    saved[e] = (t, r.save_battle_state(e))
+    # cross-load: what the reference engine saved goes into the oracle (and back into the reference), then both continue
+    assert len(saved) >= 5
+    for e, (t, state) in saved.items():
+        if o.trace["terminated"][e]:
+            continue
+        o.load_battle_state(e, state)
+        r.load_battle_state(e, state)
+    for t in range(200):
+        a1, a2 = t1[t], t2[t]
+        o.step(a1, a2)
+        r.step(a1, a2)
+        for name in ("f", "frame", "obs", "terminated", "battle_over"):
+            assert o.trace[name].tobytes() == r.trace[name].tobytes(), (t, name)
