@@ -58,7 +58,7 @@ class FgFighterState(C.Structure):
 class FgEnvState(C.Structure):
     _fields_ = [("f", FgFighterState * 2), ("frame", C.c_int32), ("recorded_input", C.c_int32 * 2),
                 ("done", C.c_int32), ("cum_reward_index", C.c_int32), ("actor_input", C.c_int32 * 2),
-                ("rng_state", C.c_uint32 * 4), ("bot_queue", C.c_uint32 * 2)]
+                ("rng_state", C.c_uint32 * 4), ("bot_queue", C.c_uint32 * 2), ("p1_bot_memory", C.c_int32)]
 
 
 # numpy view of FgEnvState (same memory layout)
@@ -67,7 +67,7 @@ def env_state_dtype():
     fighter = np.dtype([(n, {C.c_float: "<f4", C.c_int32: "<i4", C.c_uint32: "<u4"}[t]) for n, t in FgFighterState._fields_])
     dt = np.dtype([("f", fighter, (2,)), ("frame", "<i4"), ("recorded_input", "<i4", (2,)), ("done", "<i4"),
                    ("cum_reward_index", "<i4"), ("actor_input", "<i4", (2,)), ("rng_state", "<u4", (4,)),
-                   ("bot_queue", "<u4", (2,))])
+                   ("bot_queue", "<u4", (2,)), ("p1_bot_memory", "<i4")])
     assert dt.itemsize == C.sizeof(FgEnvState), (dt.itemsize, C.sizeof(FgEnvState))
     return dt
 

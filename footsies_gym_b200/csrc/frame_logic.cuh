@@ -314,6 +314,14 @@ FG_DEV uint32_t attack_apply(uint32_t result, uint32_t &apk, uint32_t &vpk, cons
     return 0u;
 }
 
+// Distance bucket index of bot_next (0..5): ceil(clamp(2 * dist, 4, 9)) - 4; bot_dist_of_index is a distance with that index.
+FG_DEV uint32_t bot_dist_index(float dist) {
+    float t2 = dist * 2.0f;
+    t2 = t2 < 4.0f ? 4.0f : t2 > 9.0f ? 9.0f : t2;
+    return (uint32_t)((int)ceilf(t2) - 4);
+}
+FG_DEV float bot_dist_of_index(uint32_t idx) { return 0.5f * (float)(idx + 4u); }
+
 // BattleAI.getNextAIInput (BattleAI.cs:41-66) on pattern-position + remaining-count queues.  `dist` and `opp_act`
 // are the state captured by the PREVIOUS call (the ascending shift loop at BattleAI.cs:358-361 makes fightStates[5]
 // exactly that).  r % n for 2 <= n <= 7 without a division: floor(r / n) == umul64hi(r, floor(2^64 / n) + 1).
@@ -334,9 +342,7 @@ FG_DEV uint32_t bot_next(const Tables &T, Env &e, uint32_t &q, float dist, uint3
     if (!(have_m && have_a)) {                                          // an empty queue is refilled and contributes 0 (BattleAI.cs:50-62)
         // distance buckets > 4, > 3, > 2.5, > 2, else (BattleAI.cs:70-124): 2 * dist is exact, ceil() turns the
         // strict comparisons into a table index
-        float t2 = dist * 2.0f;
-        t2 = t2 < 4.0f ? 4.0f : t2 > 9.0f ? 9.0f : t2;
-        const BotRow &b = T.bot[T.bucket_of[(int)ceilf(t2) - 4]];
+        const BotRow &b = T.bot[T.bucket_of[bot_dist_index(dist)]];
         if (!have_m) {                                                  // SelectMovement (BattleAI.cs:68-126)
             const uint32_t r = rng_next(e);
             const uint32_t k = r - umulhi64(r, b.magic_m) * b.n_m;      // Random.Range(0, n)
@@ -363,11 +369,25 @@ FG_DEV uint32_t bot_next(const Tables &T, Env &e, uint32_t &q, float dist, uint3
 // Stop -> Intro -> one Intro frame -> Fight (BattleCore.cs:176-200, 262-291, 329-345) for one env.
 // What survives from the previous round (SetupBattleStart, Fighter.cs:120-135, does not touch them): the actors'
 // held inputs (replayed by the Intro frame), hit stun, isInputBackward / isReserveProximityGuard.
+// P1's bot (by_example) survives too: the game is launched with --p1-bot --p1-spectator (footsies.py:230-232), the bot
+// actor is wrapped in a TrainingActorRemoteSpectator (GameManager.cs:200-201), and `actorP1 is TrainingBattleAIActor`
+// (BattleCore.cs:274) is false for the wrapper -- BattleAI.Reset() is only ever called for P2's bot.  P1's bot therefore
+// keeps its queues, decides its first input of the new round on the FightState it recorded last (before the terminal
+// frame, or the current state on a RESET in mid-round), and its very first query (fightStates still null,
+// BattleAI.cs:30,47) returns 0 without drawing.  Found and pinned by tests/test_oracle_vs_ref.py.
 template <bool P1BOT, bool P2BOT>
 FG_DEV void reset_env(const Tables &T, Env &e, bool stale_intro) {
     const bool was_done = (e.misc >> FGM_DONE_SHIFT) & 1u;
     uint32_t a1 = (e.misc >> FGM_ACTOR1_SHIFT) & 7u, a2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
     if (!stale_intro) { a1 = 0u; a2 = 0u; }
+    float p1_dist = 0.0f;
+    uint32_t p1_opp = 0u;
+    bool p1_called = false;
+    if (P1BOT) {
+        p1_called = (e.misc >> FGM_P1CALLED_SHIFT) & 1u;
+        p1_dist = was_done ? bot_dist_of_index((e.misc >> FGM_P1MEM_SHIFT) & 7u) : fabsf(e.pos2 - e.pos1);
+        p1_opp = was_done ? (e.misc >> (FGM_P1MEM_SHIFT + 3)) & 31u : (e.pk2 >> FGP_ACT_SHIFT) & 31u;
+    }
     uint32_t pk[2] = { e.pk1, e.pk2 };
     uint32_t npk[2];
 #pragma unroll
@@ -392,11 +412,13 @@ FG_DEV void reset_env(const Tables &T, Env &e, bool stale_intro) {
     e.hist1 = (T.dash_fsm[0][a1 & 3u] & 255u) | ((a1 >> 2) & 1u) << FGH_ARUN_SHIFT;
     e.hist2 = (T.dash_fsm[0][a2 & 3u] & 255u) | ((a2 >> 2) & 1u) << FGH_ARUN_SHIFT;
     e.frame = -1;
-    e.bq1 = 0u; e.bq2 = 0u;                                            // BattleAI.Reset (BattleAI.cs:393-403)
-    // first bot query at the Fight transition (BattleCore.cs:289): decision input = round-start state
-    if (P1BOT) a1 = bot_next<0>(T, e, e.bq1, 4.0f, STAND);
+    e.bq2 = 0u;                                                        // BattleAI.Reset (BattleAI.cs:393-403): P2's bot only
+    if (!P1BOT) e.bq1 = 0u;
+    // first bot query at the Fight transition (BattleCore.cs:289), P1 first: P2's decision input is the round-start state
+    if (P1BOT) a1 = p1_called ? bot_next<0>(T, e, e.bq1, p1_dist, p1_opp) : 0u;
     if (P2BOT) a2 = bot_next<1>(T, e, e.bq2, 4.0f, STAND);
-    e.misc = a1 << FGM_ACTOR1_SHIFT | a2 << FGM_ACTOR2_SHIFT;           // recorded inputs 0, done 0, cum 0
+    e.misc = a1 << FGM_ACTOR1_SHIFT | a2 << FGM_ACTOR2_SHIFT            // recorded inputs 0, done 0, cum 0
+           | (P1BOT ? 1u << FGM_P1CALLED_SHIFT : 0u);
 }
 
 // What one env-step hands back: FootsiesEnv._extract_obs / _extract_info (footsies.py:336-380) incl. the
@@ -512,6 +534,9 @@ FG_DEV void simulate_frame(const Tables &T, Env &e, uint32_t in1, uint32_t in2, 
         acc.a += 1u + (1u << (8u * (dead1 && dead2 ? 3u : dead2 ? 1u : 2u)));
         acc.ep_frames += (uint32_t)(e.frame + 1);
         e.misc |= 1u << FGM_DONE_SHIFT;
+        // P1's never-Reset() bot is not asked on the terminal frame; what it recorded last (= the state before this frame)
+        // is what it will decide on at the start of the next round (see reset_env)
+        if (P1BOT) e.misc = (e.misc & ~(255u << FGM_P1MEM_SHIFT)) | (bot_dist_index(pre_dist) | pre_a2 << 3) << FGM_P1MEM_SHIFT;
     } else {
         // ---- TrainingManager.Step (TrainingManager.cs:59-77): actors' inputs for the next frame; bots are asked
         //      after the frame, P1 first, and not on the terminal frame ----

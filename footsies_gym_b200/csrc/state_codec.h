@@ -56,7 +56,10 @@
 #define FGH_DASH_SHIFT 0     // 8 bits: dash-detection automaton state (0 = COLD / cleared history)
 #define FGH_ARUN_SHIFT 8     // 6 bits: attack run length (saturates at 59)
 
-// misc env word (bits [0:12) unused)
+// misc env word (bits [9:12) unused)
+#define FGM_P1MEM_SHIFT 0    // 8 bits, by_example only: the FightState P1's never-Reset() BattleAI recorded last, kept over a
+                             // terminal frame for its first query of the next round: distance bucket [0:3) | opponent action [3:8)
+#define FGM_P1CALLED_SHIFT 8 // 1 bit, by_example only: P1's BattleAI has been queried before (its fightStates are not null)
 #define FGM_REC1_SHIFT 12    // 3 bits: last recorded input P1 (BattleCore.cs:593-607 stops recording after 18000 frames)
 #define FGM_REC2_SHIFT 15
 #define FGM_DONE_SHIFT 18    // battle over, waiting for reset
@@ -175,6 +178,7 @@ static inline void fg_decode_env(const FgVec4 &f1, const FgVec4 &f2, const FgVec
     o->actor_input[1] = (int)fg_bits(m, FGM_ACTOR2_SHIFT, 3);
     o->rng_state[0] = r.x; o->rng_state[1] = r.y; o->rng_state[2] = r.z; o->rng_state[3] = r.w;
     o->bot_queue[0] = e.w; o->bot_queue[1] = e.z;
+    o->p1_bot_memory = (int)fg_bits(m, FGM_P1MEM_SHIFT, 9);
 }
 
 static inline int fg_encode_env(const fg_env_state *s, FgVec4 *f1, FgVec4 *f2, FgVec4 *e, FgVec4 *r) {
@@ -182,7 +186,8 @@ static inline int fg_encode_env(const fg_env_state *s, FgVec4 *f1, FgVec4 *f2, F
     if (s->cum_reward_index < 0 || s->cum_reward_index >= FT_NUM_CUM) return -1;
     uint32_t m = ((uint32_t)s->recorded_input[0] & 7u) << FGM_REC1_SHIFT | ((uint32_t)s->recorded_input[1] & 7u) << FGM_REC2_SHIFT
                | (uint32_t)(s->done != 0) << FGM_DONE_SHIFT | (uint32_t)s->cum_reward_index << FGM_CUM_SHIFT
-               | ((uint32_t)s->actor_input[0] & 7u) << FGM_ACTOR1_SHIFT | ((uint32_t)s->actor_input[1] & 7u) << FGM_ACTOR2_SHIFT;
+               | ((uint32_t)s->actor_input[0] & 7u) << FGM_ACTOR1_SHIFT | ((uint32_t)s->actor_input[1] & 7u) << FGM_ACTOR2_SHIFT
+               | ((uint32_t)s->p1_bot_memory & 0x1ffu) << FGM_P1MEM_SHIFT;
     e->x = (uint32_t)s->frame; e->y = m; e->z = s->bot_queue[1]; e->w = s->bot_queue[0];
     r->x = s->rng_state[0]; r->y = s->rng_state[1]; r->z = s->rng_state[2]; r->w = s->rng_state[3];
     return 0;

@@ -114,6 +114,10 @@ typedef struct {
     int32_t actor_input[2];     /* input each actor holds for the next frame (bots: already decided)      */
     uint32_t rng_state[4];      /* per-env xorshift128 standing in for UnityEngine.Random                 */
     uint32_t bot_queue[2];      /* per bot: move position[0:9) remaining[9:16) attack position[16:24) remaining[24:31) */
+    int32_t p1_bot_memory;      /* by_example only: what P1's BattleAI keeps across rounds -- it is never Reset() because the
+                                   game wraps it in a spectator actor (BattleCore.cs:274, GameManager.cs:200-201).  bit 8: it
+                                   has been queried at least once (fightStates no longer null, BattleAI.cs:30,47); while `done`:
+                                   bits [0:3) distance bucket, [3:8) opponent action index of its last recorded FightState */
 } fg_env_state;
 
 typedef struct fg_handle fg_handle;

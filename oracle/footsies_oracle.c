@@ -86,6 +86,7 @@ typedef struct {
 typedef struct {
     float distanceX;
     int isOpponentDamage, isOpponentGuardBreak, isOpponentBlocking, isOpponentNormalAttack, isOpponentSpecialAttack;
+    int isSet;   /* 0 = the slot still holds the C# array's initial null (BattleAI.cs:30) */
 } FightState;
 
 typedef struct { int buf[QUEUE_CAP]; int head, count; } Queue;
@@ -584,6 +585,7 @@ static void ai_UpdateFightState(Env *e, BattleAI *ai) {
                               || opp->currentActionID == A_GUARD_M);
     cur.isOpponentNormalAttack = (opp->currentActionID == A_N_ATTACK || opp->currentActionID == A_B_ATTACK);
     cur.isOpponentSpecialAttack = (opp->currentActionID == A_N_SPECIAL || opp->currentActionID == A_B_SPECIAL);
+    cur.isSet = 1;
     for (int i = 1; i < MAX_FIGHT_STATE_RECORD; i++) ai->fightStates[i] = ai->fightStates[i - 1];
     ai->fightStates[0] = cur;
 }
@@ -592,6 +594,8 @@ static int ai_getNextAIInput(Env *e, BattleAI *ai) {
     int input = 0;
     ai_UpdateFightState(e, ai);
     const FightState *s = &ai->fightStates[FIGHT_STATE_READ_INDEX];
+    if (!s->isSet) return 0;                                   /* `if (fightState != null)` :47 -- only a BattleAI that
+                                                                  was never Reset() sees this, on its very first call */
     if (ai->moveQueue.count > 0) input |= q_pop(&ai->moveQueue);
     else ai_SelectMovement(e, ai, s);
     if (ai->attackQueue.count > 0) input |= q_pop(&ai->attackQueue);
@@ -762,7 +766,11 @@ static EnvironmentState run_round_start(Env *e, const fo_config *cfg) {
     e->roundState = RS_INTRO;
     f_SetupBattleStart(&e->fighter[0], -2.0f, 1);             /* :264 */
     f_SetupBattleStart(&e->fighter[1], 2.0f, 0);              /* :265 */
-    if (cfg->p1_bot) ai_Reset(e, &e->ai[0]);                  /* :274-277 */
+    /* :274-277.  P1's bot is NOT reset: the only way the reference runs a bot as P1 is by_example, which launches the game
+     * with --p1-bot --p1-spectator (footsies.py:230-232); GameManager.cs:200-201 then wraps the bot actor in a
+     * TrainingActorRemoteSpectator, and `trainingManager.actorP1 is TrainingBattleAIActor` (:274) is false for the wrapper.
+     * P1's BattleAI therefore keeps its queues and its last recorded fight state across rounds, and its fightStates start
+     * out null (first call of the process returns 0 without drawing).  Pinned by tests/test_oracle_vs_ref.py. */
     if (cfg->p2_bot) ai_Reset(e, &e->ai[1]);
     if (!cfg->stale_intro_input) { e->actorInput[0] = 0; e->actorInput[1] = 0; }
     UpdateIntroState(e);                                      /* next tick (:183-192), introStateTime = 0 (:125) */

@@ -27,7 +27,7 @@ def _cuda():
 def _states_equal(a, b, where):
     for f in INT_FIELDS + ["pos_x", "velocity_x"]:
         assert np.array_equal(a["f"][f], b["f"][f]), f"{where}: f.{f}"
-    for f in ("frame", "recorded_input", "done", "cum_reward_index", "actor_input", "rng_state", "bot_queue"):
+    for f in ("frame", "recorded_input", "done", "cum_reward_index", "actor_input", "rng_state", "bot_queue", "p1_bot_memory"):
         assert np.array_equal(a[f], b[f]), f"{where}: {f}"
 
 

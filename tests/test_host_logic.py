@@ -30,7 +30,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_capi.FgConfig) == 48
     assert C.sizeof(_capi.FgBuffers) == 8 + 8 * (4 + 1 + 2 + 5 + 1)
     assert C.sizeof(_capi.FgFighterState) == 72
-    assert C.sizeof(_capi.FgEnvState) == 2 * 72 + 4 * 13
+    assert C.sizeof(_capi.FgEnvState) == 2 * 72 + 4 * 14
     assert _capi.env_state_dtype().itemsize == C.sizeof(_capi.FgEnvState)
 
 

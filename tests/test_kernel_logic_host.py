@@ -34,13 +34,16 @@ def test_frame_skipped_fusion_host_logic(frame_skip, p2_bot, dense, autoreset):
     pc.frame_skipped_fused_vs_masked_loop(make_env, frame_skip, p2_bot, n=120, steps=250, dense=dense, autoreset=autoreset)
 
 
-def test_masked_reset_and_state_round_trip_host_logic(oracle):
+@pytest.mark.parametrize("by_example", [False, True])
+def test_masked_reset_and_state_round_trip_host_logic(oracle, by_example):
+    """by_example: P1's bot is never Reset() (spectator wrapper, BattleCore.cs:274) -- a RESET in mid-round makes it decide
+    on the state it recorded last, a reset after a KO on the state before the terminal frame."""
     from kernel_host import HostKernelEnv
     from parity import compare_state_and_outputs
     rng = np.random.default_rng(8)
     n = 333
-    env = HostKernelEnv(num_envs=n, seed=1)
-    orc = oracle.OracleBatch(n, p2_bot=True, seed=1)
+    env = HostKernelEnv(num_envs=n, seed=1, by_example=by_example)
+    orc = oracle.OracleBatch(n, p1_bot=by_example, p2_bot=True, seed=1)
     env.reset()
     orc.reset()
     for t in range(400):

@@ -67,14 +67,7 @@ def run_pair(make_env, oracle, n, steps, *, p1_bot=False, p2_bot=True, dense=Tru
 CASES = [name for name in dir(pc) if name.startswith("case_") and name != "case_fused_frame_skip"]
 
 
-# FOUND BY THIS TEST (round 2): by_example launches the game with --p1-bot --p1-spectator, and the spectator wrapper makes
-# `actorP1 is TrainingBattleAIActor` false (BattleCore.cs:274), so P1's BattleAI is never Reset() at a round start.  The
-# oracle (and the kernel) reset it.  Being fixed in oracle + kernel; strict xfail so that the fix has to remove this.
-KNOWN_OPEN = {"case_both_bots_by_example", "case_p1_bot_vs_remote_p2"}
-
-
-@pytest.mark.parametrize("name", [pytest.param(c, marks=pytest.mark.xfail(strict=True)) if c in KNOWN_OPEN else c
-                                  for c in CASES], ids=[c[5:] for c in CASES])
+@pytest.mark.parametrize("name", CASES, ids=[c[5:] for c in CASES])
 def test_every_parity_tape_oracle_equals_transliterated_reference(monkeypatch, name):
     monkeypatch.setattr(pc, "run_case", run_pair)
     # config B (the trace bit-exactness gate) at 512 battles x 2048 frames; the others at 1/16 of their GPU size
@@ -94,11 +87,13 @@ def test_frame_delay_queue(frame_delay, dense):
     run_pair(None, None, n, steps, dense=dense, frame_delay=frame_delay, tape1=pc.tape_sticky(rng, steps, n), seed=5)
 
 
-def test_masked_hard_reset_and_reseed_mid_episode():
-    """RESET command in the middle of an episode (BattleCore.cs:143-146) and SEED (:170-173) on a subset of the battles."""
+@pytest.mark.parametrize("by_example", [False, True])
+def test_masked_hard_reset_and_reseed_mid_episode(by_example):
+    """RESET command in the middle of an episode (BattleCore.cs:143-146) and SEED (:170-173) on a subset of the battles;
+    by_example: P1's spectator-wrapped bot is not Reset() by the new round."""
     rng = np.random.default_rng(8)
     n = 128
-    kw = dict(p2_bot=True, seed=1, threads=8)
+    kw = dict(p1_bot=by_example, p2_bot=True, seed=1, threads=8)
     o, r = ob.OracleBatch(n, **kw), rb.RefBatch(n, **kw)
     o.reset()
     r.reset()
