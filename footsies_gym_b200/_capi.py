@@ -92,10 +92,11 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path):
+    if _build.is_stale(path):
+        # missing, or built from other sources than the ones in the tree (content digest): never run a stale kernel silently
         if not build_if_missing:
-            raise FootsiesLibraryError(f"{path} is missing: run `python -m footsies_gym_b200.build`")
-        _build.build()
+            raise FootsiesLibraryError(f"{path} is missing or stale: run `python -m footsies_gym_b200.build`")
+        _build.build()            # lock + atomic rename: safe when every rank of a torchrun job gets here at once
     L = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.fg_abi_version.restype = i32
@@ -133,9 +134,9 @@ def load(build_if_missing=True):
     L.fg_launch_count.restype = i64
     L.fg_launch_count.argtypes = [vp]
     L.fg_policy_mlp_sample.restype = i32
-    L.fg_policy_mlp_sample.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp]
+    L.fg_policy_mlp_sample.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, vp, i64, vp]
     L.fg_policy_mlp_sample_p2.restype = i32
-    L.fg_policy_mlp_sample_p2.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, i32, vp]
+    L.fg_policy_mlp_sample_p2.argtypes = [vp] * 8 + [i32, i32, C.c_uint64, C.c_uint64, vp, vp, vp, i32, i64, vp]
     L.fg_policy_last_error.restype = C.c_char_p
     L.fg_rollout_mlp.restype = i32
     L.fg_rollout_mlp.argtypes = [vp, C.POINTER(FgRolloutBuffers), vp]

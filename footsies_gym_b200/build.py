@@ -40,12 +40,33 @@ def deps():
                                                         "rollout_kernel.h")] + [inc]
 
 
-def is_stale(lib_path=None):
+def source_digest(extra_flags=()):
+    """sha256 over the contents of every source / header and the compiler flags: what the built library depends on.
+    (Content, not mtimes: the tree is copied to GPU boxes and checked out by git, neither of which keeps timestamps.)"""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(" ".join(NVCC_FLAGS + list(extra_flags)).encode())
+    for d in deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _digest_path(lib_path):
+    return lib_path + ".srchash"
+
+
+def is_stale(lib_path=None, extra_flags=()):
+    """True when the library is missing or was built from other sources / flags than the ones in the tree."""
     lib_path = lib_path or LIB_PATH
     if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(lib_path)
-    return any(os.path.getmtime(d) > t for d in deps() if os.path.exists(d))
+    try:
+        with open(_digest_path(lib_path)) as f:
+            return f.read().strip() != source_digest(extra_flags)
+    except OSError:
+        return True
 
 
 def translation_units():
@@ -69,32 +90,52 @@ def translation_units():
 
 
 def build(force=False, verbose=False, extra_flags=(), lib_path=None):
-    """Build libfootsies_b200.so next to this file; returns its path."""
+    """Build libfootsies_b200.so next to this file; returns its path.  Safe to call from several processes at once (one
+    rank per GPU under torchrun): an exclusive file lock serialises them, staleness is re-checked under the lock, objects
+    go to a per-process directory and the library is moved into place atomically."""
+    import fcntl
+    import tempfile
     lib_path = lib_path or LIB_PATH
-    if not force and not is_stale(lib_path):
+    if not force and not is_stale(lib_path, extra_flags):
         return lib_path
     nvcc = _nvcc()
-    obj_dir = OBJ_DIR if lib_path == LIB_PATH else lib_path + ".obj"
-    os.makedirs(obj_dir, exist_ok=True)
+    obj_root = OBJ_DIR if lib_path == LIB_PATH else lib_path + ".obj"
+    os.makedirs(obj_root, exist_ok=True)
     flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    with open(os.path.join(obj_root, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale(lib_path, extra_flags):      # another process built it while this one waited
+                return lib_path
+            obj_dir = tempfile.mkdtemp(prefix="obj.", dir=obj_root)
 
-    def compile_one(unit):
-        name, src, defs = unit
-        out = os.path.join(obj_dir, name)
-        res = subprocess.run([nvcc] + flags + defs + ["-c", src, "-o", out], capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {name}:\n" + res.stdout + res.stderr)
-        return out, res.stderr
+            def compile_one(unit):
+                name, src, defs = unit
+                out = os.path.join(obj_dir, name)
+                res = subprocess.run([nvcc] + flags + defs + ["-c", src, "-o", out], capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on {name}:\n" + res.stdout + res.stderr)
+                return out, res.stderr
 
-    units = translation_units()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 2)) as pool:
-        results = list(pool.map(compile_one, units))
-    if verbose:
-        for _, log in results:
-            print(log)
-    res = subprocess.run([nvcc, "-shared", "-o", lib_path] + [o for o, _ in results], capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+            try:
+                units = translation_units()
+                with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 2)) as pool:
+                    results = list(pool.map(compile_one, units))
+                if verbose:
+                    for _, log in results:
+                        print(log)
+                tmp_lib = os.path.join(obj_dir, LIB_NAME)
+                res = subprocess.run([nvcc, "-shared", "-o", tmp_lib] + [o for o, _ in results], capture_output=True, text=True)
+                if res.returncode != 0:
+                    raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp_lib, lib_path)
+                with open(_digest_path(lib_path) + ".tmp", "w") as f:
+                    f.write(source_digest(extra_flags) + "\n")
+                os.replace(_digest_path(lib_path) + ".tmp", _digest_path(lib_path))
+            finally:
+                shutil.rmtree(obj_dir, ignore_errors=True)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return lib_path
 
 

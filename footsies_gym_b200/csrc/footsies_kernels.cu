@@ -144,9 +144,27 @@ __global__ void __launch_bounds__(256) pack_obs_kernel(const float4 *__restrict_
 __global__ void __launch_bounds__(256) delay_ring_kernel(const float4 *__restrict__ obs, const int32_t *__restrict__ frame,
                                                          const uint32_t *__restrict__ misc, float4 *ring_obs, int32_t *ring_frame,
                                                          uint32_t *ring_misc, float4 *__restrict__ out_obs, int32_t *__restrict__ out_frame,
-                                                         uint32_t *__restrict__ out_misc, int n, int depth, int pos) {
+                                                         uint32_t *__restrict__ out_misc, const uint8_t *__restrict__ step_mask,
+                                                         int n, int depth, int pos) {
     const int oldest = (pos + 1) % depth;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (step_mask && !step_mask[i]) {
+            // a battle the step mask held back keeps its queue and its last emitted state (the reference's deque is per
+            // env, footsies.py:129-131); the ring position is shared, so its slots move along with it instead
+            const size_t last = (size_t)(depth - 1) * n + i;
+            float4 ca = ring_obs[2 * last], cb = ring_obs[2 * last + 1];
+            int32_t cf = ring_frame[last];
+            uint32_t cm = ring_misc[last];
+            for (int s = 0; s < depth; s++) {
+                const size_t k = (size_t)s * n + i;
+                const float4 ta = ring_obs[2 * k], tb = ring_obs[2 * k + 1];
+                const int32_t tf = ring_frame[k];
+                const uint32_t tm = ring_misc[k];
+                ring_obs[2 * k] = ca; ring_obs[2 * k + 1] = cb; ring_frame[k] = cf; ring_misc[k] = cm;
+                ca = ta; cb = tb; cf = tf; cm = tm;
+            }
+            continue;
+        }
         const float4 a = obs[2 * (size_t)i], b = obs[2 * (size_t)i + 1];
         const int32_t f = frame[i];
         const uint32_t m = misc[i];
@@ -483,7 +501,7 @@ int32_t fg_delay_ring_step(fg_handle *h, int32_t depth, int32_t pos, float *ring
     CUDA_TRY(cudaSetDevice(h->cfg.device));
     delay_ring_kernel<<<grid_for(h, 8), 256, 0, (cudaStream_t)stream>>>(
         (const float4 *)h->buf.obs, h->buf.info_frame, (const uint32_t *)h->buf.info_misc, (float4 *)ring_obs, ring_frame,
-        (uint32_t *)ring_misc, (float4 *)out_obs, out_frame, (uint32_t *)out_misc, h->cfg.num_envs, depth, pos);
+        (uint32_t *)ring_misc, (float4 *)out_obs, out_frame, (uint32_t *)out_misc, h->buf.step_mask, h->cfg.num_envs, depth, pos);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FG_OK;

@@ -33,6 +33,7 @@ struct PolicyParams {
     const unsigned long long *counter_base;   // optional device word added to `counter` (CUDA-graph replays bump it)
     int n, hidden;
     int mirror;                // 1: the policy drives P2 from the mirrored observation, its action is mirrored back
+    long long first_env;       // global index of battle 0 (fg_config.first_env_index): samples do not depend on the sharding
 };
 
 template <int H>
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(kPolThreads) policy_mlp_sample_kernel(const Po
         if (tid < kPolEnvs && env < p.n) {
             float lg[8], lp;
             policy_logits_of<H, kPolEnvs, kPolicyWarps>(sm, sm + PolicySmemBcast<H, kPolEnvs, kPolicyWarps>::kWeightFloats, tid, lg);
-            int a = policy_sample(lg, hash3(p.seed, counter, (uint32_t)env), lp);
+            int a = policy_sample(lg, hash3(p.seed, counter, (uint64_t)(p.first_env + env)), lp);
             if (p.mirror) a = policy_mirror_action(a);
             p.actions[env] = (uint8_t)a;
             if (p.logp) p.logp[env] = lp;
@@ -84,7 +85,7 @@ const char *fg_policy_last_error(void) { return g_perr; }
 static int32_t policy_sample_impl(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
                                   const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
                                   uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
-                                  float *obs_copy, int32_t mirror, void *stream) {
+                                  float *obs_copy, int32_t mirror, int64_t first_env_index, void *stream) {
     if (!obs || !scale || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !actions || num_envs <= 0) {
         snprintf(g_perr, sizeof g_perr, "fg_policy_mlp_sample: null argument or empty batch");
         return FG_ERR_INVALID_ARGUMENT;
@@ -94,7 +95,7 @@ static int32_t policy_sample_impl(const float *obs, const float *scale, const fl
         return FG_ERR_INVALID_ARGUMENT;
     }
     PolicyParams p = { obs, { scale, w1, b1, w2, b2, w3, b3 }, actions, logp, obs_copy, seed, counter,
-                       (const unsigned long long *)counter_base, num_envs, hidden, mirror };
+                       (const unsigned long long *)counter_base, num_envs, hidden, mirror, (long long)first_env_index };
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -123,17 +124,17 @@ static int32_t policy_sample_impl(const float *obs, const float *scale, const fl
 int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
                              const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
                              uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
-                             float *obs_copy, void *stream) {
+                             float *obs_copy, int64_t first_env_index, void *stream) {
     return policy_sample_impl(obs, scale, w1, b1, w2, b2, w3, b3, hidden, num_envs, seed, counter, counter_base, actions, logp,
-                              obs_copy, 0, stream);
+                              obs_copy, 0, first_env_index, stream);
 }
 
 int32_t fg_policy_mlp_sample_p2(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
                                 const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
                                 uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
-                                int32_t mirror, void *stream) {
+                                int32_t mirror, int64_t first_env_index, void *stream) {
     return policy_sample_impl(obs, scale, w1, b1, w2, b2, w3, b3, hidden, num_envs, seed, counter, counter_base, actions, logp,
-                              nullptr, mirror != 0, stream);
+                              nullptr, mirror != 0, first_env_index, stream);
 }
 
 }  // extern "C"

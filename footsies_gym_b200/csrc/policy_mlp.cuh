@@ -13,7 +13,8 @@
 // unrolled layer 2 thrashed the instruction cache at 4 battles per thread.
 // Every multiply-add is an explicit fma (packed pairs, __ffma2_rn): the result does not depend on the translation
 // unit's -fmad setting, and both kernels produce bit-identical logits.
-// Randomness: a counter-based hash of (seed, step counter, env index) -- reproducible, no state to carry.
+// Randomness: a counter-based hash of (seed, step counter, GLOBAL env index = first_env_index + local index) --
+// reproducible, no state to carry, and independent of how the battles are sharded over GPUs, like the simulator itself.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,7 +42,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
     return fmaf(-2.0f, r, 1.0f);
 }
 
-__device__ __forceinline__ uint32_t hash3(uint64_t seed, uint64_t counter, uint32_t idx) {
+__device__ __forceinline__ uint32_t hash3(uint64_t seed, uint64_t counter, uint64_t idx) {
     uint64_t z = seed + 0x9e3779b97f4a7c15ull * (counter * 0x100000001b3ull + idx + 1ull);   // splitmix64 finaliser
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
     z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
         if (valid) {
             float lg[8], lp;
             policy_logits_of<H, kEnvs, W>(pw, pact, stid, lg);
-            in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint32_t)i), lp);
+            in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)), lp);
             rp.actions[(size_t)t * n + i] = (uint8_t)in1;
             rp.logp[(size_t)t * n + i] = lp;
         }
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
             if (valid) {
                 float lg[8], lp;
                 policy_logits_of<H, kEnvs, W>(pw2, pact, stid, lg);
-                int a2 = policy_sample(lg, hash3(rp.seed_p2, drawn + (unsigned long long)t, (uint32_t)i), lp);
+                int a2 = policy_sample(lg, hash3(rp.seed_p2, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)), lp);
                 if (rp.p2_mirror) a2 = policy_mirror_action(a2);
                 in2 = (uint32_t)a2;
                 rp.actions_p2[(size_t)t * n + i] = (uint8_t)a2;

@@ -57,7 +57,9 @@ def _as_bitmask(action, n, device):
         t = t.reshape(1)
     else:
         raise ValueError(f"unsupported action shape {tuple(t.shape)}")
-    return t.to(device=device, dtype=torch.uint8, non_blocking=True)
+    # a device -> host copy into pageable memory is only safe as a blocking copy (the caller reads it right away)
+    to_cpu = torch.device(device).type == "cpu"
+    return t.to(device=device, dtype=torch.uint8, non_blocking=not to_cpu)
 
 
 class FootsiesEnv:
@@ -483,7 +485,10 @@ class FootsiesEnv:
                 p1 = C.c_void_p(hb["a1"].data_ptr())
         if self._opponent_mode != "bot":
             if opponent_action is None:
-                raise ValueError("opponent_action is required when the opponent is not the in-game bot")
+                if self.opponent is None:
+                    raise ValueError("opponent_action is required when the opponent is not the in-game bot")
+                # like step() and the reference (footsies.py:522-527): ask the opponent policy installed with set_opponent
+                opponent_action = self.opponent(self._most_recent_observation, self._most_recent_info)
             a = _as_bitmask(opponent_action, self.num_envs, "cpu")
             if a.data_ptr() != hb["a2"].data_ptr():
                 if a.is_pinned() and a.is_contiguous():

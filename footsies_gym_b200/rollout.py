@@ -44,10 +44,12 @@ class MLPPolicy(torch.nn.Module):
         return self.net(obs * self.scale)
 
     def fused_sample(self, obs: torch.Tensor, actions: torch.Tensor, logp: Optional[torch.Tensor], seed: int, counter: int,
-                     counter_base: Optional[torch.Tensor] = None, obs_copy: Optional[torch.Tensor] = None):
+                     counter_base: Optional[torch.Tensor] = None, obs_copy: Optional[torch.Tensor] = None,
+                     first_env_index: int = 0):
         """One launch of fg_policy_mlp_sample on the current stream: actions (uint8 [N]) and logp (float32 [N]) are
-        written in place; sampling is a pure function of (seed, counter + counter_base[0], env index); counter_base
-        is an optional int64 device tensor (bumped between CUDA-graph replays)."""
+        written in place; sampling is a pure function of (seed, counter + counter_base[0], first_env_index + env index)
+        -- the global battle index, so that shards of one job draw what the whole batch would; counter_base is an optional
+        int64 device tensor (bumped between CUDA-graph replays)."""
         lib = _capi.load()
         l1, l2, l3 = self.net[0], self.net[2], self.net[4]
         ts = [obs, self.scale, l1.weight, l1.bias, l2.weight, l2.bias, l3.weight, l3.bias]
@@ -59,12 +61,12 @@ class MLPPolicy(torch.nn.Module):
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
         rc = lib.fg_policy_mlp_sample(*[ptr(t) for t in ts], self.hidden, obs.shape[0], int(seed) & (2**64 - 1),
                                       int(counter), ptr(counter_base), ptr(actions), ptr(logp), ptr(obs_copy),
-                                      C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+                                      int(first_env_index), C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
         if rc != 0:
             raise _capi.FootsiesLibraryError(lib.fg_policy_last_error().decode())
 
     def fused_sample_p2(self, obs: torch.Tensor, actions: torch.Tensor, logp: Optional[torch.Tensor], seed: int, counter: int,
-                        counter_base: Optional[torch.Tensor] = None, mirror: bool = False):
+                        counter_base: Optional[torch.Tensor] = None, mirror: bool = False, first_env_index: int = 0):
         """fused_sample for a policy that drives P2 (fg_policy_mlp_sample_p2): with mirror=True it is fed the mirrored
         observation (per-player fields swapped, positions negated) and its Left / Right bits are mirrored back, so that
         the network that plays P1 can play P2 as well."""
@@ -79,7 +81,7 @@ class MLPPolicy(torch.nn.Module):
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())   # noqa: E731
         rc = lib.fg_policy_mlp_sample_p2(*[ptr(t) for t in ts], self.hidden, obs.shape[0], int(seed) & (2**64 - 1),
                                          int(counter), ptr(counter_base), ptr(actions), ptr(logp), int(bool(mirror)),
-                                         C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
+                                         int(first_env_index), C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream))
         if rc != 0:
             raise _capi.FootsiesLibraryError(lib.fg_policy_last_error().decode())
 
@@ -186,7 +188,8 @@ class RolloutCollector:
         self.obs[0].copy_(self.obs[h])                              # carry the last observation over
         for t in range(h):
             if self.mode == "step":
-                self.policy.fused_sample(self.obs[t], self.actions[t], self.logp[t], self._seed, t, self._drawn)
+                self.policy.fused_sample(self.obs[t], self.actions[t], self.logp[t], self._seed, t, self._drawn,
+                                         first_env_index=env.first_env_index)
             else:
                 logits = self.policy(self.obs[t])
                 logp_all = torch.log_softmax(logits, dim=-1)
@@ -198,7 +201,8 @@ class RolloutCollector:
             else:
                 if self.mode == "step":
                     self.opponent_policy.fused_sample_p2(self.obs[t], self.actions_p2[t], self.logp_p2[t],
-                                                         self._seed ^ _P2_SEED_SALT, t, self._drawn, self.mirror_opponent)
+                                                         self._seed ^ _P2_SEED_SALT, t, self._drawn, self.mirror_opponent,
+                                                         first_env_index=env.first_env_index)
                 else:
                     o = mirror_obs(self.obs[t]) if self.mirror_opponent else self.obs[t]
                     logp_all = torch.log_softmax(self.opponent_policy(o), dim=-1)

@@ -116,9 +116,10 @@ _HIT_GUARD_MOVES = (FootsiesMove.DAMAGE, FootsiesMove.GUARD_STAND, FootsiesMove.
 class FootsiesFrameSkipped(_Wrapper):
     """Skip the time steps on which the agent cannot act (frame_skip.py:46-80): envs whose observation is
     skippable keep stepping with the no-op action and the rewards are accumulated.  P1's move_frame is dropped from the
-    observation.  With the CUDA env and an opponent that is not a Python callable the whole loop runs inside the step
-    kernel (fg_config.skip_unactionable: one launch per step, no host round trip); otherwise it is a loop of masked
-    steps here -- only the skippable envs advance (the kernel's step mask)."""
+    observation.  With the CUDA env against the in-game bot the whole loop runs inside the step kernel
+    (fg_config.skip_unactionable: one launch per step, no host round trip); otherwise it is a loop of masked steps here --
+    only the skippable envs advance (the kernel's step mask; the frame_delay queue of a held-back env stands still).
+    When P2's actions come from outside, the action given to step() is held over the skipped frames (see __init__)."""
 
     def __init__(self, env, fused: Optional[bool] = None):
         super().__init__(env)
@@ -128,7 +129,12 @@ class FootsiesFrameSkipped(_Wrapper):
         if fused and not can_fuse:
             raise ValueError("fused frame skipping needs the CUDA env, an agent-controlled P1, no frame_delay and an "
                              "opponent that is not a Python callable")
-        self.fused = can_fuse if fused is None else bool(fused)
+        # Default: fuse only against the in-game bot.  With P2 driven from outside (opponent="self_play" / "remote") the
+        # reference's wrapper asks the opponent again on every skipped step (frame_skip.py:72 -> footsies.py:522-527), which
+        # a single launch cannot do: there both paths HOLD the P2 action given to step() for the skipped frames (the masked
+        # loop re-passes it), so fusing is only done on request (fused=True).
+        bot_p2 = getattr(base0, "_opponent_mode", "bot") == "bot"
+        self.fused = (can_fuse and bot_p2) if fused is None else bool(fused)
         if self.fused:
             base0.set_skip_unactionable(True)
         sp = dict(env.observation_space.spaces)

@@ -179,7 +179,8 @@ int32_t fg_reset_host_compact(fg_handle *h, const uint8_t *mask, const fg_host_o
  * the last fg_step / fg_reset wrote to the bound obs / info buffers into slot `pos` of a ring of depth = frame_delay + 1
  * slots (into every slot for envs that step just reset) and emits the oldest slot, (pos + 1) % depth, to out_*.  The
  * caller owns the ring (DEVICE memory: ring_obs [depth][num_envs][8] floats, ring_frame [depth][num_envs], ring_misc
- * [depth][num_envs][4]) and advances pos by one (mod depth) per step.  Reward and termination are not delayed. */
+ * [depth][num_envs][4]) and advances pos by one (mod depth) per step.  Reward and termination are not delayed.  Battles
+ * held back by the bound step mask keep their queue (their slots are rotated along with pos) and their last out_* entry. */
 int32_t fg_delay_ring_step(fg_handle *h, int32_t depth, int32_t pos, float *ring_obs, int32_t *ring_frame, uint8_t *ring_misc,
                            float *out_obs, int32_t *out_frame, uint8_t *out_misc, void *stream);
 
@@ -199,18 +200,19 @@ int64_t fg_launch_count(fg_handle *h);
  * hidden must be 32, 64 or 128.  actions receives the sampled index 0..7 = the input bitmask of fg_buffers.actions_p1
  * (wrappers/action_comb_disc.py:13-18); logp (optional) its log-probability; obs_copy (optional, [num_envs][8]) a copy
  * of obs, e.g. the rollout-buffer slot of this step.  The sample is a pure function of (seed, counter + *counter_base,
- * env index); counter_base is an optional DEVICE word, so that a captured CUDA graph draws fresh numbers on every
- * replay by bumping it. */
+ * first_env_index + env index) -- the GLOBAL battle index, so that samples do not depend on how the battles are sharded
+ * (pass fg_config.first_env_index); counter_base is an optional DEVICE word, so that a captured CUDA graph draws fresh
+ * numbers on every replay by bumping it. */
 int32_t fg_policy_mlp_sample(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
                              const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
                              uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
-                             float *obs_copy, void *stream);
+                             float *obs_copy, int64_t first_env_index, void *stream);
 /* The same for a policy that drives P2: writes fg_buffers.actions_p2-style bitmasks; mirror = 1 feeds it the mirrored
  * observation and mirrors its action back (see fg_rollout_buffers.p2_mirror). */
 int32_t fg_policy_mlp_sample_p2(const float *obs, const float *scale, const float *w1, const float *b1, const float *w2,
                                 const float *b2, const float *w3, const float *b3, int32_t hidden, int32_t num_envs,
                                 uint64_t seed, uint64_t counter, const uint64_t *counter_base, uint8_t *actions, float *logp,
-                                int32_t mirror, void *stream);
+                                int32_t mirror, int64_t first_env_index, void *stream);
 const char *fg_policy_last_error(void);
 
 /* BASELINE.json configs[4] as ONE launch per horizon: for t = 0 .. horizon - 1 { policy(obs[t]) -> sample -> actions[t],

@@ -128,3 +128,49 @@ def test_frame_delay_on_the_host_buffer_path(oracle):
         assert np.array_equal(reward.numpy(), orc.trace["reward"]), t
         assert np.array_equal(term.numpy().astype(np.int32), orc.trace["terminated"]), t
     env.close()
+
+
+def test_frame_skipped_wrapper_over_a_delayed_batch(oracle):
+    """FootsiesFrameSkipped(FootsiesEnv(num_envs > 1, frame_delay = 3)): the wrapper's loop of masked steps must leave the
+    frame_delay queue of the battles it holds back untouched (the reference keeps one deque per env, footsies.py:129-131,
+    533-535).  Checked against one CPU oracle per battle driven by the reference wrapper's own loop
+    (wrappers/frame_skip.py:68-80) on the DELAYED observation."""
+    from footsies_gym_b200 import FootsiesEnv
+    from footsies_gym_b200.wrappers import FootsiesFrameSkipped
+    import parity_cases as pc
+    dev = _cuda()
+    n, steps, delay = 96, 260, 3
+    rng = np.random.default_rng(41)
+    env = FootsiesFrameSkipped(FootsiesEnv(num_envs=n, device=dev, frame_delay=delay, seed=6, autoreset=False))
+    assert not env.fused
+    orcs = [oracle.OracleBatch(1, p2_bot=True, frame_delay=delay, seed=6, first_env_index=i, autoreset=False) for i in range(n)]
+    obs, info = env.reset()
+    for o in orcs:
+        o.reset()
+    tape = pc.tape_sticky(rng, steps, n, p_change=0.3)
+    zero = np.zeros(1, np.uint8)
+    held_back = 0
+    for t in range(steps):
+        obs, reward, term, trunc, info = env.step(torch.from_numpy(tape[t]))
+        exp_obs, exp_rew, exp_term, exp_frame = [], [], [], []
+        for i, o in enumerate(orcs):
+            if o.trace["terminated"][0]:                       # autoreset off: a finished battle stays as it is
+                tr, total = o.trace, 0.0
+            else:
+                tr = o.step(tape[t, i:i + 1])
+                total = float(tr["reward_f64"][0])
+                while pc._obs_is_skippable(tr["obs"])[0] and not tr["terminated"][0]:
+                    tr = o.step(zero)
+                    total += float(tr["reward_f64"][0])
+                    held_back += 1
+            exp_obs.append(tr["obs"][0].copy()); exp_rew.append(total)
+            exp_term.append(int(tr["terminated"][0])); exp_frame.append(int(tr["info_frame"][0]))
+        exp_obs = np.stack(exp_obs)
+        got = torch.cat([obs["guard"], obs["move"], obs["move_frame"], obs["position"]], 1).cpu().numpy()
+        assert np.array_equal(got, np.delete(exp_obs, 4, axis=1)), (t, np.argwhere(got != np.delete(exp_obs, 4, axis=1))[:3])
+        assert np.array_equal(info["frame"].cpu().numpy(), np.asarray(exp_frame)), t
+        assert np.array_equal(term.cpu().numpy().astype(np.int32), np.asarray(exp_term)), t
+        live = ~np.asarray([bool(o.trace["terminated"][0]) and False for o in orcs])
+        assert np.abs(reward.cpu().numpy().astype(np.float64)[live] - np.asarray(exp_rew)[live]).max() <= 1e-6, t
+    assert held_back > steps
+    env.close()

@@ -41,6 +41,11 @@ def test_config_d_one_million_envs_sharding_invariance_and_conservation(oracle):
     gen.manual_seed(99)
     for e in [whole] + halves:
         e.reset()
+    # the reference's own specification, over every battle, every step (tests/invariants.py): observation_space bounds
+    # (|position| <= 4.6), an episode's dense rewards sum to +-1, a guard break needs an already-empty guard bar
+    from invariants import ReferenceInvariants
+    inv = ReferenceInvariants(n, dev, dense=True)
+    inv.reset(whole.obs, whole.info_frame, whole.info_misc)
     sample = np.sort(np.random.default_rng(5).choice(n, size=1024, replace=False))
     orcs = [oracle.OracleBatch(1, p2_bot=True, seed=seed, first_env_index=int(i)) for i in sample]
     for o in orcs:
@@ -51,6 +56,7 @@ def test_config_d_one_million_envs_sharding_invariance_and_conservation(oracle):
         whole.step(a)
         halves[0].step(a[: n // 2])
         halves[1].step(a[n // 2:])
+        inv.update(whole.obs, whole.reward, whole.terminated, whole.info_frame, whole.info_misc, where=f"step {t}")
         a_s = a[sample_t].cpu().numpy()
         for k, o in enumerate(orcs):
             o.step(a_s[k:k + 1])
@@ -86,20 +92,31 @@ def test_config_d_one_million_envs_sharding_invariance_and_conservation(oracle):
     f = s["f"]
     assert f["guard"].min() >= 0 and f["guard"].max() <= 3 and set(np.unique(f["vital"])) <= {0, 1}
     assert f["hitstun"].min() >= 0 and f["hitstun"].max() <= 30 and f["attack_run"].max() <= 59
-    assert np.all(np.abs(f["pos_x"]) <= 5.0)
+    assert np.all(np.abs(f["pos_x"]) <= np.float32(4.6))              # footsies.py:167 (DASH_BACKWARD's 0.8 pushbox at the wall)
+    assert inv.episodes == st["episodes"] and inv.breaks > 0 and inv.blocks > 1000
     assert np.all((f["vital"].min(axis=1) == 0) == (s["done"] == 1))
     for e in [whole] + halves:
         e.close()
 
 
-def test_config_c_65536_self_play_fused_k4_equals_four_single_frames():
+def test_config_c_65536_self_play_fused_k4_equals_four_single_frames(oracle):
+    """configs[2] at full size: the fused K = 4 launch against (a) four masked K = 1 steps of the same library, every
+    battle, and (b) per-battle CPU oracles (repeat = 4) on a 1 024-battle sample of the 65 536, every macro step --
+    plus the reference-held invariants (tests/invariants.py) over all of them."""
     from footsies_gym_b200 import FootsiesEnv
+    from invariants import ReferenceInvariants
     dev = _cuda()
     n, steps, k = 65536, 300, 4
     fused = FootsiesEnv(num_envs=n, device=dev, opponent="self_play", frame_skip=k, seed=0)
     single = FootsiesEnv(num_envs=n, device=dev, opponent="self_play", frame_skip=1, seed=0)
     fused.reset()
     single.reset()
+    sample = np.sort(np.random.default_rng(6).choice(n, size=1024, replace=False))
+    sample_t = torch.from_numpy(sample).to(dev)
+    orc = oracle.OracleBatch(len(sample), p2_bot=False, seed=0, threads=8)
+    orc.reset()
+    inv = ReferenceInvariants(n, dev, dense=True)
+    inv.reset(fused.obs, fused.info_frame, fused.info_misc)
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
     cur1 = torch.randint(0, 8, (n,), generator=gen, device=dev, dtype=torch.uint8)
@@ -111,6 +128,7 @@ def test_config_c_65536_self_play_fused_k4_equals_four_single_frames():
         cur1 = torch.where(ch1, torch.randint(0, 8, (n,), generator=gen, device=dev, dtype=torch.uint8), cur1)
         cur2 = torch.where(ch2, torch.randint(0, 8, (n,), generator=gen, device=dev, dtype=torch.uint8), cur2)
         fused.step(cur1, cur2)
+        inv.update(fused.obs, fused.reward, fused.terminated, fused.info_frame, fused.info_misc, where=f"macro step {t}")
         # the same macro step as masked single frames: a finished env only resets; a running env stops at its KO
         was_done = single.terminated.clone()
         total = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -126,6 +144,15 @@ def test_config_c_65536_self_play_fused_k4_equals_four_single_frames():
         assert torch.equal(fused.info_frame, single.info_frame), f"macro step {t}"
         # rewards: the fused kernel sums in float64 and rounds once; tolerance for the per-frame float32 roundings
         assert float((fused.reward.double() - total).abs().max()) <= 1e-6, f"macro step {t}: reward"
+        # (b) the sample against the CPU oracle stepping the same macro step (same action for up to 4 frames, stop at KO)
+        tr = orc.step(cur1[sample_t].cpu().numpy(), cur2[sample_t].cpu().numpy(), repeat=k)
+        assert np.array_equal(fused.obs[sample_t].cpu().numpy(), tr["obs"]), f"macro step {t}: obs vs oracle"
+        assert np.array_equal(fused.reward[sample_t].cpu().numpy(), tr["reward"]), f"macro step {t}: reward vs oracle"
+        assert np.array_equal(fused.terminated[sample_t].cpu().numpy().astype(np.int32), tr["terminated"]), f"macro step {t}"
+        assert np.array_equal(fused.info_frame[sample_t].cpu().numpy(), tr["info_frame"]), f"macro step {t}"
+        if t % 50 == 49:
+            from parity import compare_states
+            compare_states(fused.get_state()[sample], tr, where=f"macro step {t}", check_rng=False)
     a, b = fused.episode_stats(), single.episode_stats()
     for key in ("episodes", "p1_wins", "p2_wins", "double_ko", "episode_frames", "guard_breaks", "hits", "blocks", "env_frames"):
         assert a[key] == b[key], key

@@ -167,3 +167,29 @@ def test_save_load_battle_state_through_the_games_own_commands():
         r.step(a1, a2)
         for name in ("f", "frame", "obs", "terminated", "battle_over"):
             assert o.trace[name].tobytes() == r.trace[name].tobytes(), (t, name)
+
+
+@pytest.mark.parametrize("engine", ["oracle", "reference_transliteration"])
+@pytest.mark.parametrize("dense,p2_bot", [(True, True), (False, True), (True, False)])
+def test_reference_held_invariants_on_the_cpu_engines(engine, dense, p2_bot):
+    """tests/invariants.py (observation_space bounds, episode reward sum == +-1, three blocks then guard break) over both
+    CPU engines; the B200 tests run the same checker over a million battles."""
+    import torch
+    from invariants import ReferenceInvariants
+    rng = np.random.default_rng(31)
+    n, steps = 192, 1500
+    cls = ob.OracleBatch if engine == "oracle" else rb.RefBatch
+    b = cls(n, p2_bot=p2_bot, dense_reward=dense, seed=2, threads=8)
+    inv = ReferenceInvariants(n, "cpu", dense=dense)
+
+    def tensors(tr):
+        misc = np.concatenate([tr["info_action"], tr["info_hitstun"]], axis=1).astype(np.uint8)
+        return (torch.from_numpy(tr["obs"].copy()), torch.from_numpy(tr["reward"].copy()),
+                torch.from_numpy(tr["terminated"].astype(bool)), torch.from_numpy(tr["info_frame"].copy()), torch.from_numpy(misc))
+    obs, _, _, frame, misc = tensors(b.reset())
+    inv.reset(obs, frame, misc)
+    t1 = pc.tape_sticky(rng, steps, n, weights=[1, 1, 3, 0.3, 2, 0.5, 2, 0.3])
+    t2 = pc.tape_sticky(rng, steps, n, weights=[1, 0.5, 5, 0.2, 1, 0.2, 1, 0.1])
+    for t in range(steps):
+        inv.update(*tensors(b.step(t1[t], None if p2_bot else t2[t])), where=f"step {t}")
+    assert inv.episodes > 50 and inv.blocks > 20 and (p2_bot or inv.breaks > 0)

@@ -143,3 +143,44 @@ def test_frame_skipped_batch_matches_single_env_semantics(oracle):
     exp = [bool((mf[i, 0] != 0.0 and FOOTSIES_MOVE_INDEX_TO_MOVE[moves[i, 1]] not in hit_guard)
                 or FOOTSIES_MOVE_INDEX_TO_MOVE[moves[i, 0]] == FootsiesMove.DAMAGE) for i in range(500)]
     assert got == exp
+
+
+def test_get_dict_obs_from_vector_obs_round_trip():
+    """footsies_gym/utils.py:7-40 on batches: normalised + flattened observations come back as the original dictionary;
+    the flattened layout is gymnasium's (one-hot MultiDiscrete entries, Dict entries in declaration order)."""
+    import torch
+    from footsies_gym_b200.spaces import Box, Dict, footsies_observation_space
+    from footsies_gym_b200.utils import flatdim, flatten_observation, get_dict_obs_from_vector_obs
+    from footsies_gym_b200.wrappers import FOOTSIES_MOVE_INDEX_TO_MOVE
+    g = torch.Generator().manual_seed(0)
+    n = 257
+    move = torch.randint(0, 15, (n, 2), generator=g).float()
+    dur = torch.tensor([float(m.value.duration) for m in FOOTSIES_MOVE_INDEX_TO_MOVE])[move.long()]
+    obs = {"guard": torch.randint(0, 4, (n, 2), generator=g).float(), "move": move,
+           "move_frame": torch.floor(torch.rand((n, 2), generator=g) * dur),
+           "position": (torch.rand((n, 2), generator=g) * 9.2 - 4.6)}
+    space = footsies_observation_space()
+    assert flatdim(space) == 4 + 4 + 15 + 15 + 2 + 2
+    # (1) plain flatten -> unflatten
+    flat = flatten_observation(space, obs)
+    assert flat.shape == (n, 42) and bool((flat[:, :8].sum(dim=1) == 2).all())
+    back = get_dict_obs_from_vector_obs(flat, flattened=True, unflattenend_observation_space=space, normalized=False)
+    for k in obs:
+        assert torch.equal(back[k], obs[k]), k
+    # (2) normalised (guard too) and flattened, as a FootsiesNormalized + FlattenObservation stack would deliver it
+    norm = {"guard": obs["guard"] / 3.0, "move": obs["move"], "move_frame": obs["move_frame"] / dur, "position": obs["position"] / 4.6}
+    nspace = Dict({"guard": Box(0.0, 1.0, (2,)), "move": space["move"], "move_frame": Box(0.0, 1.0, (2,)), "position": Box(-1.0, 1.0, (2,))})
+    back = get_dict_obs_from_vector_obs(flatten_observation(nspace, norm), True, nspace, normalized=True, normalized_guard=True)
+    for k in obs:
+        assert torch.allclose(back[k], obs[k], atol=1e-5), k
+    # (3) a single unbatched observation, dictionary form, guard not normalised
+    one = {k: v[3] for k, v in norm.items()}
+    one["guard"] = obs["guard"][3]
+    back = get_dict_obs_from_vector_obs(one, flattened=False, normalized=True, normalized_guard=False)
+    for k in obs:
+        assert torch.allclose(back[k], obs[k][3], atol=1e-5), k
+    import pytest
+    with pytest.raises(ValueError):
+        get_dict_obs_from_vector_obs(flat, flattened=True)
+    with pytest.raises(ValueError):
+        get_dict_obs_from_vector_obs(flat, flattened=False)
