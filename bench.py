@@ -305,86 +305,181 @@ def main():
         device_step(i)
     torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-
-    # ---------------- timed region: K device-resident steps ----------------
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    frames_before = env.episode_stats()["env_frames"]
-    launches_before = env.launch_count()
-    barrier()
+    # how many blocks of `steps` launches: at least 25, and enough for ~0.6 s so that nvidia-smi can sample the clocks
+    # DURING the timed region (50 ms period); every rank uses the same count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.time()
     ev0.record()
     for i in range(args.steps):
         device_step(i)
     ev1.record()
+    torch.cuda.synchronize(dev)
+    est_block_ms = max(ev0.elapsed_time(ev1), 1e-3)
+    blocks_t = torch.tensor([max(25, min(2000, int(600.0 / est_block_ms) + 1))], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(blocks_t, op=dist.ReduceOp.MAX)
+    blocks = int(blocks_t.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+
+    # ---------------- timed region: `blocks` x K device-resident steps, back to back; the MEDIAN block is reported ------------
+    frames_before = env.episode_stats()["env_frames"]
+    launches_before = env.launch_count()
+    barrier()
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(blocks + 1)]
+    wall0 = time.time()
+    events[0].record()
+    for b in range(blocks):
+        for i in range(args.steps):
+            device_step(b * args.steps + i)
+        events[b + 1].record()
     barrier()
     wall1 = time.time()
-    ms_local = ev0.elapsed_time(ev1)
-    frames_local = env.episode_stats()["env_frames"] - frames_before
+    block_ms = sorted(events[b].elapsed_time(events[b + 1]) for b in range(blocks))
+    ms_local = block_ms[len(block_ms) // 2]
+    frames_local = (env.episode_stats()["env_frames"] - frames_before) / blocks      # per block (steady state)
     launches = env.launch_count() - launches_before
 
     clocks = None
     if rank == 0:
-        clocks = sampler.summary(wall0, wall1)
-        if clocks is None or clocks["samples"] < 3:
-            # region too short to sample: repeat the identical load for ~1.2 s just to read the clocks
-            w0 = time.time()
-            i = 0
-            while time.time() - w0 < 1.2:
-                for _ in range(20):
-                    device_step(i)
-                    i += 1
-                torch.cuda.synchronize(dev)
-            w1 = time.time()
-            clocks = sampler.summary(w0, w1) or {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-            clocks["sampled"] = "identical launch loop right after the timed region (region shorter than the sampler period)"
+        clocks = sampler.summary(wall0, wall1) or {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        clocks["sampled"] = "nvidia-smi -lms 50 during the %d timed blocks (%.2f s)" % (blocks, wall1 - wall0)
         sampler.stop()
 
-    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    f = torch.tensor([frames_local], dtype=torch.int64, device=dev)
+    t = torch.tensor([ms_local, -block_ms[0], block_ms[-1]], dtype=torch.float64, device=dev)
+    f = torch.tensor([frames_local], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(f, op=dist.ReduceOp.SUM)
-    ms_total = float(t.item())
-    frames_total = int(f.item())
+    ms_total, ms_block_min, ms_block_max = float(t[0].item()), -float(t[1].item()), float(t[2].item())
+    frames_total = float(f.item())
     value = frames_total / (ms_total * 1e-3)
 
-    # ---------------- e2e: the host-buffer C-ABI call (pinned host actions in, results out) ----------------
+    # ---------------- e2e: the host-buffer C-ABI call (pinned host actions in, results out), median of blocks -------------
     e2e_steps = args.e2e_steps or min(args.steps, 20)
     host_tapes = [tp.cpu().pin_memory() for tp in tapes[:4]]
     env.bind_actions(torch.zeros(n, dtype=torch.uint8, device=dev))   # staging buffer for the host actions
-    for i in range(2):
-        env.step_host(host_tapes[i % 4])
-    fb = env.episode_stats()["env_frames"]
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        obs_h, rew_h, term_h, _, info_h = env.step_host(host_tapes[i % 4])
-    torch.cuda.synchronize(dev)
-    e2e_dt = time.perf_counter() - t0
-    e2e_frames = env.episode_stats()["env_frames"] - fb
-    te = torch.tensor([e2e_dt], dtype=torch.float64, device=dev)
-    fe = torch.tensor([e2e_frames], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(fe, op=dist.ReduceOp.SUM)
-    e2e_value = int(fe.item()) / float(te.item())
-    h2d, d2h = env.host_io_bytes_per_step()
+
+    def e2e_measure(call, e2e_blocks=9):
+        for i in range(2):
+            call(host_tapes[i % 4])
+        fb = env.episode_stats()["env_frames"]
+        barrier()
+        dts = []
+        for b in range(e2e_blocks):
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                call(host_tapes[i % 4])          # returns when the results are in host memory
+            dts.append(time.perf_counter() - t0)
+        torch.cuda.synchronize(dev)
+        fr = (env.episode_stats()["env_frames"] - fb) / e2e_blocks
+        dts.sort()
+        te = torch.tensor([dts[len(dts) // 2], -dts[0], dts[-1]], dtype=torch.float64, device=dev)
+        fe = torch.tensor([fr], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fe, op=dist.ReduceOp.SUM)
+        return float(fe.item()) / float(te[0].item()), float(fe.item()) / float(te[2].item()), float(fe.item()) / -float(te[1].item())
+
+    e2e_value, e2e_lo, e2e_hi = e2e_measure(env.step_host_packed)
+    h2d, d2h = env.host_io_bytes_per_step(packed=True)
+    e2e_compact_value, _, _ = e2e_measure(env.step_host)
+    h2d_c, d2h_c = env.host_io_bytes_per_step()
 
     # ---------------- end-of-rollout statistics all-reduce (the only collective on the path) ----------------
     stats = env.all_reduce_stats()
 
-    # ---------------- extra single-GPU workloads (parity-gate configs, informational) ----------------
+    # ---------------- extras every rank takes part in: BASELINE configs[3] as written and configs[4] ----------------
     extra = {}
-    if rank == 0 and not args.no_extra:
+
+    def agg(ms, frames):
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        ff = torch.tensor([frames], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ff, op=dist.ReduceOp.SUM)
+        return float(tt.item()), float(ff.item())
+
+    if not args.no_extra:
+        from footsies_gym_b200.distributed import shard_range
+        total = 1 << 20
+        first_s, n_s = shard_range(total, rank, world)
+        es = FootsiesEnv(num_envs=n_s, device=dev, opponent=None, seed=0, first_env_index=first_s)
+        es.reset()
+        ts = [torch.randint(0, 8, (n_s,), generator=gen, device=dev, dtype=torch.uint8) for _ in range(4)]
+
+        def one_s(i):
+            es.bind_actions(ts[i % 4])
+            es.step_bound()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(300):
+                one_s(i)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        gs = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gs):
+            for i in range(200):
+                one_s(i)
+        gs.replay()
+        barrier()
+        f0 = es.episode_stats()["env_frames"]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(5):
+            gs.replay()
+        s1.record()
+        barrier()
+        ms_s, fr_s = agg(s0.elapsed_time(s1), es.episode_stats()["env_frames"] - f0)
+        hs = [tp.cpu().pin_memory() for tp in ts]
+        for i in range(2):
+            es.step_host_packed(hs[i % 4])
+        f0 = es.episode_stats()["env_frames"]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(40):
+            es.step_host_packed(hs[i % 4])
+        dt_s = time.perf_counter() - t0
+        ms_e, fr_e = agg(dt_s * 1e3, es.episode_stats()["env_frames"] - f0)
+        es.close()
+        extra["D_1048576_envs_sharded_strong"] = {
+            "env_frames_per_sec": fr_s / (ms_s * 1e-3), "ms_per_step": ms_s / 1000.0, "e2e_env_frames_per_sec": fr_e / (ms_e * 1e-3),
+            "total_envs": total, "envs_per_gpu": n_s, "n_gpus": world, "scaling": "strong",
+            "note": "BASELINE configs[3] as written: 1 048 576 envs sharded over the ranks by global env index, random P1 vs "
+                    "BattleAI, frame-skip 1; CUDA-graph replay of 5 x 200 launches, max over ranks; shards fit the 126 MB L2 "
+                    "(latency-bound regime, not the roofline workload); e2e = fg_step_host_packed, 40 calls"}
+
+        from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
+        er = FootsiesEnv(num_envs=16384, device=dev, opponent=None, seed=0, first_env_index=rank * 16384)
+        torch.manual_seed(0)
+        col = RolloutCollector(er, MLPPolicy(64).to(dev), horizon=128, use_cuda_graph=True, seed=0)
+        for _ in range(3):
+            col.collect()
+        barrier()
+        f0 = er.episode_stats()["env_frames"]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(50):
+            col.collect()
+        s1.record()
+        barrier()
+        ms_r, fr_r = agg(s0.elapsed_time(s1), er.episode_stats()["env_frames"] - f0)
+        er.close()
+        extra["E_ppo_rollout_16384_per_gpu"] = {
+            "env_frames_per_sec": fr_r / (ms_r * 1e-3), "ms_per_horizon": ms_r / 50.0, "n_gpus": world, "mode": col.mode,
+            "note": "BASELINE configs[4] on every rank: 16384 envs per GPU x 128-step horizon, MLP 8-64-64-8 policy + sampling + "
+                    "simulator step in ONE launch per horizon (fg_rollout_mlp); 50 horizons, max over ranks, frames summed"}
+
+    # ---------------- extra single-GPU workloads (parity-gate configs, informational) ----------------
+    if rank == 0 and world == 1 and not args.no_extra:
         def quick(n_envs, frame_skip, self_play, steps=200):
             """Device-resident throughput of another configuration; the `steps` launches are captured into one CUDA
             graph and replayed, so that small batches are not timed on the Python launch overhead (~15 us/step)."""
@@ -472,12 +567,17 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_per_env = env.algorithmic_bytes_per_env_step
-        ms_per_launch = ms_total / max(args.steps, 1)
+        ms_per_launch = ms_total / max(args.steps, 1)        # median block / launches per block
         achieved = bytes_per_env * n / (ms_per_launch * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(bytes_per_env, n)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_launch, "higher_is_better": True,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_launch, "blocks": blocks,
+            "ms_per_step_min": ms_block_min / max(args.steps, 1), "ms_per_step_max": ms_block_max / max(args.steps, 1),
+            "timing": "the block of `steps` launches is run `blocks` times back to back after the burn-in; value and "
+                      "ms_per_step are the MEDIAN block (CUDA events on the launching stream, max over ranks); "
+                      "min / max are the fastest / slowest block",
+            "higher_is_better": True,
             "scaling": "strong" if args.total_envs > 0 else "weak", "vs_baseline": None, "dtype": "int32+fp32",
             "data": "synthetic",
             "config": {"workload": (STRONG_WORKLOAD.format(t=args.total_envs, w=world) if args.total_envs > 0
@@ -497,7 +597,16 @@ def main():
                          "algorithmic_bytes_per_env_frame": bytes_per_env, "peak_source": peak_src,
                          "kernel": "step_kernel<K=1, P2 bot, dense>"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "FootsiesEnv.step_host -> fg_step_host_compact (pinned host buffers; compact 27-byte result layout, 1 Mi-env slices pipelined over two streams)"},
+                    "steps": e2e_steps, "blocks": 9, "value_slowest_block": e2e_lo, "value_fastest_block": e2e_hi,
+                    "api": "FootsiesEnv.step_host_packed -> fg_step_host_packed: pinned host actions in, one lossless 16-byte "
+                           "record per battle out (NUMA-local pinned block from fg_host_alloc; 1 Mi-env slices pipelined "
+                           "over two streams, one contiguous copy per slice); median of 9 blocks of `steps` calls, "
+                           "wall clock around calls that return with the results in host memory, max over ranks",
+                    "natural_width_layout": {"value": e2e_compact_value, "h2d_bytes_per_step": h2d_c,
+                                             "d2h_bytes_per_step": d2h_c,
+                                             "api": "FootsiesEnv.step_host -> fg_step_host_compact (27 bytes per battle: every "
+                                                    "field in its natural width, six copies per slice)"},
+                    "scaling_efficiency_note": "driver computes efficiency from the per-N lines"},
             "gpu_launches": launches,
             "clocks": clocks,
             "episode_stats_all_ranks": stats,

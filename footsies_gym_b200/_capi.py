@@ -76,12 +76,52 @@ class FootsiesLibraryError(RuntimeError):
     pass
 
 
+FG_PACKED_REWARD_TABLE_SIZE = 128
+
+
+class HostBlock:
+    """Pinned host memory from fg_host_alloc (placed on the GPU's NUMA node), viewed as torch tensors."""
+
+    def __init__(self, device_index: int, nbytes: int):
+        import torch
+        self._lib = load()
+        self.nbytes = int(nbytes)
+        self.ptr = self._lib.fg_host_alloc(int(device_index), self.nbytes)
+        if not self.ptr:
+            raise FootsiesLibraryError("fg_host_alloc failed: " + self._lib.fg_last_error().decode("utf-8", "replace"))
+        self._raw = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
+        self.bytes = torch.frombuffer(self._raw, dtype=torch.uint8, count=self.nbytes)
+        self._offset = 0
+
+    def take(self, shape, dtype):
+        """Next tensor of the block (64-byte aligned)."""
+        import torch
+        n = int(torch.Size(shape).numel()) * torch.empty((), dtype=dtype).element_size()
+        off = (self._offset + 63) // 64 * 64
+        if off + n > self.nbytes:
+            raise ValueError("host block exhausted")
+        self._offset = off + n
+        return self.bytes[off:off + n].view(dtype).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self._lib.fg_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 _lib = None
 
 # every symbol include/footsies_b200.h declares
 EXPORTS = ["fg_abi_version", "fg_last_error", "fg_algorithmic_bytes_per_env_step", "fg_create", "fg_destroy",
            "fg_bind", "fg_seed", "fg_reset", "fg_step", "fg_step_host", "fg_reset_host", "fg_step_host_compact",
-           "fg_reset_host_compact", "fg_delay_ring_step", "fg_get_state",
+           "fg_reset_host_compact", "fg_packed_reward_table", "fg_step_host_packed", "fg_reset_host_packed", "fg_host_alloc",
+           "fg_host_free", "fg_delay_ring_step", "fg_get_state",
            "fg_set_state", "fg_read_stats", "fg_launch_count", "fg_policy_mlp_sample", "fg_policy_mlp_sample_p2", "fg_policy_last_error",
            "fg_rollout_mlp"]
 
@@ -92,7 +132,9 @@ def load(build_if_missing=True):
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if _build.is_stale(path):
+    if os.environ.get("FOOTSIES_B200_LIB"):
+        pass                      # developer experiment: an explicitly named variant build is loaded as it is
+    elif _build.is_stale(path):
         # missing, or built from other sources than the ones in the tree (content digest): never run a stale kernel silently
         if not build_if_missing:
             raise FootsiesLibraryError(f"{path} is missing or stale: run `python -m footsies_gym_b200.build`")
@@ -123,6 +165,16 @@ def load(build_if_missing=True):
     L.fg_step_host_compact.argtypes = [vp, vp, vp, C.POINTER(FgHostOutputs), vp]
     L.fg_reset_host_compact.restype = i32
     L.fg_reset_host_compact.argtypes = [vp, vp, C.POINTER(FgHostOutputs), vp]
+    L.fg_packed_reward_table.restype = i32
+    L.fg_packed_reward_table.argtypes = [vp, vp, vp]
+    L.fg_step_host_packed.restype = i32
+    L.fg_step_host_packed.argtypes = [vp, vp, vp, vp, vp]
+    L.fg_reset_host_packed.restype = i32
+    L.fg_reset_host_packed.argtypes = [vp, vp, vp, vp]
+    L.fg_host_alloc.restype = vp
+    L.fg_host_alloc.argtypes = [i32, C.c_uint64]
+    L.fg_host_free.restype = None
+    L.fg_host_free.argtypes = [vp]
     L.fg_delay_ring_step.restype = i32
     L.fg_delay_ring_step.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.fg_get_state.restype = i32

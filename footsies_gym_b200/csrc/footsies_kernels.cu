@@ -1,6 +1,8 @@
 // footsies_kernels.cu -- C ABI of the batched FOOTSIES simulator (include/footsies_b200.h) on top of the kernels in
 // step_kernel.cuh.
+#include <sched.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #include "rollout_kernel.h"
 #include "step_kernel.cuh"
@@ -27,11 +29,17 @@ struct fg_handle {
     Tables *d_tables;
     int sm_count;
     int64_t launches;
+    int64_t step_calls;    // fg_step calls so far: every other one walks the battles backwards (L2 reuse across launches)
     uint8_t *d_mask;       // staging for fg_reset_host
     int large_shape_min_envs;
     // host-buffer path (fg_step_host*): slices of host_chunk_envs battles are pipelined over two library-owned
     // streams, so that the D2H copies of slice c run while slice c+1 is being simulated and its actions uploaded
     int host_chunk_envs;
+    uint4 *d_packed;       // [num_envs] packed host layout (fg_packed_result)
+    float *d_reward_table; // [FG_PACKED_REWARD_TABLE_SIZE] ascending; h_reward_table is the host copy
+    uint32_t *d_pack_error;
+    float h_reward_table[FG_PACKED_REWARD_TABLE_SIZE];
+    int reward_table_count;
     float2 *d_position;    // [num_envs] compact host layout: position p1,p2
     uint8_t *d_obs_u8;     // [num_envs][6] compact host layout: guard p1,p2 | move p1,p2 | move_frame p1,p2
     cudaStream_t s_compute, s_copy;
@@ -62,6 +70,7 @@ Params make_params(const fg_handle *h, int first = 0, int count = -1) {
     p.step_mask = h->buf.step_mask ? h->buf.step_mask + o : nullptr;
     p.tables = h->d_tables;
     p.first_env_index = h->cfg.first_env_index + first;
+    p.reverse = (int)(h->step_calls & 1);
     p.n = count < 0 ? h->cfg.num_envs - first : count; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
     p.stale_intro = h->cfg.stale_intro_input;
     p.skip_unactionable = h->cfg.skip_unactionable;
@@ -80,14 +89,10 @@ cudaError_t launch_step_k(const fg_config &c, int sm_count, cudaStream_t s, cons
 
 template <bool B1, bool B2>
 cudaError_t launch_reset(int grid, cudaStream_t s, const Params &p) {
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(reset_kernel<B1, B2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tables));
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = true;
-    }
+    static DeviceOnceFlags configured;
+    if (cudaError_t e = configure_once_per_device(configured, [] {
+            return cudaFuncSetAttribute(reset_kernel<B1, B2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Tables)); }))
+        return e;
     reset_kernel<B1, B2><<<grid, kThreads, sizeof(Tables), s>>>(p);
     return cudaSuccess;
 }
@@ -148,9 +153,11 @@ __global__ void __launch_bounds__(256) delay_ring_kernel(const float4 *__restric
                                                          int n, int depth, int pos) {
     const int oldest = (pos + 1) % depth;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (step_mask && !step_mask[i]) {
-            // a battle the step mask held back keeps its queue and its last emitted state (the reference's deque is per
-            // env, footsies.py:129-131); the ring position is shared, so its slots move along with it instead
+        const int32_t f_now = frame[i];
+        if ((step_mask && !step_mask[i]) || (f_now != -1 && f_now == ring_frame[(size_t)((pos + depth - 1) % depth) * n + i])) {
+            // a battle that did not advance -- held back by the step mask, or over and waiting for its reset (its frame
+            // counter still is the newest entry's) -- keeps its queue and its last emitted state (the reference's deque is
+            // per env, footsies.py:129-131); the ring position is shared, so its slots move along with it instead
             const size_t last = (size_t)(depth - 1) * n + i;
             float4 ca = ring_obs[2 * last], cb = ring_obs[2 * last + 1];
             int32_t cf = ring_frame[last];
@@ -193,6 +200,34 @@ int step_range(fg_handle *h, int first, int count, cudaStream_t s) {
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FG_OK;
+}
+
+// obs / reward / terminated / info of one battle -> one 16-byte fg_packed_result (include/footsies_b200.h).  The reward is
+// carried as its index in the ascending table of the float32 values a single-frame step can pay (exact match by binary
+// search; a value outside the table raises *error).  One thread per battle, 128-bit coalesced loads and stores.
+__global__ void __launch_bounds__(256) pack_records_kernel(const float4 *__restrict__ obs, const float *__restrict__ reward,
+                                                            const uint8_t *__restrict__ terminated, const int32_t *__restrict__ frame,
+                                                            const uint32_t *__restrict__ misc, const float *__restrict__ table,
+                                                            int table_n, uint4 *__restrict__ out, uint32_t *error, int n) {
+    __shared__ float tab[FG_PACKED_REWARD_TABLE_SIZE];
+    for (int k = threadIdx.x; k < FG_PACKED_REWARD_TABLE_SIZE; k += blockDim.x) tab[k] = k < table_n ? table[k] : 3.0e38f;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = obs[2 * (size_t)i], b = obs[2 * (size_t)i + 1];
+        const float r = reward[i];
+        const uint32_t m = misc[i];
+        int lo = 0;
+#pragma unroll
+        for (int stepw = FG_PACKED_REWARD_TABLE_SIZE / 2; stepw >= 1; stepw >>= 1)      // largest lo with tab[lo] <= r
+            if (tab[lo + stepw] <= r) lo += stepw;
+        if (tab[lo] != r) atomicOr(error, 1u);
+        const int32_t f = frame[i] + 1;
+        const uint32_t w0 = (uint32_t)a.x | (uint32_t)a.y << 2 | (uint32_t)a.z << 4 | (uint32_t)a.w << 8 | (uint32_t)b.x << 12
+                          | (uint32_t)b.y << 18 | (terminated[i] ? 1u << 24 : 0u) | (m & 7u) << 25 | ((m >> 8) & 7u) << 28;
+        const uint32_t w1 = ((m >> 16) & 31u) | ((m >> 24) & 31u) << 5 | (uint32_t)lo << 10
+                          | (uint32_t)(f < 0 ? 0 : f > 32767 ? 32767 : f) << 17;
+        out[i] = make_uint4(__float_as_uint(b.z), __float_as_uint(b.w), w0, w1);
+    }
 }
 
 // Library-owned resources of the host-buffer path, created on first use.
@@ -277,6 +312,90 @@ int host_step(fg_handle *h, const uint8_t *a1, const uint8_t *a2, const HostOut 
     return FG_OK;
 }
 
+// ---- packed host layout -------------------------------------------------------------------------------------------
+int packed_init(fg_handle *h) {
+    if (h->cfg.frame_skip != 1 || h->cfg.skip_unactionable)
+        return fail(FG_ERR_INVALID_STATE, "the packed host layout needs frame_skip = 1 and no fused frame skipping "
+                                          "(summed rewards are not table values)%s");
+    if (h->d_packed) return FG_OK;
+    // every float32 value a single-frame step can pay: 0, the +-0.3 guard steps, +-1 and the dense terminal compensations
+    static const double step_r[4] = FT_STEP_REWARD_INIT;
+    static const double term_r[FT_NUM_CUM][4][2] = FT_TERM_REWARD_INIT;
+    std::vector<float> v = { 0.0f, 1.0f, -1.0f };
+    for (int k = 0; k < 4; k++) v.push_back((float)step_r[k]);
+    for (int c = 0; c < FT_NUM_CUM; c++) for (int k = 0; k < 4; k++) for (int d = 0; d < 2; d++) v.push_back((float)term_r[c][k][d]);
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    if ((int)v.size() >= FG_PACKED_REWARD_TABLE_SIZE) return fail(FG_ERR_INVALID_STATE, "reward table overflow%s");
+    h->reward_table_count = (int)v.size();
+    for (int k = 0; k < FG_PACKED_REWARD_TABLE_SIZE; k++) h->h_reward_table[k] = k < (int)v.size() ? v[k] : 0.0f;
+    CUDA_TRY(cudaMalloc(&h->d_reward_table, sizeof h->h_reward_table));
+    CUDA_TRY(cudaMemcpy(h->d_reward_table, h->h_reward_table, sizeof h->h_reward_table, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&h->d_pack_error, sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(h->d_pack_error, 0, sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->d_packed, sizeof(uint4) * (size_t)h->cfg.num_envs));
+    return FG_OK;
+}
+
+int pack_records_range(fg_handle *h, size_t first, size_t m, cudaStream_t s) {
+    const int want = (int)((m + 255) / 256), cap = h->sm_count * 8;
+    const fg_buffers &b = h->buf;
+    pack_records_kernel<<<want < cap ? (want > 0 ? want : 1) : cap, 256, 0, s>>>(
+        (const float4 *)b.obs + 2 * first, b.reward + first, b.terminated + first, b.info_frame + first,
+        (const uint32_t *)b.info_misc + first, h->d_reward_table, h->reward_table_count, h->d_packed + first, h->d_pack_error, (int)m);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FG_OK;
+}
+
+int packed_finish(fg_handle *h, cudaStream_t s) {
+    uint32_t err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, h->d_pack_error, sizeof err, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (err) {
+        cudaMemset(h->d_pack_error, 0, sizeof(uint32_t));
+        return fail(FG_ERR_INVALID_STATE, "a reward outside the packed reward table was produced%s");
+    }
+    return FG_OK;
+}
+
+// fg_step_host_packed: like host_step, but every slice ends in ONE pack kernel and ONE contiguous device->host copy.
+int host_step_packed(fg_handle *h, const uint8_t *a1, const uint8_t *a2, fg_packed_result *out, cudaStream_t user) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!out) return fail(FG_ERR_INVALID_ARGUMENT, "out is null%s");
+    if (!h->cfg.p1_bot && !a1) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p1 is required unless p1_bot%s");
+    if (!h->cfg.p2_bot && !a2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
+    if (int rc = packed_init(h)) return rc;
+    const size_t n = (size_t)h->cfg.num_envs, chunk = (size_t)h->host_chunk_envs;
+    const int slices = (int)((n + chunk - 1) / chunk);
+    if (int rc = host_path_init(h, false, slices)) return rc;
+    cudaStream_t sc = user, sd = user;
+    if (slices > 1) {
+        sc = h->s_compute; sd = h->s_copy;
+        CUDA_TRY(cudaEventRecord(h->ev_fork, user));
+        CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_fork, 0));
+    }
+    h->step_calls++;
+    for (int c = 0; c < slices; c++) {
+        const size_t first = (size_t)c * chunk, m = n - first < chunk ? n - first : chunk;
+        if (!h->cfg.p1_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p1 + first), a1 + first, m, cudaMemcpyHostToDevice, sc));
+        if (!h->cfg.p2_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p2 + first), a2 + first, m, cudaMemcpyHostToDevice, sc));
+        if (int rc = step_range(h, (int)first, (int)m, sc)) return rc;
+        if (int rc = pack_records_range(h, first, m, sc)) return rc;
+        if (slices > 1) {
+            CUDA_TRY(cudaEventRecord(h->ev_slice[c], sc));
+            CUDA_TRY(cudaStreamWaitEvent(sd, h->ev_slice[c], 0));
+        }
+        CUDA_TRY(cudaMemcpyAsync(out + first, h->d_packed + first, m * sizeof(uint4), cudaMemcpyDeviceToHost, sd));
+    }
+    if (slices > 1) {
+        CUDA_TRY(cudaEventRecord(h->ev_join, sd));
+        CUDA_TRY(cudaStreamWaitEvent(user, h->ev_join, 0));
+    }
+    return packed_finish(h, sd);
+}
+
 int reset_on(fg_handle *h, const uint8_t *dmask, cudaStream_t s) {
     Params p = make_params(h);
     p.mask = dmask;
@@ -313,10 +432,92 @@ int host_reset(fg_handle *h, const uint8_t *mask, const HostOut &o, cudaStream_t
     return FG_OK;
 }
 
+int host_reset_packed(fg_handle *h, const uint8_t *mask, fg_packed_result *out, cudaStream_t s) {
+    if (int rc = check_bound(h)) return rc;
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (!out) return fail(FG_ERR_INVALID_ARGUMENT, "out is null%s");
+    if (int rc = packed_init(h)) return rc;
+    const size_t n = (size_t)h->cfg.num_envs;
+    const uint8_t *dmask = nullptr;
+    if (mask) {
+        if (!h->d_mask) CUDA_TRY(cudaMalloc(&h->d_mask, n));
+        CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask, n, cudaMemcpyHostToDevice, s));
+        dmask = h->d_mask;
+    }
+    if (int rc = reset_on(h, dmask, s)) return rc;
+    if (int rc = pack_records_range(h, 0, n, s)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, h->d_packed, n * sizeof(uint4), cudaMemcpyDeviceToHost, s));
+    return packed_finish(h, s);
+}
+
+// NUMA node of a CUDA device (/sys/bus/pci/devices/<bdf>/numa_node), -1 if unknown
+int gpu_numa_node(int dev) {
+    char bdf[64] = "", path[160], buf[32] = "";
+    if (cudaDeviceGetPCIBusId(bdf, sizeof bdf, dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *c = bdf; *c; c++) if (*c >= 'A' && *c <= 'Z') *c += 32;
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = fopen(path, "r");
+    if (!f) return -1;
+    if (!fgets(buf, sizeof buf, f)) buf[0] = 0;
+    fclose(f);
+    return atoi(buf);
+}
+bool node_cpuset(int node, cpu_set_t *set) {
+    char path[96], buf[1024] = "";
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    if (!fgets(buf, sizeof buf, f)) buf[0] = 0;
+    fclose(f);
+    CPU_ZERO(set);
+    int n = 0;
+    for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a, b;
+        if (sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, set); n++; } }
+        else if (sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) { CPU_SET(a, set); n++; }
+    }
+    return n > 0;
+}
 
 }  // namespace
 
 extern "C" {
+
+void *fg_host_alloc(int32_t device, uint64_t bytes) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        fail(FG_ERR_INVALID_ARGUMENT, "fg_host_alloc: no such device%s");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(FG_ERR_CUDA, "fg_host_alloc: cudaSetDevice failed%s"); return nullptr; }
+    cpu_set_t old_set, node_set;
+    const int node = gpu_numa_node(device);
+    const bool have_old = sched_getaffinity(0, sizeof old_set, &old_set) == 0;
+    const bool bound = node >= 0 && have_old && node_cpuset(node, &node_set) && sched_setaffinity(0, sizeof node_set, &node_set) == 0;
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e == cudaSuccess) memset(p, 0, bytes);              // first touch from the bound thread places the pages
+    if (bound) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (e != cudaSuccess) { cudaGetLastError(); fail(FG_ERR_CUDA, "fg_host_alloc: cudaHostAlloc failed%s"); return nullptr; }
+    return p;
+}
+void fg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int32_t fg_packed_reward_table(fg_handle *h, float *table, int32_t *count) {
+    if (!h || !table || !count) return fail(FG_ERR_INVALID_ARGUMENT, "null argument%s");
+    CUDA_TRY(cudaSetDevice(h->cfg.device));
+    if (int rc = packed_init(h)) return rc;
+    memcpy(table, h->h_reward_table, sizeof h->h_reward_table);
+    *count = h->reward_table_count;
+    return FG_OK;
+}
+int32_t fg_step_host_packed(fg_handle *h, const uint8_t *a1, const uint8_t *a2, fg_packed_result *out, void *stream) {
+    return host_step_packed(h, a1, a2, out, (cudaStream_t)stream);
+}
+int32_t fg_reset_host_packed(fg_handle *h, const uint8_t *mask, fg_packed_result *out, void *stream) {
+    return host_reset_packed(h, mask, out, (cudaStream_t)stream);
+}
 
 int32_t fg_abi_version(void) { return FG_ABI_VERSION; }
 const char *fg_last_error(void) { return g_err; }
@@ -347,8 +548,10 @@ int32_t fg_create(const fg_config *cfg, fg_handle **out) {
     h->cfg = *cfg;
     h->bound = false;
     h->launches = 0;
+    h->step_calls = 0;
     h->d_mask = nullptr;
     h->d_position = nullptr; h->d_obs_u8 = nullptr;
+    h->d_packed = nullptr; h->d_reward_table = nullptr; h->d_pack_error = nullptr; h->reward_table_count = 0;
     h->s_compute = h->s_copy = nullptr;
     h->ev_fork = h->ev_join = nullptr;
     // slice size of the pipelined host-buffer path (measured, tools/e2e_bench.py, 4 Mi battles: no slices 2.28 ms, 2 Mi 2.20, 1 Mi 2.21,
@@ -380,6 +583,7 @@ void fg_destroy(fg_handle *h) {
     cudaFree(h->d_tables);
     if (h->d_mask) cudaFree(h->d_mask);
     if (h->d_position) cudaFree(h->d_position);
+    if (h->d_packed) { cudaFree(h->d_packed); cudaFree(h->d_reward_table); cudaFree(h->d_pack_error); }
     if (h->d_obs_u8) cudaFree(h->d_obs_u8);
     if (h->s_compute) { cudaStreamDestroy(h->s_compute); cudaStreamDestroy(h->s_copy); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
     for (cudaEvent_t e : h->ev_slice) cudaEventDestroy(e);
@@ -422,6 +626,7 @@ int32_t fg_reset(fg_handle *h, const uint8_t *mask, void *stream) {
 int32_t fg_step(fg_handle *h, void *stream) {
     if (int rc = check_bound(h)) return rc;
     CUDA_TRY(cudaSetDevice(h->cfg.device));
+    h->step_calls++;
     return step_range(h, 0, -1, (cudaStream_t)stream);
 }
 

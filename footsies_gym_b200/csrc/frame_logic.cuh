@@ -113,6 +113,7 @@ struct Env {            // one battle, in registers
     int32_t frame;
     uint32_t misc, bq2, bq1;
     uint32_t r0, r1, r2, r3;
+    bool drew;          // the RNG advanced since the state was loaded (the RNG plane is only written back then)
 };
 
 // packed-word masks
@@ -127,6 +128,7 @@ FG_DEV uint32_t rng_next(Env &e) {
     uint32_t t = e.r0 ^ (e.r0 << 11);
     e.r0 = e.r1; e.r1 = e.r2; e.r2 = e.r3;
     e.r3 = e.r3 ^ (e.r3 >> 19) ^ t ^ (t >> 8);
+    e.drew = true;
     return e.r3;
 }
 

@@ -8,6 +8,7 @@
 // battles; policy_mlp.cuh); the sampled action is written as the uint8 input bitmask the step kernel is bound to, next
 // to its log-probability, and (optionally) the observation row is copied into the rollout buffer on the way.
 // The per-step path for configurations the whole-horizon kernel (rollout_kernel.cu) does not cover (self-play, masks).
+#include "device_once.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -106,8 +107,9 @@ static int32_t policy_sample_impl(const float *obs, const float *scale, const fl
     cudaError_t e = cudaSuccess;
     cudaStream_t s = (cudaStream_t)stream;
 #define FG_POLICY_LAUNCH(HH) do { \
-        static bool configured[64] = {}; \
-        if (!configured[dev & 63]) { e = cudaFuncSetAttribute(policy_mlp_sample_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); configured[dev & 63] = (e == cudaSuccess); } \
+        static fg::DeviceOnceFlags configured; \
+        e = fg::configure_once_per_device(configured, [bytes] { \
+            return cudaFuncSetAttribute(policy_mlp_sample_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }); \
         if (e == cudaSuccess) policy_mlp_sample_kernel<HH><<<grid, kPolThreads, bytes, s>>>(p); } while (0)
     if (hidden == 32) FG_POLICY_LAUNCH(32);
     else if (hidden == 64) FG_POLICY_LAUNCH(64);

@@ -189,14 +189,10 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
 template <int H, int E, int W, bool DENSE, bool P2POL, bool SKIP>
 static cudaError_t launch_rollout_s(cudaStream_t s, const RolloutParams &rp) {
     constexpr size_t bytes = RolloutSmem<H, E, W, P2POL>::kBytes;
-    static bool configured[64] = {};                    // per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE, P2POL, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = true;
-    }
+    static fg::DeviceOnceFlags configured;
+    if (cudaError_t e = fg::configure_once_per_device(configured, [] {
+            return cudaFuncSetAttribute(rollout_kernel<H, E, W, DENSE, P2POL, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }))
+        return e;
     constexpr int kEnvs = RolloutSmem<H, E, W, P2POL>::kEnvs;
     const int grid = (rp.sim.n + kEnvs - 1) / kEnvs;
     rollout_kernel<H, E, W, DENSE, P2POL, SKIP><<<grid, 32 * W, bytes, s>>>(rp);

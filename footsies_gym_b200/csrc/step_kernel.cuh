@@ -8,6 +8,7 @@
 // shared memory; CTAs are persistent (grid-stride over chunks of 256 envs) and the state planes of the next chunk
 // stream into shared memory with TMA bulk copies while the current chunk is simulated.
 // No tensor cores: nothing here is a contraction.  Bounds: the ALU pipe first, then HBM bandwidth (K = 1).
+#include "device_once.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -57,6 +58,16 @@ using ShapeLargeSingle = StepShape<768, 256, 3, 1>;
 using ShapeLargeFused = StepShape<1024, 256, 3, 1>;
 #endif
 constexpr int kLargeShapeMinEnvs = 768 * 1024;
+// developer switches for A/B measurements (tools/probes/build_variant.sh <tag> -DFG_...=0|1)
+#ifndef FG_SKIP_RNG_STORE
+#define FG_SKIP_RNG_STORE 1
+#endif
+#ifndef FG_PDL
+#define FG_PDL 1
+#endif
+#ifndef FG_REVERSE
+#define FG_REVERSE 1
+#endif
 constexpr int kThreads = 256;                    // reset / seed kernels
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -76,6 +87,7 @@ struct Params {
     int n, frame_skip, autoreset, stale_intro;
     int skip_unactionable;      // fused FootsiesFrameSkipped (KFUSED kernels only)
     int large_shape_min_envs;   // host side only: batch size from which the large CTA shapes are launched
+    int reverse;                // walk the chunks from the last to the first (alternates per launch, see step_kernel)
 };
 
 __device__ __forceinline__ void write_outputs(const Params &p, int i, const Env &e, float reward, bool terminated) {
@@ -102,13 +114,16 @@ __device__ __forceinline__ void load_env(const Params &p, int i, Env &e) {
     e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
     e.frame = (int32_t)c.x; e.misc = c.y; e.bq2 = c.z; e.bq1 = c.w;
     if (WITH_RNG) { const uint4 r = p.pl_rng[i]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
+    e.drew = false;
 }
 template <bool WITH_RNG>
 __device__ __forceinline__ void store_env(const Params &p, int i, const Env &e) {
     p.pl_f1[i] = make_uint4(f2u(e.pos1), f2u(e.vel1), e.pk1, e.hist1);
     p.pl_f2[i] = make_uint4(f2u(e.pos2), f2u(e.vel2), e.pk2, e.hist2);
     p.pl_env[i] = make_uint4((uint32_t)e.frame, e.misc, e.bq2, e.bq1);
-    if (WITH_RNG) p.pl_rng[i] = make_uint4(e.r0, e.r1, e.r2, e.r3);
+    // the bot draws once every few dozen frames: an unchanged RNG plane entry is not written back (saves ~9 % of the
+    // launch's DRAM traffic)
+    if (WITH_RNG && (!FG_SKIP_RNG_STORE || e.drew)) p.pl_rng[i] = make_uint4(e.r0, e.r1, e.r2, e.r3);
 }
 
 // Warp-cooperative fold of the packed per-thread counters into the CTA's shared-memory vector.
@@ -192,17 +207,33 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
             tma_load_1d(S.stage[g][s][k], planes[k] + (size_t)chunk * kGroupThreads, (uint32_t)(kGroupThreads * sizeof(uint4)),
                         &S.full_bar[g][s]);
     };
+    // Chunk order: launch k walks the chunks forwards, launch k + 1 backwards (p.reverse), so that a launch starts on the
+    // battles whose state and output lines the previous launch left in the 126 MB L2.
+    auto chunk_of = [&](int c) { return (FG_REVERSE && p.reverse) ? num_chunks - 1 - c : c; };
     if (lt == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&S.full_bar[g][s], 1u); mbar_init(&S.empty_bar[g][s], kGroupThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#if FG_PDL
+    // Programmatic dependent launch: this CTA may have become resident while the previous launch on the stream was still
+    // draining.  What does not depend on it (barriers, the constant tables) is set up first; battle state, actions and
+    // masks are only touched after griddepcontrol.wait.  The next launch is allowed to move in as soon as SMs free up.
+    load_tables(&S.T, p.tables);
+    if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+    if (lt == 0) {
         // prologue: the group's first kStages-1 chunks are in flight while the tables are being staged
         for (int j = 0; j < kStages - 1; j++) {
             const int cj = first + j * stride;
-            if (cj < full_chunks) issue(cj, j);
+            if (cj < num_chunks && chunk_of(cj) < full_chunks) issue(chunk_of(cj), j);
         }
     }
+#if !FG_PDL
     load_tables(&S.T, p.tables);
     if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
+#endif
     __syncthreads();
     StatAcc acc = { 0u, 0u, 0u, 0u };
     uint32_t frames_since_flush = 0u;
@@ -210,27 +241,29 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
     // 256-byte bulk copy +3.5 %, register-less cp.async into per-thread slots +3 %, loading at the point of use +16 %.)
     uint32_t nin1 = 0u, nin2 = 0u;
     {
-        const int i0 = first * kGroupThreads + lt;
+        const int i0 = (first < num_chunks ? chunk_of(first) : num_chunks) * kGroupThreads + lt;
         if (i0 < p.n) { if (!P1BOT) nin1 = p.act1[i0]; if (!P2BOT) nin2 = p.act2[i0]; }
     }
     int k = 0;
-    for (int c = first; c < num_chunks; c += stride, k++) {
+    for (int cl = first; cl < num_chunks; cl += stride, k++) {
         const int s = k % kStages;
+        const int c = chunk_of(cl);
         const int i = c * kGroupThreads + lt;
         const bool staged = c < full_chunks;
         bool valid = staged || i < p.n;
         if (MASKED) valid = valid && p.step_mask[valid ? i : 0] != 0;
         if (lt == 0) {                                                  // producer: chunk k + kStages - 1 -> the stage read at k - 1
-            const int cn = c + (kStages - 1) * stride;
-            if (cn < full_chunks) {
+            const int cn = cl + (kStages - 1) * stride;
+            if (cn < num_chunks && chunk_of(cn) < full_chunks) {
                 const int sn = (k + kStages - 1) % kStages;
                 if (k >= 1) mbar_wait(&S.empty_bar[g][sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
-                issue(cn, sn);
+                issue(chunk_of(cn), sn);
             }
         }
         const uint32_t act1 = nin1, act2 = nin2;
         {
-            const int in = i + stride * kGroupThreads;
+            const int cn1 = cl + stride;
+            const int in = (cn1 < num_chunks ? chunk_of(cn1) : num_chunks) * kGroupThreads + lt;
             if (in < p.n) { if (!P1BOT) nin1 = p.act1[in]; if (!P2BOT) nin2 = p.act2[in]; }
         }
         Env e;
@@ -243,6 +276,7 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
             e.pos2 = u2f(b.x); e.vel2 = u2f(b.y); e.pk2 = b.z; e.hist2 = b.w;
             e.frame = (int32_t)cc.x; e.misc = cc.y; e.bq2 = cc.z; e.bq1 = cc.w;
             if (kRng) { const uint4 r = S.stage[g][s][kPlanes - 1][lt]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
+            e.drew = false;
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.empty_bar[g][s]);
         } else if (valid) {
@@ -345,18 +379,28 @@ template <class SH, bool KF, bool B1, bool B2, bool D, bool M>
 cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
     constexpr int kPlanes = (B1 || B2) ? 4 : 3;
     constexpr size_t bytes = sizeof(StepSmem<SH, kPlanes>);
-    static bool configured[64] = {};                    // per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<SH, KF, B1, B2, D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        configured[dev & 63] = true;
-    }
+    static DeviceOnceFlags configured;
+    if (cudaError_t e = configure_once_per_device(configured, [] {
+            return cudaFuncSetAttribute(step_kernel<SH, KF, B1, B2, D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }))
+        return e;
     const int want = (p.n + SH::kThreads - 1) / SH::kThreads, cap = sm_count * SH::kMinBlocks;
     const int grid = want < cap ? (want > 0 ? want : 1) : cap;
+#if FG_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)SH::kThreads);
+    cfg.dynamicSmemBytes = bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, step_kernel<SH, KF, B1, B2, D, M>, p);
+#else
     step_kernel<SH, KF, B1, B2, D, M><<<grid, SH::kThreads, bytes, s>>>(p);
     return cudaSuccess;
+#endif
 }
 template <bool KF, bool B1, bool B2, bool D, bool M>
 cudaError_t launch_step(int sm_count, cudaStream_t s, const Params &p) {

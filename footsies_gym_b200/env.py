@@ -136,6 +136,8 @@ class FootsiesEnv:
         self.frame_skip = int(frame_skip)
         self.autoreset = bool(autoreset)
         self.first_env_index = int(first_env_index)
+        self._reward_table = None
+        self._load_fix = {}          # env index -> (guards last seen, guards loaded, reward-automaton index): see load_battle_state
         self.stale_intro_input = bool(stale_intro_input)
         self.skip_unactionable = bool(skip_unactionable)
         if self.skip_unactionable and self.by_example:
@@ -282,6 +284,8 @@ class FootsiesEnv:
                 opponent_action = self.opponent(self._most_recent_observation, self._most_recent_info)
             self.actions_p2.copy_(_as_bitmask(opponent_action, self.num_envs, self.device), non_blocking=True)
         _capi.check(self._lib.fg_step(self._handle, self._stream()))
+        if self._load_fix:
+            self._apply_load_fix()
         if self.frame_delay > 0:
             self._advance_delay_ring()
         obs, info = self._finish_obs()
@@ -325,6 +329,8 @@ class FootsiesEnv:
         if not self.has_reset:
             raise RuntimeError("call reset() before step()")
         _capi.check(self._lib.fg_step(self._handle, self._stream()))
+        if self._load_fix:
+            self._apply_load_fix()
         if self.frame_delay > 0:
             self._advance_delay_ring()
         obs, info = self._finish_obs()
@@ -408,12 +414,14 @@ class FootsiesEnv:
         the call is PCIe-bound, so the integer-valued observation fields travel as bytes)."""
         if self._host is None:
             n = self.num_envs
-            pin = dict(pin_memory=True)
+            # one pinned block from fg_host_alloc: its pages sit on the NUMA node of this GPU
+            blk = _capi.HostBlock(self.device.index or 0, n * (1 + 1 + 8 + 6 + 4 + 1 + 4 + 4 + 16) + 64 * 16)
             hb = dict(
-                a1=torch.zeros(n, dtype=torch.uint8, **pin), a2=torch.zeros(n, dtype=torch.uint8, **pin),
-                position=torch.zeros((n, 2), dtype=torch.float32, **pin), obs_u8=torch.zeros((n, 6), dtype=torch.uint8, **pin),
-                reward=torch.zeros(n, dtype=torch.float32, **pin), terminated=torch.zeros(n, dtype=torch.bool, **pin),
-                info_frame=torch.zeros(n, dtype=torch.int32, **pin), info_misc=torch.zeros((n, 4), dtype=torch.uint8, **pin),
+                block=blk, a1=blk.take((n,), torch.uint8), a2=blk.take((n,), torch.uint8),
+                position=blk.take((n, 2), torch.float32), obs_u8=blk.take((n, 6), torch.uint8),
+                reward=blk.take((n,), torch.float32), terminated=blk.take((n,), torch.bool),
+                info_frame=blk.take((n,), torch.int32), info_misc=blk.take((n, 4), torch.uint8),
+                packed=blk.take((n, 4), torch.int32),
                 truncated=torch.zeros(n, dtype=torch.bool))     # the reference never truncates (footsies.py:570)
             out = _capi.FgHostOutputs(struct_size=C.sizeof(_capi.FgHostOutputs), reserved0=0)
             for k in ("position", "obs_u8", "reward", "terminated", "info_frame", "info_misc"):
@@ -473,6 +481,30 @@ class FootsiesEnv:
             self.step(action, opponent_action)
             self._deliver_delayed_to_host()
             return hb["obs"], hb["reward"], hb["terminated"], hb["truncated"], hb["info"]
+        p1, p2 = self._host_action_ptrs(action, opponent_action, hb)
+        _capi.check(self._lib.fg_step_host_compact(self._handle, p1, p2, C.byref(hb["out"]), self._stream()))
+        if self._load_fix:
+            self._apply_load_fix(host_reward=hb["reward"])
+        return hb["obs"], hb["reward"], hb["terminated"], hb["truncated"], hb["info"]
+
+    def host_io_bytes_per_step(self, packed: bool = False):
+        """(host->device, device->host) bytes moved by one step_host (or step_host_packed) call."""
+        n = self.num_envs
+        h2d = n * ((0 if self.by_example else 1) + (0 if self._opponent_mode == "bot" else 1))
+        d2h = n * (16 if packed else 8 + 6 + 4 + 1 + 4 + 4)
+        return h2d, d2h
+
+    # ---- packed host layout: one 16-byte record per battle, one device->host copy per slice (fg_step_host_packed) ----
+    def packed_reward_table(self) -> torch.Tensor:
+        """float32 [128]: the reward values a packed record's 7-bit reward index stands for."""
+        if self._reward_table is None:
+            tab = np.zeros(_capi.FG_PACKED_REWARD_TABLE_SIZE, dtype=np.float32)
+            cnt = C.c_int32(0)
+            _capi.check(self._lib.fg_packed_reward_table(self._handle, C.c_void_p(tab.ctypes.data), C.byref(cnt)))
+            self._reward_table = torch.from_numpy(tab)
+        return self._reward_table
+
+    def _host_action_ptrs(self, action, opponent_action, hb):
         p1 = p2 = None
         if not self.by_example:
             a = _as_bitmask(action, self.num_envs, "cpu")
@@ -487,7 +519,6 @@ class FootsiesEnv:
             if opponent_action is None:
                 if self.opponent is None:
                     raise ValueError("opponent_action is required when the opponent is not the in-game bot")
-                # like step() and the reference (footsies.py:522-527): ask the opponent policy installed with set_opponent
                 opponent_action = self.opponent(self._most_recent_observation, self._most_recent_info)
             a = _as_bitmask(opponent_action, self.num_envs, "cpu")
             if a.data_ptr() != hb["a2"].data_ptr():
@@ -497,15 +528,51 @@ class FootsiesEnv:
                     hb["a2"].copy_(a)
             if p2 is None:
                 p2 = C.c_void_p(hb["a2"].data_ptr())
-        _capi.check(self._lib.fg_step_host_compact(self._handle, p1, p2, C.byref(hb["out"]), self._stream()))
-        return hb["obs"], hb["reward"], hb["terminated"], hb["truncated"], hb["info"]
+        return p1, p2
 
-    def host_io_bytes_per_step(self):
-        """(host->device, device->host) bytes moved by one step_host call."""
-        n = self.num_envs
-        h2d = n * ((0 if self.by_example else 1) + (0 if self._opponent_mode == "bot" else 1))
-        d2h = n * (8 + 6 + 4 + 1 + 4 + 4)
-        return h2d, d2h
+    def step_host_packed(self, action=None, opponent_action=None) -> torch.Tensor:
+        """step() for host callers in the densest lossless form: returns the pinned int32 [N, 4] tensor of
+        fg_packed_result records (position p1, position p2 as float32 bits | w0 | w1, see include/footsies_b200.h);
+        `decode_packed` turns (a slice of) it into the usual (obs, reward, terminated, info).  16 bytes per battle cross
+        the host link instead of 27.  Needs frame_skip = 1, no fused frame skipping, no frame_delay."""
+        if not self.has_reset:
+            raise RuntimeError("call reset() before step()")
+        if self.frame_delay > 0:
+            raise ValueError("the packed host layout does not carry a frame_delay queue; use step_host")
+        hb = self._host_buffers()
+        p1, p2 = self._host_action_ptrs(action, opponent_action, hb)
+        _capi.check(self._lib.fg_step_host_packed(self._handle, p1, p2, C.c_void_p(hb["packed"].data_ptr()), self._stream()))
+        return hb["packed"]
+
+    def reset_host_packed(self, *, seed: Optional[int] = None, mask=None) -> torch.Tensor:
+        hb = self._host_buffers()
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(device="cpu", dtype=torch.uint8).contiguous()
+            if m.numel() != self.num_envs:
+                raise ValueError("mask must have num_envs entries")
+        if seed is not None:
+            self.seed(seed, None if m is None else m.to(self.device))
+        _capi.check(self._lib.fg_reset_host_packed(self._handle, None if m is None else C.c_void_p(m.data_ptr()),
+                                                   C.c_void_p(hb["packed"].data_ptr()), self._stream()))
+        self.has_reset = True
+        return hb["packed"]
+
+    def decode_packed(self, packed: torch.Tensor):
+        """(obs, reward, terminated, truncated, info) from packed records [M, 4] int32 (any slice of what step_host_packed
+        returned), with the dtypes of step_host: uint8 observation fields, float32 position / reward."""
+        w0, w1 = packed[:, 2], packed[:, 3]
+        pos = packed[:, 0:2].contiguous().view(torch.float32)
+
+        def bits(w, shift, n):
+            return ((w >> shift) & ((1 << n) - 1)).to(torch.uint8)
+        obs = {"guard": torch.stack([bits(w0, 0, 2), bits(w0, 2, 2)], 1), "move": torch.stack([bits(w0, 4, 4), bits(w0, 8, 4)], 1),
+               "move_frame": torch.stack([bits(w0, 12, 6), bits(w0, 18, 6)], 1), "position": pos}
+        reward = self.packed_reward_table()[((w1 >> 10) & 127).long()]
+        terminated = ((w0 >> 24) & 1).bool()
+        frame = ((w1 >> 17) & 32767) - 1
+        info = self._make_info_dict(frame.to(torch.int32), torch.stack([bits(w0, 25, 3), bits(w0, 28, 3), bits(w1, 0, 5), bits(w1, 5, 5)], 1), obs)
+        return obs, reward, terminated, torch.zeros_like(terminated), info
 
     # ------------------------------------------------------------------ state access, statistics
     def get_state(self, first: int = 0, count: Optional[int] = None) -> np.ndarray:
@@ -533,14 +600,49 @@ class FootsiesEnv:
         """FootsiesEnv.load_battle_state (footsies.py:439-444, STATE_LOAD -> BattleCore.LoadState,
         BattleCore.cs:677-683): overwrite the fighters and the frame counter of env `index`; actors' held inputs,
         bot queues, RNG and the reward accumulator are untouched like in the game.  Accepts a FootsiesBattleState
-        or its JSON string.  One difference: the next dense reward is computed against the loaded guard bars (the
-        reference would compare with the last state it received before the load)."""
+        or its JSON string.  Like in the reference, the next dense reward compares the next state's guard bars with those
+        of the last state received BEFORE the load (footsies.py:530, 556-558); with frame_skip > 1 or the fused frame
+        skipping that one reward is computed against the loaded guard bars instead."""
         from .state import FootsiesBattleState, battle_state_into_env_state
         if isinstance(battle_state, str):
             battle_state = FootsiesBattleState.from_json(battle_state)
-        rec = self.get_state(int(index), 1)
+        index = int(index)
+        rec = self.get_state(index, 1)
+        guard_seen = rec[0]["f"]["guard"].copy()            # guard bars of the last state the agent received
+        cum_index = int(rec[0]["cum_reward_index"])
         battle_state_into_env_state(battle_state, rec[0])
-        self.set_state(rec, int(index))
+        self.set_state(rec, index)
+        if self.dense_reward and self.frame_skip == 1 and not self.skip_unactionable:
+            # footsies.py:530, 556-558: the next dense reward compares the guard bars of the next state with those of the
+            # last state RECEIVED (the Python side never learns about the load); the kernel sees guard drops as events of
+            # the frame, so the one step after a load is corrected on the host (_apply_load_fix)
+            if index in self._load_fix:
+                guard_seen, cum_index = self._load_fix[index][0], self._load_fix[index][2]
+            self._load_fix[index] = (guard_seen, rec[0]["f"]["guard"].copy(), cum_index)
+
+    def _apply_load_fix(self, host_reward=None):
+        """First step after load_battle_state: redo that step's dense reward the way the reference computes it, from the
+        guard bars before the load (see load_battle_state).  Exact float64 values from the kernel's own reward tables."""
+        from .reward_automaton import CUM_NEXT, STEP_REWARD, TERM_REWARD
+        fixes, self._load_fix = self._load_fix, {}
+        for index, (g_seen, g_loaded, cum_before) in fixes.items():
+            rec = self.get_state(index, 1)
+            if int(rec[0]["frame"]) == -1:
+                continue                                    # this step was the automatic restart: no reward
+            g_now = rec[0]["f"]["guard"]
+            code_kernel = int(g_now[0] < g_loaded[0]) | int(g_now[1] < g_loaded[1]) << 1
+            code_ref = int(g_now[0] < g_seen[0]) | int(g_now[1] < g_seen[1]) << 1
+            if code_ref == code_kernel:
+                continue
+            cum_after = CUM_NEXT[cum_before][code_ref]
+            done = bool(rec[0]["done"])
+            p2_dead = int(rec[0]["f"]["vital"][1] == 0)
+            r = TERM_REWARD[cum_after][code_ref][p2_dead] if done else STEP_REWARD[code_ref]
+            self.reward[index] = float(np.float32(r))
+            if host_reward is not None:
+                host_reward[index] = float(np.float32(r))
+            rec[0]["cum_reward_index"] = cum_after
+            self.set_state(rec, index)
 
     def episode_stats(self) -> dict:
         """Episode statistics accumulated on the device by the step kernel's warp reductions."""

@@ -175,6 +175,34 @@ int32_t fg_step_host_compact(fg_handle *h, const uint8_t *actions_p1, const uint
                              const fg_host_outputs *out, void *stream);
 int32_t fg_reset_host_compact(fg_handle *h, const uint8_t *mask, const fg_host_outputs *out, void *stream);
 
+/* ---- packed host layout: ONE 16-byte record per battle and ONE device->host copy per slice ------------------------------
+ * The host-buffer calls are bound by the host link, not by the GPU, so the bytes per battle decide their throughput:
+ * 45 (device layout) -> 27 (fg_host_outputs) -> 16 here.  Everything FootsiesEnv.step returns is in the record, losslessly:
+ *   position[2]  obs["position"] as float32, bit for bit
+ *   w0  [0:2) guard p1  [2:4) guard p2  [4:8) move index p1  [8:12) move index p2  [12:18) move_frame p1  [18:24) move_frame
+ *       p2  [24] terminated  [25:28) info p1_action mask  [28:31) info p2_action mask        (footsies.py:336-380, 555)
+ *   w1  [0:5) p1_hitstun  [5:10) p2_hitstun  [10:17) index of the reward in the table fg_packed_reward_table returns
+ *       (the dense reward only ever takes a few dozen distinct float32 values: +-0.3 steps and the terminal
+ *       compensations of footsies.py:388-405)  [17:32) info frame + 1, saturating at 32767 (frame -1 = reset -> 0)
+ * Needs frame_skip = 1, no fused frame skipping (their summed rewards are not table values) and no frame_delay. */
+typedef struct {
+    float position[2];
+    uint32_t w0, w1;
+} fg_packed_result;
+#define FG_PACKED_REWARD_TABLE_SIZE 128
+/* table[i] for i < *count are the float32 rewards a record can carry, in ascending order (count <= 128). */
+int32_t fg_packed_reward_table(fg_handle *h, float *table, int32_t *count);
+/* fg_step_host / fg_reset_host delivering packed records to out[num_envs] (HOST memory, pinned for full link speed).
+ * Large batches are pipelined in slices like fg_step_host_compact; each slice is one contiguous copy. */
+int32_t fg_step_host_packed(fg_handle *h, const uint8_t *actions_p1, const uint8_t *actions_p2, fg_packed_result *out,
+                            void *stream);
+int32_t fg_reset_host_packed(fg_handle *h, const uint8_t *mask, fg_packed_result *out, void *stream);
+/* Pinned host memory placed on the NUMA node of the GPU (the calling thread is bound to that node's CPUs while the pages
+ * are allocated and first touched, then gets its affinity back): device<->host copies then stay on the socket the GPU
+ * hangs off.  Returns NULL on failure (fg_last_error).  Free with fg_host_free. */
+void *fg_host_alloc(int32_t device, uint64_t bytes);
+void fg_host_free(void *p);
+
 /* Replaces: the frame_delay queue of FootsiesEnv (footsies.py:129-131, 502-504, 533-535) for all envs: pushes the state
  * the last fg_step / fg_reset wrote to the bound obs / info buffers into slot `pos` of a ring of depth = frame_delay + 1
  * slots (into every slot for envs that step just reset) and emits the oldest slot, (pos + 1) % depth, to out_*.  The

@@ -1107,10 +1107,10 @@ void fo_load_battle_state(fo_batch *b, int32_t env, const fo_battle_state *in) {
         f->hasWon = s->hasWon;
     }
     e->frameCount = in->frameCount;
-    /* test convenience (not in the reference, whose Python side only learns about the load from the next state it
-     * receives, so that its next dense reward compares guard bars across the load): make the loaded state the
-     * "previous state" of the next step and refresh the trace so that fo_get_trace shows the loaded fighters */
-    e->current_state = GetEnvironmentState(e);
+    /* FootsiesEnv._current_state is NOT touched: the Python side only learns about the load from the next state it
+     * receives, so its next dense reward compares guard bars across the load (footsies.py:530, 556-558).
+     * Test convenience (not in the reference): refresh has_terminated and the trace so that fo_get_trace shows the loaded
+     * fighters. */
     e->has_terminated = f_isDead(&e->fighter[0]) || f_isDead(&e->fighter[1]);
     fill_fighter_state(&e->fighter[0], &e->last.f[0]);
     fill_fighter_state(&e->fighter[1], &e->last.f[1]);

@@ -108,8 +108,11 @@ def test_compact_mapping_preserves_behaviour(oracle):
             assert np.array_equal(ta[f], tb[f]), f"frame {t}: {f}"
         # the terminal dense reward compensates the episode's accumulated reward, which is Python-side state and
         # not part of a battle state (footsies.py:399-403): compare the per-step part only
+        # ... and not on the first step after the load, where the reference compares the guard bars with those of the last
+        # state b's agent had received before the load (footsies.py:530, 556-558)
         live = ~ta["terminated"].astype(bool)
-        assert np.array_equal(ta["reward"][live], tb["reward"][live]), f"frame {t}: reward"
+        if t > stop:
+            assert np.array_equal(ta["reward"][live], tb["reward"][live]), f"frame {t}: reward"
         compared += int(alive.sum())
     assert compared > 3000
 
@@ -254,5 +257,45 @@ def test_oracle_save_then_gpu_follows(oracle):
             assert np.array_equal(ks["f"][f][alive], orc.trace["f"][f][alive]), f"frame {t}: {f}"
         assert np.array_equal(env.obs.cpu().numpy()[alive], orc.trace["obs"][alive])
         live = alive & ~orc.trace["terminated"].astype(bool)
-        assert np.array_equal(env.reward.cpu().numpy()[live], orc.trace["reward"][live])
+        if t > warm:          # the step after the load is rewarded against the guard bars the env's agent saw before it
+            assert np.array_equal(env.reward.cpu().numpy()[live], orc.trace["reward"][live])
     assert alive.sum() > 0
+
+
+@pytest.mark.gpu
+def test_dense_reward_across_a_load_follows_the_reference(oracle):
+    """footsies.py:530, 556-558: the reward of the step after load_battle_state compares the new guard bars with those of
+    the last state received BEFORE the load, and the cumulative reward of the episode runs on.  GPU env and oracle live the
+    same life, both load the same earlier state in mid-episode; every reward afterwards (terminal ones included) agrees."""
+    import torch
+    from footsies_gym_b200 import FootsiesEnv
+    n, steps = 96, 700
+    rng = np.random.default_rng(79)
+    env = FootsiesEnv(num_envs=n, device="cuda:0", opponent="self_play", seed=0, autoreset=False)
+    orc = oracle.OracleBatch(n, p2_bot=False, seed=0, autoreset=False)
+    env.reset()
+    orc.reset()
+    t1 = sticky_tape(rng, steps, n)
+    t2 = sticky_tape(rng, steps, n)
+    saved, loads, differing = {}, 0, 0
+    for t in range(steps):
+        env.step(torch.from_numpy(t1[t]), torch.from_numpy(t2[t]))
+        orc.step(t1[t], t2[t])
+        assert np.array_equal(env.reward.cpu().numpy(), orc.trace["reward"]), f"step {t}"
+        assert np.array_equal(env.terminated.cpu().numpy().astype(np.int32), orc.trace["terminated"]), f"step {t}"
+        assert np.array_equal(env.get_state()["f"]["guard"], orc.trace["f"]["guard"]), f"step {t}"
+        live = ~orc.trace["terminated"].astype(bool)
+        if t % 45 == 10:                              # remember an early state of every running battle ...
+            for i in np.flatnonzero(live):
+                saved.setdefault(int(i), orc.save_battle_state(int(i)))
+        if t % 45 == 40:                              # ... and throw the battle back to it later in the same episode
+            for i in np.flatnonzero(live):
+                st = saved.pop(int(i), None)
+                if st is None:
+                    continue
+                now = orc.trace["f"]["guard"][i]
+                differing += int(st["p1State"]["guardHealth"] != now[0] or st["p2State"]["guardHealth"] != now[1])
+                env.load_battle_state(json.dumps(st), int(i))
+                orc.load_battle_state(int(i), st)
+                loads += 1
+    assert loads > 50 and differing > 5 and int(orc.trace["terminated"].sum()) > 10

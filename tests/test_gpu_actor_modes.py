@@ -130,7 +130,8 @@ def test_frame_delay_on_the_host_buffer_path(oracle):
     env.close()
 
 
-def test_frame_skipped_wrapper_over_a_delayed_batch(oracle):
+@pytest.mark.parametrize("autoreset", [False, True])
+def test_frame_skipped_wrapper_over_a_delayed_batch(oracle, autoreset):
     """FootsiesFrameSkipped(FootsiesEnv(num_envs > 1, frame_delay = 3)): the wrapper's loop of masked steps must leave the
     frame_delay queue of the battles it holds back untouched (the reference keeps one deque per env, footsies.py:129-131,
     533-535).  Checked against one CPU oracle per battle driven by the reference wrapper's own loop
@@ -141,9 +142,9 @@ def test_frame_skipped_wrapper_over_a_delayed_batch(oracle):
     dev = _cuda()
     n, steps, delay = 96, 260, 3
     rng = np.random.default_rng(41)
-    env = FootsiesFrameSkipped(FootsiesEnv(num_envs=n, device=dev, frame_delay=delay, seed=6, autoreset=False))
+    env = FootsiesFrameSkipped(FootsiesEnv(num_envs=n, device=dev, frame_delay=delay, seed=6, autoreset=autoreset))
     assert not env.fused
-    orcs = [oracle.OracleBatch(1, p2_bot=True, frame_delay=delay, seed=6, first_env_index=i, autoreset=False) for i in range(n)]
+    orcs = [oracle.OracleBatch(1, p2_bot=True, frame_delay=delay, seed=6, first_env_index=i, autoreset=autoreset) for i in range(n)]
     obs, info = env.reset()
     for o in orcs:
         o.reset()
@@ -154,7 +155,7 @@ def test_frame_skipped_wrapper_over_a_delayed_batch(oracle):
         obs, reward, term, trunc, info = env.step(torch.from_numpy(tape[t]))
         exp_obs, exp_rew, exp_term, exp_frame = [], [], [], []
         for i, o in enumerate(orcs):
-            if o.trace["terminated"][0]:                       # autoreset off: a finished battle stays as it is
+            if o.trace["terminated"][0] and not autoreset:     # autoreset off: a finished battle stays as it is
                 tr, total = o.trace, 0.0
             else:
                 tr = o.step(tape[t, i:i + 1])
@@ -173,4 +174,64 @@ def test_frame_skipped_wrapper_over_a_delayed_batch(oracle):
         live = ~np.asarray([bool(o.trace["terminated"][0]) and False for o in orcs])
         assert np.abs(reward.cpu().numpy().astype(np.float64)[live] - np.asarray(exp_rew)[live]).max() <= 1e-6, t
     assert held_back > steps
+    env.close()
+
+
+@pytest.mark.parametrize("dense,p2_bot", [(True, True), (False, True), (True, False)])
+def test_packed_host_layout_is_lossless(oracle, monkeypatch, dense, p2_bot):
+    """fg_step_host_packed / fg_reset_host_packed: one 16-byte record per battle (include/footsies_b200.h).  Decoding the
+    records gives exactly what the CPU oracle says FootsiesEnv.step returns -- observation, reward (through the reward
+    table), termination, info -- for a batch large enough to be cut into pipelined slices, masked resets included."""
+    from footsies_gym_b200 import FootsiesEnv
+    import parity_cases as pc
+    dev = _cuda()
+    n, steps = 3 * 1024 * 1024 // 8 + 77, 260
+    monkeypatch.setenv("FOOTSIES_B200_HOST_CHUNK_ENVS", "131072")      # four pipelined slices, the last one ragged
+    rng = np.random.default_rng(12)
+    env = FootsiesEnv(num_envs=n, device=dev, dense_reward=dense, opponent=None if p2_bot else "self_play", seed=9)
+    orc = oracle.OracleBatch(n, p2_bot=p2_bot, dense_reward=dense, seed=9, threads=8)
+    keys = ("guard", "move", "move_frame", "position")
+
+    def check(packed, where):
+        assert packed.dtype == torch.int32 and tuple(packed.shape) == (n, 4) and not packed.is_cuda and packed.is_pinned()
+        obs, reward, term, trunc, info = env.decode_packed(packed)
+        got = np.concatenate([obs[k].numpy().astype(np.float32) for k in keys], 1)
+        assert np.array_equal(got, orc.trace["obs"]), where
+        assert np.array_equal(reward.numpy(), orc.trace["reward"]), where
+        assert np.array_equal(term.numpy().astype(np.int32), orc.trace["terminated"]), where
+        assert np.array_equal(info["frame"].numpy(), orc.trace["info_frame"]), where
+        assert np.array_equal(np.stack([info[k].numpy() for k in ("p1_action", "p2_action")], 1), orc.trace["info_action"]), where
+        assert np.array_equal(np.stack([info[k].numpy() for k in ("p1_hitstun", "p2_hitstun")], 1), orc.trace["info_hitstun"]), where
+        assert not bool(trunc.any())
+    orc.reset()
+    check(env.reset_host_packed(), "reset")
+    t1 = pc.tape_sticky(rng, steps, n, p_change=0.25)
+    t2 = pc.tape_sticky(rng, steps, n, p_change=0.25)
+    for t in range(steps):
+        a2 = None if p2_bot else t2[t]
+        orc.step(t1[t], a2)
+        check(env.step_host_packed(t1[t], a2), f"step {t}")
+        if t == 120:
+            mask = rng.random(n) < 0.2
+            orc.seed(33, mask)
+            orc.reset(mask)
+            check(env.reset_host_packed(seed=33, mask=mask), "masked reset")
+    tab = env.packed_reward_table()
+    assert tab.numel() == 128 and bool((tab[:10].diff() > 0).all())
+    assert env.host_io_bytes_per_step(packed=True) == (n * (1 if p2_bot else 2), n * 16)
+    env.close()
+
+
+def test_packed_host_layout_refuses_what_it_cannot_carry():
+    from footsies_gym_b200 import FootsiesEnv, _capi
+    dev = _cuda()
+    env = FootsiesEnv(num_envs=64, device=dev, frame_skip=4, seed=0)
+    env.reset()
+    with pytest.raises(_capi.FootsiesLibraryError):
+        env.step_host_packed(np.zeros(64, np.uint8))
+    env.close()
+    env = FootsiesEnv(num_envs=64, device=dev, frame_delay=2, seed=0)
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step_host_packed(np.zeros(64, np.uint8))
     env.close()

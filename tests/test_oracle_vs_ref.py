@@ -165,7 +165,9 @@ def test_save_load_battle_state_through_the_games_own_commands():
         a1, a2 = t1[t], t2[t]
         o.step(a1, a2)
         r.step(a1, a2)
-        for name in ("f", "frame", "obs", "terminated", "battle_over"):
+        # reward included: after a load both engines reward the next step against the guard bars the agent saw last
+        # (footsies.py:530, 556-558), and the episode's cumulative reward runs on across the load
+        for name in ("f", "frame", "obs", "terminated", "battle_over", "reward", "reward_f64"):
             assert o.trace[name].tobytes() == r.trace[name].tobytes(), (t, name)
 
 
