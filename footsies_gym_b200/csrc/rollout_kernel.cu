@@ -212,6 +212,7 @@ static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
     constexpr int E4 = H <= 64 ? 4 : 2;                                  // H = 128: 4 battles per lane do not fit the registers
     if (rp.p2_policy)       // two weight sets in shared memory: always 2 battles per lane
         return launch_rollout_v<H, 2, kPolicyWarps, DENSE, true>(s, rp);
+    if (e == 1) return launch_rollout_v<H, 1, kPolicyWarps, DENSE, false>(s, rp);
     return e == 4 ? launch_rollout_v<H, E4, kPolicyWarps, DENSE, false>(s, rp) : launch_rollout_v<H, 2, kPolicyWarps, DENSE, false>(s, rp);
 }
 

@@ -137,7 +137,7 @@ class FootsiesEnv:
         self.autoreset = bool(autoreset)
         self.first_env_index = int(first_env_index)
         self._reward_table = None
-        self._load_fix = {}          # env index -> (guards last seen, guards loaded, reward-automaton index): see load_battle_state
+        self._load_fix = {}          # env index -> {"cum", "guard"}: battles whose reward is host-tracked after a load
         self.stale_intro_input = bool(stale_intro_input)
         self.skip_unactionable = bool(skip_unactionable)
         if self.skip_unactionable and self.by_example:
@@ -601,8 +601,9 @@ class FootsiesEnv:
         BattleCore.cs:677-683): overwrite the fighters and the frame counter of env `index`; actors' held inputs,
         bot queues, RNG and the reward accumulator are untouched like in the game.  Accepts a FootsiesBattleState
         or its JSON string.  Like in the reference, the next dense reward compares the next state's guard bars with those
-        of the last state received BEFORE the load (footsies.py:530, 556-558); with frame_skip > 1 or the fused frame
-        skipping that one reward is computed against the loaded guard bars instead."""
+        of the last state received BEFORE the load and the episode's cumulative reward runs on across it (footsies.py:530,
+        556-558): the rewards of a loaded battle are recomputed on the host until its episode ends.  With frame_skip > 1 or
+        the fused frame skipping the kernel's own value is kept (it compares with the loaded guard bars)."""
         from .state import FootsiesBattleState, battle_state_into_env_state
         if isinstance(battle_state, str):
             battle_state = FootsiesBattleState.from_json(battle_state)
@@ -613,36 +614,39 @@ class FootsiesEnv:
         battle_state_into_env_state(battle_state, rec[0])
         self.set_state(rec, index)
         if self.dense_reward and self.frame_skip == 1 and not self.skip_unactionable:
-            # footsies.py:530, 556-558: the next dense reward compares the guard bars of the next state with those of the
-            # last state RECEIVED (the Python side never learns about the load); the kernel sees guard drops as events of
-            # the frame, so the one step after a load is corrected on the host (_apply_load_fix)
-            if index in self._load_fix:
-                guard_seen, cum_index = self._load_fix[index][0], self._load_fix[index][2]
-            self._load_fix[index] = (guard_seen, rec[0]["f"]["guard"].copy(), cum_index)
+            # footsies.py:530, 556-558: the Python side never learns about the load -- its next dense reward compares the
+            # guard bars of the next state with those of the last state RECEIVED, and its cumulative episode reward runs on
+            # (possibly past what one round can reach, which is all the kernel's 13-value reward automaton covers).  From
+            # here to the end of this episode the battle's reward is therefore recomputed on the host in Python float
+            # arithmetic, exactly like the reference does (_apply_load_fix); a handful of battles, never the hot path.
+            from .reward_automaton import CUM_VALUES
+            if index not in self._load_fix:
+                self._load_fix[index] = {"cum": float(CUM_VALUES[cum_index]), "guard": (int(guard_seen[0]), int(guard_seen[1]))}
 
     def _apply_load_fix(self, host_reward=None):
-        """First step after load_battle_state: redo that step's dense reward the way the reference computes it, from the
-        guard bars before the load (see load_battle_state).  Exact float64 values from the kernel's own reward tables."""
-        from .reward_automaton import CUM_NEXT, STEP_REWARD, TERM_REWARD
-        fixes, self._load_fix = self._load_fix, {}
-        for index, (g_seen, g_loaded, cum_before) in fixes.items():
-            rec = self.get_state(index, 1)
-            if int(rec[0]["frame"]) == -1:
-                continue                                    # this step was the automatic restart: no reward
-            g_now = rec[0]["f"]["guard"]
-            code_kernel = int(g_now[0] < g_loaded[0]) | int(g_now[1] < g_loaded[1]) << 1
-            code_ref = int(g_now[0] < g_seen[0]) | int(g_now[1] < g_seen[1]) << 1
-            if code_ref == code_kernel:
+        """Battles that went through load_battle_state: FootsiesEnv._get_dense_reward (footsies.py:388-405) in Python floats
+        on the guard bars before / after this step, until the episode ends."""
+        for index in list(self._load_fix):
+            tr = self._load_fix[index]
+            rec = self.get_state(index, 1)[0]
+            if int(rec["frame"]) == -1:
+                del self._load_fix[index]                  # the battle was restarted: the kernel's accumulator starts afresh
                 continue
-            cum_after = CUM_NEXT[cum_before][code_ref]
-            done = bool(rec[0]["done"])
-            p2_dead = int(rec[0]["f"]["vital"][1] == 0)
-            r = TERM_REWARD[cum_after][code_ref][p2_dead] if done else STEP_REWARD[code_ref]
-            self.reward[index] = float(np.float32(r))
+            g_now = (int(rec["f"]["guard"][0]), int(rec["f"]["guard"][1]))
+            reward = 0.0
+            if g_now[0] < tr["guard"][0]:
+                reward -= 0.3
+            if g_now[1] < tr["guard"][1]:
+                reward += 0.3
+            tr["cum"] += reward
+            tr["guard"] = g_now
+            if bool(rec["done"]):
+                reward += (1 if int(rec["f"]["vital"][1]) == 0 else -1) - tr["cum"]
+                del self._load_fix[index]
+            r32 = float(np.float32(reward))
+            self.reward[index] = r32
             if host_reward is not None:
-                host_reward[index] = float(np.float32(r))
-            rec[0]["cum_reward_index"] = cum_after
-            self.set_state(rec, index)
+                host_reward[index] = r32
 
     def episode_stats(self) -> dict:
         """Episode statistics accumulated on the device by the step kernel's warp reductions."""
