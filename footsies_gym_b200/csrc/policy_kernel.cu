@@ -15,6 +15,7 @@
 
 #include "../../include/footsies_b200.h"
 #include "policy_mlp.cuh"
+#include "policy_mma.cuh"
 
 namespace {
 
@@ -75,6 +76,51 @@ __global__ void __launch_bounds__(kPolThreads) policy_mlp_sample_kernel(const Po
     }
 }
 
+// The same policy step on the tensor-core path (policy_mma.cuh) for H <= 64: a warp owns 32 battles for the whole forward
+// pass; the CTA's warps share nothing but the staged weight fragments.  Persistent: every warp walks groups of 32 battles.
+constexpr int kMmaWarps = 4;
+template <int H>
+struct PolicyMmaKernelSmem {
+    static constexpr size_t kObs = (PolicyMmaSmem<H>::kBytes + 15) / 16 * 16;             // float [kMmaWarps][32][8]
+    static constexpr size_t kLogits = kObs + sizeof(float) * kMmaWarps * 256;
+    static constexpr size_t kBytes = kLogits + sizeof(float) * kMmaWarps * 256;
+};
+template <int H, bool MIRROR>
+__global__ void __launch_bounds__(32 * kMmaWarps) policy_mma_sample_kernel(const PolicyParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sm = reinterpret_cast<float *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *obs_w = reinterpret_cast<float *>(smem_raw + PolicyMmaKernelSmem<H>::kObs) + warp * 256;
+    float *lg_w = reinterpret_cast<float *>(smem_raw + PolicyMmaKernelSmem<H>::kLogits) + warp * 256;
+    policy_mma_stage<H>(sm, p.w, tid, 32 * kMmaWarps);
+    __syncthreads();
+    const unsigned long long counter = p.counter + (p.counter_base ? *p.counter_base : 0ull);
+    for (int base = (blockIdx.x * kMmaWarps + warp) * 32; base < p.n; base += gridDim.x * kMmaWarps * 32) {
+        const int env = base + lane;
+        const bool valid = env < p.n;
+        const float4 a = valid ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env] : make_float4(0, 0, 0, 0);
+        const float4 b = valid ? reinterpret_cast<const float4 *>(p.obs)[2 * (size_t)env + 1] : make_float4(0, 0, 0, 0);
+        if (valid && p.obs_copy) {
+            reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env] = a;
+            reinterpret_cast<float4 *>(p.obs_copy)[2 * (size_t)env + 1] = b;
+        }
+        __syncwarp();                                           // the previous group's fragment loads are done
+        reinterpret_cast<float4 *>(obs_w)[2 * lane] = a;
+        reinterpret_cast<float4 *>(obs_w)[2 * lane + 1] = b;
+        __syncwarp();
+        policy_mma_logits<H, 2, MIRROR>(sm, obs_w, lg_w, lane);
+        if (valid) {
+            const float4 l0 = reinterpret_cast<const float4 *>(lg_w)[2 * lane], l1 = reinterpret_cast<const float4 *>(lg_w)[2 * lane + 1];
+            const float lg[8] = { l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w };
+            float lp;
+            int act = policy_sample(lg, hash3(p.seed, counter, (uint64_t)(p.first_env + env)), lp);
+            if (MIRROR) act = policy_mirror_action(act);
+            p.actions[env] = (uint8_t)act;
+            if (p.logp) p.logp[env] = lp;
+        }
+    }
+}
+
 thread_local char g_perr[256] = "";
 
 }  // namespace
@@ -106,6 +152,25 @@ static int32_t policy_sample_impl(const float *obs, const float *scale, const fl
                                       : PolicySmemBcast<128, kPolEnvs, kPolicyWarps>::kBytes;
     cudaError_t e = cudaSuccess;
     cudaStream_t s = (cudaStream_t)stream;
+    if (hidden <= kMmaMaxHidden) {                  // tensor-core path (policy_mma.cuh)
+        int mgrid = (num_envs + 32 * kMmaWarps - 1) / (32 * kMmaWarps);
+        if (mgrid > sms * 4) mgrid = sms * 4;
+#define FG_POLICY_MMA_LAUNCH(HH, MM) do { \
+        constexpr size_t mbytes = PolicyMmaKernelSmem<HH>::kBytes; \
+        static fg::DeviceOnceFlags configured; \
+        e = fg::configure_once_per_device(configured, [] { \
+            return cudaFuncSetAttribute(policy_mma_sample_kernel<HH, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mbytes); }); \
+        if (e == cudaSuccess) policy_mma_sample_kernel<HH, MM><<<mgrid, 32 * kMmaWarps, mbytes, s>>>(p); } while (0)
+        if (hidden == 32) { if (mirror) FG_POLICY_MMA_LAUNCH(32, true); else FG_POLICY_MMA_LAUNCH(32, false); }
+        else { if (mirror) FG_POLICY_MMA_LAUNCH(64, true); else FG_POLICY_MMA_LAUNCH(64, false); }
+#undef FG_POLICY_MMA_LAUNCH
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            snprintf(g_perr, sizeof g_perr, "fg_policy_mlp_sample: %s", cudaGetErrorString(e));
+            return FG_ERR_CUDA;
+        }
+        return FG_OK;
+    }
 #define FG_POLICY_LAUNCH(HH) do { \
         static fg::DeviceOnceFlags configured; \
         e = fg::configure_once_per_device(configured, [bytes] { \

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "rollout_kernel.h"
+#include "policy_mma.cuh"
 
 namespace fgk {
 
@@ -186,6 +187,183 @@ __global__ void __launch_bounds__(32 * W) rollout_kernel(const RolloutParams rp)
     if (tid < FG_STAT_COUNT && s_stats[tid]) atomicAdd(&p.stats[tid], s_stats[tid]);
 }
 
+// ---- tensor-core version (H <= 64): every WARP owns 16 MT battles for the whole horizon -- policy (policy_mma.cuh: mma.sync
+// m16n8k8 with the 3 x TF32 split, activations never leave the registers between layers) and simulator alike -- so the
+// horizon loop contains no CTA barrier at all: warps drift apart and one warp's simulator phase overlaps its neighbours'
+// tensor-core phases.  MT = 2: 32 battles per warp, every lane simulates one; MT = 1: 16 battles per warp (lanes 16-31 only
+// feed the MMA), twice the warps per SM -- what a batch of 16 384 battles (111 per SM) needs to keep two warps per scheduler.
+template <int H, int W, bool P2POL>
+struct RolloutMmaSmem {
+    using PL = PolicyMmaSmem<H>;
+    static constexpr size_t kTables = 0;
+    static constexpr size_t kPolicy = (sizeof(Tables) + 127) / 128 * 128;
+    static constexpr size_t kPolicy2 = kPolicy + (PL::kBytes + 15) / 16 * 16;
+    static constexpr size_t kObs = kPolicy2 + (P2POL ? (PL::kBytes + 15) / 16 * 16 : 0);      // float [W][32][8]
+    static constexpr size_t kLogits = kObs + sizeof(float) * W * 256;                        // float [W][32][8]
+    static constexpr size_t kStats = kLogits + sizeof(float) * W * 256;
+    static constexpr size_t kBytes = kStats + sizeof(unsigned long long) * FG_STAT_COUNT;
+};
+
+template <int H, int W, int MT, bool DENSE, bool P2POL, bool SKIP>
+__global__ void __launch_bounds__(32 * W) rollout_mma_kernel(const RolloutParams rp) {
+    using SM = RolloutMmaSmem<H, W, P2POL>;
+    constexpr bool kP2Bot = !P2POL;
+    constexpr int kWarpEnvs = 16 * MT, kEnvs = kWarpEnvs * W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Tables &Tw = *reinterpret_cast<Tables *>(smem_raw + SM::kTables);
+    const Tables &T = Tw;
+    float *pw = reinterpret_cast<float *>(smem_raw + SM::kPolicy);
+    float *pw2 = reinterpret_cast<float *>(smem_raw + SM::kPolicy2);
+    unsigned long long *s_stats = reinterpret_cast<unsigned long long *>(smem_raw + SM::kStats);
+    const Params &p = rp.sim;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *obs_w = reinterpret_cast<float *>(smem_raw + SM::kObs) + warp * 256;      // this warp's observation rows
+    float *lg_w = reinterpret_cast<float *>(smem_raw + SM::kLogits) + warp * 256;    // ... and logits
+    const int n = p.n, horizon = rp.horizon;
+    const int i = blockIdx.x * kEnvs + warp * kWarpEnvs + lane;                      // one battle per simulating lane
+    const bool valid = lane < kWarpEnvs && i < n;
+
+    load_tables(&Tw, p.tables);
+    policy_mma_stage<H>(pw, rp.w, tid, 32 * W);
+    if (P2POL) policy_mma_stage<H>(pw2, rp.w_p2, tid, 32 * W);
+    if (tid < FG_STAT_COUNT) s_stats[tid] = 0ull;
+    Env e;
+    if (valid) load_env<kP2Bot>(p, i, e);
+    {
+        // the observation the first step acts on: the last one of the previous horizon, carried over into slot 0
+        float4 a = make_float4(0, 0, 0, 0), b = a;
+        if (valid) {
+            const size_t src = ((size_t)horizon * n + i) * 2;
+            a = rp.obs[src]; b = rp.obs[src + 1];
+            rp.obs[(size_t)i * 2] = a; rp.obs[(size_t)i * 2 + 1] = b;
+        }
+        reinterpret_cast<float4 *>(obs_w)[2 * lane] = a; reinterpret_cast<float4 *>(obs_w)[2 * lane + 1] = b;
+    }
+    __syncthreads();                                            // tables, weight fragments, statistics: the only CTA barrier before the end
+    const unsigned long long drawn = rp.counter_base ? *rp.counter_base : 0ull;
+    StatAcc acc = { 0u, 0u, 0u, 0u };
+    uint32_t frames_since_flush = 0u;
+    const int K = p.frame_skip;
+
+    for (int t = 0; t < horizon; t++) {
+        // ---- policy: the warp's battles through the MLP on the tensor cores, then one lane per battle samples ----
+        policy_mma_logits<H, MT, false>(pw, obs_w, lg_w, lane);
+        uint32_t in1 = 0u, in2 = 0u;
+        if (valid) {
+            const float4 l0 = reinterpret_cast<const float4 *>(lg_w)[2 * lane], l1 = reinterpret_cast<const float4 *>(lg_w)[2 * lane + 1];
+            const float lg[8] = { l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w };
+            float lp;
+            in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)), lp);
+            rp.actions[(size_t)t * n + i] = (uint8_t)in1;
+            rp.logp[(size_t)t * n + i] = lp;
+        }
+        if (P2POL) {
+            if (rp.p2_mirror) policy_mma_logits<H, MT, true>(pw2, obs_w, lg_w, lane);
+            else policy_mma_logits<H, MT, false>(pw2, obs_w, lg_w, lane);
+            if (valid) {
+                const float4 l0 = reinterpret_cast<const float4 *>(lg_w)[2 * lane], l1 = reinterpret_cast<const float4 *>(lg_w)[2 * lane + 1];
+                const float lg[8] = { l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w };
+                float lp;
+                int a2 = policy_sample(lg, hash3(rp.seed_p2, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)), lp);
+                if (rp.p2_mirror) a2 = policy_mirror_action(a2);
+                in2 = (uint32_t)a2;
+                rp.actions_p2[(size_t)t * n + i] = (uint8_t)a2;
+                rp.logp_p2[(size_t)t * n + i] = lp;
+            }
+        }
+        // ---- FootsiesEnv.step for the warp's battles (same order of events as step_kernel) ----
+        double reward = 0.0;
+        bool terminal = false, ran = false;
+        if (valid) {
+            if ((e.misc >> FGM_DONE_SHIFT) & 1u) {                      // next-step autoreset: this step only resets
+                reset_env<false, kP2Bot>(T, e, p.stale_intro != 0);
+                acc.s += 0x10000u;
+            } else {
+                ran = true;
+                if (kP2Bot) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                for (int kk = 0; kk < K; kk++) {
+                    if (!terminal) {
+                        simulate_frame<false, kP2Bot, DENSE, false>(T, e, in1, in2, reward, terminal, acc);
+                        acc.s += 1u << 24;
+                        if (kP2Bot) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                    }
+                }
+            }
+        }
+        if (SKIP) {                                                     // fused FootsiesFrameSkipped, exactly as in step_kernel
+            bool more = ran && !terminal && obs_is_skippable(e);
+            while (__any_sync(kFull, more)) {
+                for (int kk = 0; kk < K; kk++) {
+                    if (more && !terminal) {
+                        simulate_frame<false, kP2Bot, DENSE, false>(T, e, 0u, in2, reward, terminal, acc);
+                        acc.s += 1u << 24;
+                        if (kP2Bot) in2 = (e.misc >> FGM_ACTOR2_SHIFT) & 7u;
+                    }
+                }
+                more = more && !terminal && obs_is_skippable(e);
+                frames_since_flush += (uint32_t)K;
+                if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, s_stats, lane); frames_since_flush = 0u; }
+            }
+        }
+        if (valid) {
+            StepOutputs o;
+            make_outputs(e, o);
+            const float4 a = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]), b = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
+            const size_t dst = ((size_t)(t + 1) * n + i) * 2;
+            rp.obs[dst] = a; rp.obs[dst + 1] = b;
+            rp.rewards[(size_t)t * n + i] = (float)reward;
+            rp.dones[(size_t)t * n + i] = terminal ? 1 : 0;
+            reinterpret_cast<float4 *>(obs_w)[2 * lane] = a; reinterpret_cast<float4 *>(obs_w)[2 * lane + 1] = b;
+            if (t == horizon - 1) { p.info_frame[i] = e.frame; p.info_misc[i] = o.info_misc; }
+        }
+        frames_since_flush += (uint32_t)K;                              // uniform across the warp
+        if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, s_stats, lane); frames_since_flush = 0u; }
+        __syncwarp();                                                   // observation rows are in place for the next policy pass
+    }
+    if (valid) store_env<kP2Bot>(p, i, e);
+    flush_stats(acc, s_stats, lane);
+    __syncthreads();
+    if (tid < FG_STAT_COUNT && s_stats[tid]) atomicAdd(&p.stats[tid], s_stats[tid]);
+}
+
+template <int H, int W, int MT, bool DENSE, bool P2POL, bool SKIP>
+static cudaError_t launch_rollout_mma_s(cudaStream_t s, const RolloutParams &rp) {
+    constexpr size_t bytes = RolloutMmaSmem<H, W, P2POL>::kBytes;
+    static fg::DeviceOnceFlags configured;
+    if (cudaError_t e = fg::configure_once_per_device(configured, [] {
+            return cudaFuncSetAttribute(rollout_mma_kernel<H, W, MT, DENSE, P2POL, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }))
+        return e;
+    constexpr int kEnvs = 16 * MT * W;
+    const int grid = (rp.sim.n + kEnvs - 1) / kEnvs;
+    rollout_mma_kernel<H, W, MT, DENSE, P2POL, SKIP><<<grid, 32 * W, bytes, s>>>(rp);
+    return cudaSuccess;
+}
+template <int H, int W, bool DENSE>
+static cudaError_t launch_rollout_mma_w(int mt, cudaStream_t s, const RolloutParams &rp) {
+    const bool skip = rp.sim.skip_unactionable != 0;
+#define FG_MMA_GO(MT, P2, SK) launch_rollout_mma_s<H, W, MT, DENSE, P2, SK>(s, rp)
+    if (rp.p2_policy) {
+        if (mt == 1) return skip ? FG_MMA_GO(1, true, true) : FG_MMA_GO(1, true, false);
+        return skip ? FG_MMA_GO(2, true, true) : FG_MMA_GO(2, true, false);
+    }
+    if (mt == 1) return skip ? FG_MMA_GO(1, false, true) : FG_MMA_GO(1, false, false);
+    return skip ? FG_MMA_GO(2, false, true) : FG_MMA_GO(2, false, false);
+#undef FG_MMA_GO
+}
+template <int H, bool DENSE>
+static cudaError_t launch_rollout_mma(cudaStream_t s, const RolloutParams &rp) {
+    // Measured (profiles/r02f_rollout_mma.log, H = 64, us per step, 16-battle / 32-battle warps / round-1 FFMA2 kernel):
+    // 16 384 battles 4.49 / 5.90 / 6.37; 131 072: 28.0 / 31.3 / -; 1 Mi: 216 / 227 / 262 -- more, lighter warps hide the
+    // simulator's latency under the neighbours' tensor-core phases at every size, so 16-battle warps are the default
+    // (developer knob: FOOTSIES_B200_ROLLOUT_MT = 1 | 2).
+    int mt = 1;
+    if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_MT")) mt = atoi(v) == 2 ? 2 : 1;
+    // (7-warp CTAs, which would spread 16 384 battles evenly as 147 x 112, measured 4.55 us per step against 4.46 for 4 warps.)
+    // Two policies (self-play): 32-battle warps from 131 072 battles up (1 Mi: 479 us per step against 567).
+    if (rp.p2_policy && rp.sim.n >= 131072 && !getenv("FOOTSIES_B200_ROLLOUT_MT")) mt = 2;
+    return launch_rollout_mma_w<H, 4, DENSE>(mt, s, rp);
+}
+
 template <int H, int E, int W, bool DENSE, bool P2POL, bool SKIP>
 static cudaError_t launch_rollout_s(cudaStream_t s, const RolloutParams &rp) {
     constexpr size_t bytes = RolloutSmem<H, E, W, P2POL>::kBytes;
@@ -205,6 +383,9 @@ static cudaError_t launch_rollout_v(cudaStream_t s, const RolloutParams &rp) {
 
 template <int H, bool DENSE>
 static cudaError_t launch_rollout_h(cudaStream_t s, const RolloutParams &rp) {
+    if constexpr (H <= kMmaMaxHidden) {
+        if (!getenv("FOOTSIES_B200_ROLLOUT_FFMA")) return launch_rollout_mma<H, DENSE>(s, rp);   // knob: the round-1 FFMA2 kernel for A/B runs
+    }
     // battles per lane (measured, tools/rollout_sweep.py, H = 64, us per step): 16 384 battles E = 2 / 4: 6.5 / 7.2 (too few
     // CTAs for E = 4); 131 072: 37.5 / 34.6; 1 Mi: 288 / 264
     int e = rp.sim.n >= 65536 ? 4 : 2;
