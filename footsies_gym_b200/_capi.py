@@ -192,7 +192,7 @@ def load(build_if_missing=True):
     L.fg_policy_last_error.restype = C.c_char_p
     L.fg_rollout_mlp.restype = i32
     L.fg_rollout_mlp.argtypes = [vp, C.POINTER(FgRolloutBuffers), vp]
-    if L.fg_abi_version() != 1:
+    if L.fg_abi_version() != 2:
         raise FootsiesLibraryError("libfootsies_b200.so ABI version mismatch")
     _lib = L
     return L

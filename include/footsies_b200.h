@@ -22,7 +22,9 @@
 extern "C" {
 #endif
 
-#define FG_ABI_VERSION 1
+/* 2 (round 2): fg_env_state.p1_bot_memory, first_env_index argument of fg_policy_mlp_sample[_p2], packed host layout
+ * (fg_packed_result, fg_step_host_packed, fg_reset_host_packed, fg_packed_reward_table), fg_host_alloc / fg_host_free */
+#define FG_ABI_VERSION 2
 
 typedef enum {
     FG_OK = 0,

@@ -22,7 +22,7 @@ def test_header_symbols_are_all_exported():
     lib = _capi.load()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.fg_abi_version() == 1
+    assert lib.fg_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():

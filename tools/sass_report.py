@@ -20,16 +20,16 @@ LIB = os.path.join(ROOT, "footsies_gym_b200", "libfootsies_b200.so")
 TARGETS = {
     "step": ("step_kernel", ["StepShape<768, 256, 3, 1>", "false, false, true, true, false"],
              "K = 1, P1 = agent, P2 = BattleAI, dense reward, unmasked: the benchmark kernel (bench.py roofline)"),
-    "rollout": ("rollout_kernel", ["<64, 2, 4, true, false, false>"],
-                "hidden 64, E = 2, 4 warps, dense reward, P2 = BattleAI: BASELINE configs[4] at 16 384 battles per GPU"),
-    "policy": ("policy_mlp_sample_kernel", ["<64>"], "hidden 64: the per-step policy kernel"),
+    "rollout": ("rollout_mma_kernel", ["<64, 4, 1, true, false, false>"],
+                "hidden 64, 4 warps x 16 battles, dense reward, P2 = BattleAI: BASELINE configs[4] at 16 384 battles per GPU"),
+    "policy": ("policy_mma_sample_kernel", ["<64, false>"], "hidden 64: the per-step policy kernel"),
 }
 INTERESTING = [
     ("TMA bulk copy (cp.async.bulk, 1-D)", r"\bUBLKCP\b|\bUBLKRED\b"),
     ("mbarrier (SYNCS)", r"\bSYNCS\b"),
     ("programmatic dependent launch (griddepcontrol)", r"\bACQBULK\b|\bPDL\b|\bDEPBAR\b.*SB|\bBAR\.ARV\b|PREEXIT|\bACQ"),
     ("packed fp32 pairs (FFMA2 / FADD2 / FMUL2)", r"\bFFMA2\b|\bFADD2\b|\bFMUL2\b"),
-    ("tensor-core MMA (expected: none)", r"\bHMMA\b|\bIMMA\b|\bUTCHMMA\b|\bUTCMMA\b|\bUTC[A-Z]*MMA\b|\bQGMMA\b|\bHGMMA\b"),
+    ("tensor-core MMA (step kernel: none -- nothing there is a contraction; rollout / policy kernels: HMMA.1688.F32.TF32)", r"\bHMMA\b|\bIMMA\b|\bUTCHMMA\b|\bUTCMMA\b|\bUTC[A-Z]*MMA\b|\bQGMMA\b|\bHGMMA\b"),
     ("128-bit global stores / loads", r"\bSTG\.E\.128\b|\bLDG\.E\.128\b"),
     ("warp reductions (REDUX) / votes", r"\bREDUX\b|\bVOTE\b"),
     ("local memory (spills; expected: none)", r"\bSTL\b|\bLDL\b"),
