@@ -36,19 +36,22 @@ def test_fused_frame_skip(oracle, k, p2_bot):
     pc.case_fused_frame_skip(make_env, oracle, k, p2_bot)
 
 
-def test_masked_hard_reset_and_reseed(oracle):
+@pytest.mark.parametrize("by_example", [False, True])
+def test_masked_hard_reset_and_reseed(oracle, by_example):
+    """RESET in mid-round and SEED on a subset of the battles.  by_example: P1's spectator-wrapped bot is never Reset()
+    (BattleCore.cs:274) -- it keeps its queues and decides on the state it recorded last (found by tests/test_oracle_vs_ref.py)."""
     from footsies_gym_b200 import FootsiesEnv
     from parity import compare_state_and_outputs
     _require_cuda()
     rng = np.random.default_rng(8)
     n = 777                                  # ragged: not a multiple of the warp or CTA size
-    env = FootsiesEnv(num_envs=n, device="cuda:0", seed=1)
-    orc = oracle.OracleBatch(n, p2_bot=True, seed=1)
+    env = FootsiesEnv(num_envs=n, device="cuda:0", seed=1, by_example=by_example)
+    orc = oracle.OracleBatch(n, p1_bot=by_example, p2_bot=True, seed=1)
     env.reset()
     orc.reset()
     for t in range(400):
         a = rng.integers(0, 8, size=n, dtype=np.uint8)
-        env.step(torch.from_numpy(a))
+        env.step(None if by_example else torch.from_numpy(a))
         orc.step(a)
         if t % 50 == 25:
             mask = rng.random(n) < 0.3
