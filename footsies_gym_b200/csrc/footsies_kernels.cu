@@ -32,6 +32,7 @@ struct fg_handle {
     int64_t step_calls;    // fg_step calls so far: every other one walks the battles backwards (L2 reuse across launches)
     uint8_t *d_mask;       // staging for fg_reset_host
     int large_shape_min_envs;
+    int pdl_min_envs;      // batch size from which the step kernel is launched with programmatic dependent launch
     // host-buffer path (fg_step_host*): slices of host_chunk_envs battles are pipelined over two library-owned
     // streams, so that the D2H copies of slice c run while slice c+1 is being simulated and its actions uploaded
     int host_chunk_envs;
@@ -71,6 +72,7 @@ Params make_params(const fg_handle *h, int first = 0, int count = -1) {
     p.tables = h->d_tables;
     p.first_env_index = h->cfg.first_env_index + first;
     p.reverse = (int)(h->step_calls & 1);
+    p.pdl = (count < 0 ? h->cfg.num_envs - first : count) >= h->pdl_min_envs;
     p.n = count < 0 ? h->cfg.num_envs - first : count; p.frame_skip = h->cfg.frame_skip; p.autoreset = h->cfg.autoreset;
     p.stale_intro = h->cfg.stale_intro_input;
     p.skip_unactionable = h->cfg.skip_unactionable;
@@ -564,6 +566,12 @@ int32_t fg_create(const fg_config *cfg, fg_handle **out) {
     // developer / test knob: force the large CTA shapes onto small batches (or the small shape onto large ones)
     h->large_shape_min_envs = kLargeShapeMinEnvs;
     if (const char *v = getenv("FOOTSIES_B200_LARGE_SHAPE_MIN_ENVS")) h->large_shape_min_envs = atoi(v);
+    // programmatic dependent launch (measured, profiles/r02j_pdl_threshold.log, us per launch with / without): K = 1 -- 4096
+    // battles 4.2 / 5.2, 65 536: 6.0 / 6.3, 262 144: 10.8 / 11.9, 1 Mi: 33.4 / 35.2, 4 Mi: 115.6 / 122; fused K = 4 -- 1 Mi:
+    // 83.8 / 85.4, but 65 536 self-play (config C, under one wave of long-running CTAs): 10.4 / 9.2 -> fused kernels only
+    // from 262 144 battles up
+    h->pdl_min_envs = (cfg->frame_skip > 1 || cfg->skip_unactionable) ? 262144 : 0;
+    if (const char *v = getenv("FOOTSIES_B200_PDL_MIN_ENVS")) h->pdl_min_envs = atoi(v);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
     h->sm_count = prop.multiProcessorCount;

@@ -88,6 +88,8 @@ struct Params {
     int skip_unactionable;      // fused FootsiesFrameSkipped (KFUSED kernels only)
     int large_shape_min_envs;   // host side only: batch size from which the large CTA shapes are launched
     int reverse;                // walk the chunks from the last to the first (alternates per launch, see step_kernel)
+    int pdl;                    // launched with programmatic stream serialization: dependent data only after griddepcontrol.wait
+    int pdl_min_envs;           // host side only: batch size from which launches use it
 };
 
 __device__ __forceinline__ void write_outputs(const Params &p, int i, const Env &e, float reward, bool terminated) {
@@ -214,26 +216,28 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
         for (int s = 0; s < kStages; s++) { mbar_init(&S.full_bar[g][s], 1u); mbar_init(&S.empty_bar[g][s], kGroupThreads / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-#if FG_PDL
-    // Programmatic dependent launch: this CTA may have become resident while the previous launch on the stream was still
-    // draining.  What does not depend on it (barriers, the constant tables) is set up first; battle state, actions and
-    // masks are only touched after griddepcontrol.wait.  The next launch is allowed to move in as soon as SMs free up.
-    load_tables(&S.T, p.tables);
-    if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
+    // Programmatic dependent launch (p.pdl, large batches): this CTA may have become resident while the previous launch on
+    // the stream was still draining.  What does not depend on it (barriers, the constant tables) is set up first; battle
+    // state, actions and masks are only touched after griddepcontrol.wait, and the next launch is allowed to move in as soon
+    // as SMs free up.  Without it (small batches: the kernel is a wave or less and its own start-up latency is what
+    // counts) the first chunks are requested before the tables are staged, so that the two overlap.
+    if (FG_PDL && p.pdl) {
+        load_tables(&S.T, p.tables);
+        if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     if (lt == 0) {
-        // prologue: the group's first kStages-1 chunks are in flight while the tables are being staged
+        // prologue: the group's first kStages-1 chunks are in flight
         for (int j = 0; j < kStages - 1; j++) {
             const int cj = first + j * stride;
             if (cj < num_chunks && chunk_of(cj) < full_chunks) issue(chunk_of(cj), j);
         }
     }
-#if !FG_PDL
-    load_tables(&S.T, p.tables);
-    if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
-#endif
+    if (!(FG_PDL && p.pdl)) {
+        load_tables(&S.T, p.tables);
+        if (threadIdx.x < FG_STAT_COUNT) S.stats[threadIdx.x] = 0ull;
+    }
     __syncthreads();
     StatAcc acc = { 0u, 0u, 0u, 0u };
     uint32_t frames_since_flush = 0u;
@@ -386,6 +390,10 @@ cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
     const int want = (p.n + SH::kThreads - 1) / SH::kThreads, cap = sm_count * SH::kMinBlocks;
     const int grid = want < cap ? (want > 0 ? want : 1) : cap;
 #if FG_PDL
+    if (!p.pdl) {
+        step_kernel<SH, KF, B1, B2, D, M><<<grid, SH::kThreads, bytes, s>>>(p);
+        return cudaSuccess;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)SH::kThreads);

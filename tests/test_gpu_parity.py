@@ -31,6 +31,21 @@ def test_parity_case(oracle, name):
     getattr(pc, name)(make_env, oracle)
 
 
+@pytest.mark.parametrize("name", ["case_config_b_4096_envs_random_vs_bot_every_frame", "case_both_bots_by_example",
+                                  "case_input_personalities_self_play"])
+def test_parity_case_directly_against_the_transliterated_reference(name):
+    """The CUDA path against the reference's OWN battle code (oracle/_ref: Assets/Script/*.cs transliterated by
+    tools/cs2cpp.py; the prebuilt library travels to the GPU box) without the hand-written oracle in between: the trace
+    gate of BASELINE configs[1], by_example and the self-play personalities, every battle, every frame, every field."""
+    import types
+    import ref_binding
+    if not ref_binding.available():
+        pytest.skip("oracle/_ref not built")
+    _require_cuda()
+    ref = types.SimpleNamespace(OracleBatch=ref_binding.RefBatch)
+    getattr(pc, name)(make_env, ref, scale=0.125)
+
+
 @pytest.mark.parametrize("k,p2_bot", pc.FUSED_PARAMS)
 def test_fused_frame_skip(oracle, k, p2_bot):
     pc.case_fused_frame_skip(make_env, oracle, k, p2_bot)
