@@ -171,8 +171,8 @@ def test_frame_skipped_wrapper_over_a_delayed_batch(oracle, autoreset):
         assert np.array_equal(got, np.delete(exp_obs, 4, axis=1)), (t, np.argwhere(got != np.delete(exp_obs, 4, axis=1))[:3])
         assert np.array_equal(info["frame"].cpu().numpy(), np.asarray(exp_frame)), t
         assert np.array_equal(term.cpu().numpy().astype(np.int32), np.asarray(exp_term)), t
-        live = ~np.asarray([bool(o.trace["terminated"][0]) and False for o in orcs])
-        assert np.abs(reward.cpu().numpy().astype(np.float64)[live] - np.asarray(exp_rew)[live]).max() <= 1e-6, t
+        # the wrapper adds float32 step rewards, the reference Python floats: 1e-6
+        assert np.abs(reward.cpu().numpy().astype(np.float64) - np.asarray(exp_rew)).max() <= 1e-6, t
     assert held_back > steps
     env.close()
 
