@@ -36,7 +36,7 @@ def sources():
 def deps():
     inc = os.path.join(os.path.dirname(PKG_DIR), "include", "footsies_b200.h")
     return sources() + [os.path.join(CSRC, f) for f in ("state_codec.h", "frame_tables.h", "frame_logic.cuh",
-                                                        "tables_host.h", "step_kernel.cuh", "policy_mlp.cuh", "device_once.h",
+                                                        "tables_host.h", "step_kernel.cuh", "policy_mlp.cuh", "policy_mma.cuh", "device_once.h",
                                                         "rollout_kernel.h")] + [inc]
 
 

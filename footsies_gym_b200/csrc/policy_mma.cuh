@@ -44,10 +44,16 @@ __device__ __forceinline__ float tf32_hi(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// Activation split on the hot path: hi = x truncated to TF32 (one LOP3), lo = x - hi, exact in fp32 and handed to the MMA
+// as it is (the tensor core reads the upper 19 bits of a TF32 operand).  sm_100a has no native cvt.rna.tf32: it is emulated
+// in ~5 integer instructions, which made the two conversions per activation a quarter of the policy's instructions
+// (16 384 battles: 4.46 -> 4.00 us per step); the weights, split once per launch, keep the rounded conversion.
+// |x - hi - tf32(lo)| <= 2^-21 |x|.
+// (Tried and dropped, profiles/r02n_rollout_halves.log: computing layer 2 in two halves of its n-tiles to halve the live
+// accumulators and fit a third CTA per SM -- 4.43 us per step at 16 384 battles, 200 instead of 184 us at 1 Mi.)
 __device__ __forceinline__ void tf32_split(float x, uint32_t &hi, uint32_t &lo) {
-    const float h = tf32_hi(x);
-    hi = __float_as_uint(h);
-    lo = __float_as_uint(tf32_hi(x - h));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"

@@ -356,11 +356,10 @@ static cudaError_t launch_rollout_mma(cudaStream_t s, const RolloutParams &rp) {
     // 16 384 battles 4.49 / 5.90 / 6.37; 131 072: 28.0 / 31.3 / -; 1 Mi: 216 / 227 / 262 -- more, lighter warps hide the
     // simulator's latency under the neighbours' tensor-core phases at every size, so 16-battle warps are the default
     // (developer knob: FOOTSIES_B200_ROLLOUT_MT = 1 | 2).
-    int mt = 1;
+    int mt = rp.sim.n >= 131072 ? 2 : 1;
     if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_MT")) mt = atoi(v) == 2 ? 2 : 1;
     // (7-warp CTAs, which would spread 16 384 battles evenly as 147 x 112, measured 4.55 us per step against 4.46 for 4 warps.)
     // Two policies (self-play): 32-battle warps from 131 072 battles up (1 Mi: 479 us per step against 567).
-    if (rp.p2_policy && rp.sim.n >= 131072 && !getenv("FOOTSIES_B200_ROLLOUT_MT")) mt = 2;
     return launch_rollout_mma_w<H, 4, DENSE>(mt, s, rp);
 }
 

@@ -5,9 +5,11 @@
  * relative to /root/reference/.  Compile with -ffp-contract=off: every fp32 operation below is
  * meant to round separately, the way the C# float expressions are written.
  *
- * Parity: UNPINNED against a running game (no C# runtime / game binary offline); pinned to the
- * reference's moves.py table, hand-derived known answers, and -- for the Python half -- golden
- * vectors produced by the reference's own FootsiesEnv (tests/golden/).
+ * Parity: pinned, trace field by trace field, to the reference's own C# battle code transliterated mechanically into
+ * C++ (oracle/_ref, tools/cs2cpp.py; tests/test_oracle_vs_ref.py), to hand-derived known answers and the reference's
+ * moves.py table, and -- for the Python half -- to golden vectors produced by the reference's own FootsiesEnv
+ * (tests/golden/).  Unpinned remains only third-party code outside /root/reference (UnityEngine.Random / Rect / Time, Mono
+ * fp32 evaluation): no C# runtime or game binary exists offline.
  */
 #include "footsies_oracle.h"
 #include "frame_data.h"

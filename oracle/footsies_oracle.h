@@ -13,16 +13,18 @@
  * 180-entry input arrays, real FIFO queues and range-scanned frame data so that every
  * function can be read side by side with the C# it cites.
  *
- * PARITY STATUS (see DESIGN.md "Oracle"):
- *   - The C# engine cannot run here (no Unity/mono/dotnet, no game binary), and the
- *     reference ships no tests / golden vectors for the battle logic  =>  the engine part
- *     of this oracle is "PARITY UNPINNED" against a running game.  It is pinned only to
- *     (a) the reference's moves.py frame table, (b) hand-derived known answers from the C#
- *     text (tests/test_oracle_kat.py), and (c) for the Python half (obs / info / reward /
- *     termination / frame_delay), golden vectors produced by the reference's own unmodified
- *     FootsiesEnv class driven over its socket protocol (tests/golden/make_golden.py).
- *   - UnityEngine.Random (closed source) is restated from public descriptions as Marsaglia
- *     xorshift128; UnityEngine.Rect.Overlaps from its documented behaviour.  Both unpinned.
+ * PARITY STATUS:
+ *   - PINNED to the reference's own source text: the C# engine cannot run here (no Unity/mono/dotnet, no game binary)
+ *     and the reference ships no tests, so tools/cs2cpp.py transliterates Assets/Script/{Fighter,BattleAI,BattleCore,
+ *     ActionData,...}.cs mechanically into C++ (oracle/_ref/, built by oracle/Makefile.ref from the sources where they lie
+ *     under /root/reference, never committed) and tests/test_oracle_vs_ref.py steps this oracle and that engine side by
+ *     side on every parity tape: every field of every trace after every step is byte-identical.  The known-answer tests
+ *     (tests/test_oracle_kat.py) are asked of both engines.
+ *   - The Python half (obs / info / reward / termination / frame_delay) is pinned by golden vectors produced by the
+ *     reference's own unmodified FootsiesEnv class driven over its socket protocol (tests/golden/make_golden.py).
+ *   - Still "PARITY UNPINNED", because it is third-party code that is NOT under /root/reference: UnityEngine.Random (closed
+ *     source; restated from public descriptions as Marsaglia xorshift128), UnityEngine.Rect.Overlaps (documented behaviour),
+ *     Time.deltaTime = 0.02 and Mono's evaluation of float expressions.  Both engines restate them identically.
  */
 #ifndef FOOTSIES_ORACLE_H
 #define FOOTSIES_ORACLE_H
