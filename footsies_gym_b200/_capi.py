@@ -80,17 +80,23 @@ FG_PACKED_REWARD_TABLE_SIZE = 128
 
 
 class HostBlock:
-    """Pinned host memory from fg_host_alloc (placed on the GPU's NUMA node), viewed as torch tensors."""
+    """Pinned host memory from fg_host_alloc (placed on the GPU's NUMA node), viewed as torch tensors.  The memory lives as
+    long as any tensor taken from it: torch.frombuffer keeps the ctypes buffer object alive, and the buffer's finaliser is
+    what returns the block to fg_host_free."""
 
     def __init__(self, device_index: int, nbytes: int):
+        import weakref
+
         import torch
-        self._lib = load()
+        lib = load()
         self.nbytes = int(nbytes)
-        self.ptr = self._lib.fg_host_alloc(int(device_index), self.nbytes)
-        if not self.ptr:
-            raise FootsiesLibraryError("fg_host_alloc failed: " + self._lib.fg_last_error().decode("utf-8", "replace"))
-        self._raw = (C.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr)
-        self.bytes = torch.frombuffer(self._raw, dtype=torch.uint8, count=self.nbytes)
+        ptr = lib.fg_host_alloc(int(device_index), self.nbytes)
+        if not ptr:
+            raise FootsiesLibraryError("fg_host_alloc failed: " + lib.fg_last_error().decode("utf-8", "replace"))
+        self.ptr = ptr
+        raw = (C.c_uint8 * max(self.nbytes, 1)).from_address(ptr)
+        weakref.finalize(raw, lib.fg_host_free, ptr).atexit = False     # at interpreter exit the process goes away anyway
+        self.bytes = torch.frombuffer(raw, dtype=torch.uint8, count=self.nbytes)
         self._offset = 0
 
     def take(self, shape, dtype):
@@ -102,17 +108,6 @@ class HostBlock:
             raise ValueError("host block exhausted")
         self._offset = off + n
         return self.bytes[off:off + n].view(dtype).reshape(shape)
-
-    def close(self):
-        if self.ptr:
-            self._lib.fg_host_free(self.ptr)
-            self.ptr = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:  # noqa: BLE001
-            pass
 
 
 _lib = None
