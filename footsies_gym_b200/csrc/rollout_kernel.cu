@@ -247,13 +247,17 @@ __global__ void __launch_bounds__(32 * W) rollout_mma_kernel(const RolloutParams
 
     for (int t = 0; t < horizon; t++) {
         // ---- policy: the warp's battles through the MLP on the tensor cores, then one lane per battle samples ----
+        // (the random words do not depend on the logits: their 64-bit multiply chains are issued before the MMAs, under
+        // whose latency they complete)
+        const uint32_t rnd1 = hash3(rp.seed, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i));
+        const uint32_t rnd2 = P2POL ? hash3(rp.seed_p2, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)) : 0u;
         policy_mma_logits<H, MT, false>(pw, obs_w, lg_w, lane);
         uint32_t in1 = 0u, in2 = 0u;
         if (valid) {
             const float4 l0 = reinterpret_cast<const float4 *>(lg_w)[2 * lane], l1 = reinterpret_cast<const float4 *>(lg_w)[2 * lane + 1];
             const float lg[8] = { l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w };
             float lp;
-            in1 = (uint32_t)policy_sample(lg, hash3(rp.seed, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)), lp);
+            in1 = (uint32_t)policy_sample(lg, rnd1, lp);
             rp.actions[(size_t)t * n + i] = (uint8_t)in1;
             rp.logp[(size_t)t * n + i] = lp;
         }
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(32 * W) rollout_mma_kernel(const RolloutParams
                 const float4 l0 = reinterpret_cast<const float4 *>(lg_w)[2 * lane], l1 = reinterpret_cast<const float4 *>(lg_w)[2 * lane + 1];
                 const float lg[8] = { l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w };
                 float lp;
-                int a2 = policy_sample(lg, hash3(rp.seed_p2, drawn + (unsigned long long)t, (uint64_t)(p.first_env_index + i)), lp);
+                int a2 = policy_sample(lg, rnd2, lp);
                 if (rp.p2_mirror) a2 = policy_mirror_action(a2);
                 in2 = (uint32_t)a2;
                 rp.actions_p2[(size_t)t * n + i] = (uint8_t)a2;

@@ -195,8 +195,9 @@ def test_library_fails_loudly_on_bad_arguments():
     env.close()
 
 
-@pytest.mark.parametrize("min_envs", ["0", "1000000000"], ids=["large_shapes_on_small_batches", "small_shape_only"])
-def test_cta_shapes_are_interchangeable(min_envs):
+@pytest.mark.parametrize("min_envs,pdl_min_envs", [("0", "0"), ("1000000000", "0"), ("0", "1000000000")],
+                         ids=["large_shapes_on_small_batches_with_pdl", "small_shape_only_with_pdl", "large_shapes_without_pdl"])
+def test_cta_shapes_are_interchangeable(min_envs, pdl_min_envs):
     """The step kernel picks a CTA shape by batch size (768 / 1024-thread pipeline groups from 0.75 Mi envs, 256-thread
     CTAs below).  Forcing each choice onto ragged, small batches (few chunks per pipeline group, tail chunks, masked
     steps, fused K) must not change a single bit: tools/sanitize_check.py compares against the oracle."""
@@ -205,7 +206,8 @@ def test_cta_shapes_are_interchangeable(min_envs):
     import sys
     _require_cuda()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, FOOTSIES_B200_LARGE_SHAPE_MIN_ENVS=min_envs, SAN_STEPS="120")
+    # ... and with / without programmatic dependent launch (by default the fused-K kernels only use it from 262 144 battles)
+    env = dict(os.environ, FOOTSIES_B200_LARGE_SHAPE_MIN_ENVS=min_envs, FOOTSIES_B200_PDL_MIN_ENVS=pdl_min_envs, SAN_STEPS="120")
     res = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_check.py")], env=env, capture_output=True,
                          text=True, timeout=600)
     assert res.returncode == 0 and "sanitize_check done" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
