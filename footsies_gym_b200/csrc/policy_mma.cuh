@@ -22,21 +22,43 @@
 // the k index of an MMA is a summation index, so its order is free as long as A and B agree -- A column t is taken to be
 // unit 8j + 2t and column t + 4 unit 8j + 2t + 1 (a0 = c0, a1 = c2, a2 = c1, a3 = c3), and the weight fragments are staged
 // with their rows permuted the same way.
+//
+// Layers 2 and 3 (FG_POLICY_F16, default): the same split on FP16 operands -- mma.sync m16n8k16, 1024 MAC per cycle per SM,
+// twice the TF32 rate, and half as many instructions (layer 2 of H = 64: 96 HMMA.16816 instead of 192 HMMA.1688).  FP16
+// carries the same 11 significant bits as TF32, so hi + lo holds 22 bits just the same; what FP16 lacks is exponent
+// range, and after a tanh the range is known: the activations are produced as 256 tanh(.) (|x| <= 256, hi and lo normal
+// FP16 numbers down to |tanh| = 2^-12) and each weight matrix is scaled by a power of two chosen at staging time so that
+// its largest entry lies in [2^12, 2^13).  The biases are staged pre-multiplied by the same factor and the inverse is
+// folded into the constant of the next tanh's exp2, so the scaling costs no instruction and no rounding.  Layer 1 sees
+// raw observations times a caller-supplied scale (unbounded) and stays on TF32.  With k = 16 the C tiles 2j and 2j + 1 of
+// one layer are the A fragment of k-step j of the next in their natural order (a0 = (c0, c1) of tile 2j, a1 = (c2, c3),
+// a2 / a3 the same of tile 2j + 1): no row permutation.
+#include <cuda_fp16.h>
+
 #include "policy_mlp.cuh"
+
+#ifndef FG_POLICY_F16
+#define FG_POLICY_F16 1
+#endif
 
 namespace fgp {
 
 constexpr int kMmaMaxHidden = 64;
+constexpr float kActScale = 256.0f;             // FP16 path: hidden activations are carried as kActScale * tanh
 
 // Shared memory of one weight set: per (layer, k-step, n-tile) one float4 per lane = {b0_hi, b1_hi, b0_lo, b1_lo}
 // (one conflict-free LDS.128 per fragment), then the biases and the observation scale.
+// FP16 path: layers 2 and 3 hold per (k-step of 16, n-tile) one uint4 per lane = {b0_hi, b1_hi, b0_lo, b1_lo} as half2
+// pairs; kInv2 / kInv3 = 1 / (kActScale x the layer's weight scale), kMax = scratch of the staging reduction.
 template <int H>
 struct PolicyMmaSmem {
-    static_assert(H % 8 == 0 && H <= kMmaMaxHidden, "hidden size of the MMA path");
-    static constexpr int NT = H / 8;                              // n-tiles of a hidden layer = k-steps of the next one
-    static constexpr int kW1 = 0, kW2 = kW1 + NT * 32, kW3 = kW2 + NT * NT * 32, kFrags = kW3 + NT * 32;   // in float4
-    static constexpr int kB1 = kFrags * 4, kB2 = kB1 + H, kB3 = kB2 + H, kScale = kB3 + 8, kFloats = kScale + 8;   // in floats
-    static constexpr size_t kBytes = sizeof(float) * kFloats;
+    static_assert(H % 16 == 0 && H <= kMmaMaxHidden, "hidden size of the MMA path");
+    static constexpr int NT = H / 8;                              // n-tiles of a hidden layer = k-steps (of 8) of the next one
+    static constexpr int KT = FG_POLICY_F16 ? H / 16 : NT;        // k-steps of layers 2 and 3
+    static constexpr int kW1 = 0, kW2 = kW1 + NT * 32, kW3 = kW2 + KT * NT * 32, kFrags = kW3 + KT * 32;   // in float4
+    static constexpr int kB1 = kFrags * 4, kB2 = kB1 + H, kB3 = kB2 + H, kScale = kB3 + 8, kInv2 = kScale + 8, kInv3 = kInv2 + 1,
+                         kMax = kInv3 + 1, kFloats = kMax + 2;    // in floats
+    static constexpr size_t kBytes = sizeof(float) * ((kFloats + 3) / 4 * 4);
 };
 
 __device__ __forceinline__ float tf32_hi(float x) {
@@ -67,7 +89,41 @@ __device__ __forceinline__ void mma_3xtf32(float (&c)[4], const uint32_t (&ahi)[
     mma_tf32(c, ahi, __float_as_uint(b.x), __float_as_uint(b.y));
 }
 
-// Stage one weight set (torch.nn.Linear layout: W[out][in]) as pre-split, pre-permuted B fragments.
+
+// ---- FP16 operands (layers 2 and 3) ----
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {      // x -> low half, y -> high half (F2FP.PACK_AB)
+    const __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+// Two activations -> the hi and lo halves of one A register.  hi = x truncated to 11 significant bits (exact in FP16 for
+// 2^-14 <= |x| < 2^16), lo = x - hi, exact in fp32, rounded to FP16: |x - hi - lo| <= 2^-22 |x|.
+__device__ __forceinline__ void f16_split2(float x, float y, uint32_t &hi, uint32_t &lo) {
+    const float xh = __uint_as_float(__float_as_uint(x) & 0xffffe000u), yh = __uint_as_float(__float_as_uint(y) & 0xffffe000u);
+    hi = pack_half2(xh, yh);
+    lo = pack_half2(x - xh, y - yh);
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xf16(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], const uint4 &b) {
+    mma_f16(c, alo, b.x, b.y);
+    mma_f16(c, ahi, b.z, b.w);
+    mma_f16(c, ahi, b.x, b.y);
+}
+// kActScale * tanh(x * inv) with c = inv * 2 log2(e): the scaled activation the FP16 layers consume (same two MUFU
+// approximations as fast_tanh; inv is a power of two, so x * c rounds exactly like (x * inv) * 2 log2(e))
+__device__ __forceinline__ float scaled_tanh(float x, float c) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * c));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f * kActScale, r, kActScale);
+}
+constexpr float kTwoLog2e = 2.8853900432586669921875f;
+
+// Stage one weight set (torch.nn.Linear layout: W[out][in]) as pre-split B fragments.  Called by every thread of the CTA
+// (nthreads a multiple of 32); the FP16 path contains two CTA barriers (the per-matrix maximum that fixes the scale).
 template <int H>
 __device__ __forceinline__ void policy_mma_stage(float *sm, const PolicyWeights &p, int tid, int nthreads) {
     using L = PolicyMmaSmem<H>;
@@ -77,6 +133,56 @@ __device__ __forceinline__ void policy_mma_stage(float *sm, const PolicyWeights 
         const float h0 = tf32_hi(b0), h1 = tf32_hi(b1);
         frag[idx] = make_float4(h0, h1, tf32_hi(b0 - h0), tf32_hi(b1 - h1));
     };
+#if FG_POLICY_F16
+    // layer 1: k = observation feature (natural order: t, t + 4), n = unit 8 nt + g
+    for (int i = tid; i < NT * 32; i += nthreads) {
+        const int nt = i >> 5, lane = i & 31, g = lane >> 2, t = lane & 3;
+        put(L::kW1 + i, p.w1[(8 * nt + g) * 8 + t], p.w1[(8 * nt + g) * 8 + t + 4]);
+    }
+    // largest |w| of W2 and of W3 -> power-of-two scales that put it into [2^12, 2^13)
+    uint32_t *smax = reinterpret_cast<uint32_t *>(sm + L::kMax);
+    if (tid < 2) smax[tid] = 0u;
+    __syncthreads();
+    {
+        uint32_t m2 = 0u, m3 = 0u;                                  // |w| as bits: ordered like the values
+        for (int i = tid; i < H * H; i += nthreads) m2 = max(m2, __float_as_uint(p.w2[i]) & 0x7fffffffu);
+        for (int i = tid; i < 8 * H; i += nthreads) m3 = max(m3, __float_as_uint(p.w3[i]) & 0x7fffffffu);
+        m2 = __reduce_max_sync(0xffffffffu, m2); m3 = __reduce_max_sync(0xffffffffu, m3);
+        if ((tid & 31) == 0) { atomicMax(&smax[0], m2); atomicMax(&smax[1], m3); }
+    }
+    __syncthreads();
+    // biased exponent E of the maximum (clamped: all-zero / non-finite weights keep the arithmetic finite):
+    // weight scale 2^(139 - E), inverse of (kActScale x scale) = 2^(E - 147)
+    const int e2 = min(max((int)(smax[0] >> 23), 40), 254), e3 = min(max((int)(smax[1] >> 23), 40), 254);
+    const float s2 = __uint_as_float((uint32_t)(266 - e2) << 23), s3 = __uint_as_float((uint32_t)(266 - e3) << 23);
+    uint4 *hfrag = reinterpret_cast<uint4 *>(sm);
+    auto put16 = [&](int idx, const float *row, float scale) {      // row -> k = 2t, 2t + 1 (b0) and 2t + 8, 2t + 9 (b1)
+        const float w0 = row[0] * scale, w1 = row[1] * scale, w2 = row[8] * scale, w3 = row[9] * scale;
+        const __half2 h0 = __floats2half2_rn(w0, w1), h1 = __floats2half2_rn(w2, w3);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        uint4 v;
+        v.x = *reinterpret_cast<const uint32_t *>(&h0); v.y = *reinterpret_cast<const uint32_t *>(&h1);
+        v.z = pack_half2(w0 - f0.x, w1 - f0.y); v.w = pack_half2(w2 - f1.x, w3 - f1.y);
+        hfrag[idx] = v;
+    };
+    // layer 2: k-step kt (16 inputs), n = output unit 8 nt + g
+    for (int i = tid; i < L::KT * NT * 32; i += nthreads) {
+        const int lane = i & 31, g = lane >> 2, t = lane & 3, nt = (i >> 5) % NT, kt = (i >> 5) / NT;
+        put16(L::kW2 + i, p.w2 + (8 * nt + g) * H + 16 * kt + 2 * t, s2);
+    }
+    // layer 3: one n-tile (the 8 logits), n = g
+    for (int i = tid; i < L::KT * 32; i += nthreads) {
+        const int kt = i >> 5, lane = i & 31, g = lane >> 2, t = lane & 3;
+        put16(L::kW3 + i, p.w3 + g * H + 16 * kt + 2 * t, s3);
+    }
+    // biases of the scaled layers in accumulator units
+    for (int i = tid; i < H; i += nthreads) { sm[L::kB1 + i] = p.b1[i]; sm[L::kB2 + i] = p.b2[i] * (kActScale * s2); }
+    if (tid < 8) { sm[L::kB3 + tid] = p.b3[tid] * (kActScale * s3); sm[L::kScale + tid] = p.scale[tid]; }
+    if (tid == 0) {
+        sm[L::kInv2] = __uint_as_float((uint32_t)(e2 - 20) << 23);
+        sm[L::kInv3] = __uint_as_float((uint32_t)(e3 - 20) << 23);
+    }
+#else
     // layer 1: k = observation feature (natural order: t, t + 4), n = unit 8 nt + g
     for (int i = tid; i < NT * 32; i += nthreads) {
         const int nt = i >> 5, lane = i & 31, g = lane >> 2, t = lane & 3;
@@ -94,6 +200,7 @@ __device__ __forceinline__ void policy_mma_stage(float *sm, const PolicyWeights 
     }
     for (int i = tid; i < H; i += nthreads) { sm[L::kB1 + i] = p.b1[i]; sm[L::kB2 + i] = p.b2[i]; }
     if (tid < 8) { sm[L::kB3 + tid] = p.b3[tid]; sm[L::kScale + tid] = p.scale[tid]; }
+#endif
 }
 
 // The 8 logits of the warp's 16 MT battles.  obs_rows: the battles' raw observation rows ([16 MT][8] floats, shared or
@@ -136,7 +243,7 @@ __device__ __forceinline__ void policy_mma_logits(const float *sm, const float *
             h[m][nt][0] = bias.x; h[m][nt][1] = bias.y; h[m][nt][2] = bias.x; h[m][nt][3] = bias.y;
             mma_3xtf32(h[m][nt], xhi[m], xlo[m], b);
 #pragma unroll
-            for (int k = 0; k < 4; k++) h[m][nt][k] = fast_tanh(h[m][nt][k]);
+            for (int k = 0; k < 4; k++) h[m][nt][k] = FG_POLICY_F16 ? scaled_tanh(h[m][nt][k], kTwoLog2e) : fast_tanh(h[m][nt][k]);
         }
     }
     // ---- layer 2 ----
@@ -147,6 +254,53 @@ __device__ __forceinline__ void policy_mma_logits(const float *sm, const float *
 #pragma unroll
         for (int m = 0; m < MT; m++) { acc[m][nt][0] = bias.x; acc[m][nt][1] = bias.y; acc[m][nt][2] = bias.x; acc[m][nt][3] = bias.y; }
     }
+#if FG_POLICY_F16
+    constexpr int KT = L::KT;
+    const uint4 *hfrag = reinterpret_cast<const uint4 *>(sm);
+#pragma unroll
+    for (int kt = 0; kt < KT; kt++) {
+        uint32_t ahi[MT][4], alo[MT][4];
+#pragma unroll
+        for (int m = 0; m < MT; m++) {                 // C tiles 2kt, 2kt + 1 -> A fragment of k-step kt
+            f16_split2(h[m][2 * kt][0], h[m][2 * kt][1], ahi[m][0], alo[m][0]);
+            f16_split2(h[m][2 * kt][2], h[m][2 * kt][3], ahi[m][1], alo[m][1]);
+            f16_split2(h[m][2 * kt + 1][0], h[m][2 * kt + 1][1], ahi[m][2], alo[m][2]);
+            f16_split2(h[m][2 * kt + 1][2], h[m][2 * kt + 1][3], ahi[m][3], alo[m][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+            const uint4 b = hfrag[L::kW2 + (kt * NT + nt) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < MT; m++) mma_3xf16(acc[m][nt], ahi[m], alo[m], b);
+        }
+    }
+    // ---- layer 3 on tanh(layer 2); the accumulators are in units of 1 / inv2, the logits of 1 / inv3 ----
+    const float c2 = sm[L::kInv2] * kTwoLog2e, inv3 = sm[L::kInv3];
+    float lg[MT][4];
+    {
+        const float2 bias = *reinterpret_cast<const float2 *>(b3 + 2 * t);
+#pragma unroll
+        for (int m = 0; m < MT; m++) { lg[m][0] = bias.x; lg[m][1] = bias.y; lg[m][2] = bias.x; lg[m][3] = bias.y; }
+    }
+#pragma unroll
+    for (int kt = 0; kt < KT; kt++) {
+        const uint4 b = hfrag[L::kW3 + kt * 32 + lane];
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            uint32_t ahi[4], alo[4];
+            f16_split2(scaled_tanh(acc[m][2 * kt][0], c2), scaled_tanh(acc[m][2 * kt][1], c2), ahi[0], alo[0]);
+            f16_split2(scaled_tanh(acc[m][2 * kt][2], c2), scaled_tanh(acc[m][2 * kt][3], c2), ahi[1], alo[1]);
+            f16_split2(scaled_tanh(acc[m][2 * kt + 1][0], c2), scaled_tanh(acc[m][2 * kt + 1][1], c2), ahi[2], alo[2]);
+            f16_split2(scaled_tanh(acc[m][2 * kt + 1][2], c2), scaled_tanh(acc[m][2 * kt + 1][3], c2), ahi[3], alo[3]);
+            mma_3xf16(lg[m], ahi, alo, b);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) lg[m][k] *= inv3;
+    }
+#else
 #pragma unroll
     for (int kt = 0; kt < NT; kt++) {
         uint32_t ahi[MT][4], alo[MT][4];
@@ -184,6 +338,7 @@ __device__ __forceinline__ void policy_mma_logits(const float *sm, const float *
             mma_3xtf32(lg[m], ahi, alo, b);
         }
     }
+#endif
     // ---- logits of row r to lg_rows[r][0 .. 7]: this lane holds columns 2t, 2t + 1 of rows 16 m + g and 16 m + g + 8 ----
     __syncwarp();                                     // the previous step's readers are done with lg_rows
 #pragma unroll
