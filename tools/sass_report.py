@@ -29,7 +29,7 @@ INTERESTING = [
     ("mbarrier (SYNCS)", r"\bSYNCS\b"),
     ("programmatic dependent launch (griddepcontrol)", r"\bACQBULK\b|\bPDL\b|\bDEPBAR\b.*SB|\bBAR\.ARV\b|PREEXIT|\bACQ"),
     ("packed fp32 pairs (FFMA2 / FADD2 / FMUL2)", r"\bFFMA2\b|\bFADD2\b|\bFMUL2\b"),
-    ("tensor-core MMA (step kernel: none -- nothing there is a contraction; rollout / policy kernels: HMMA.1688.F32.TF32)", r"\bHMMA\b|\bIMMA\b|\bUTCHMMA\b|\bUTCMMA\b|\bUTC[A-Z]*MMA\b|\bQGMMA\b|\bHGMMA\b"),
+    ("tensor-core MMA (step kernel: none -- nothing there is a contraction; rollout / policy kernels: HMMA.1688.F32.TF32 in layer 1, HMMA.16816.F32 on FP16 operands in layers 2 and 3)", r"\bHMMA\b|\bIMMA\b|\bUTCHMMA\b|\bUTCMMA\b|\bUTC[A-Z]*MMA\b|\bQGMMA\b|\bHGMMA\b"),
     ("128-bit global stores / loads", r"\bSTG\.E\.128\b|\bLDG\.E\.128\b"),
     ("warp reductions (REDUX) / votes", r"\bREDUX\b|\bVOTE\b"),
     ("local memory (spills; expected: none)", r"\bSTL\b|\bLDL\b"),
@@ -70,6 +70,9 @@ def main():
     for title, pat in INTERESTING:
         hits = [ln for ln in insts if re.search(pat, ln)]
         print(f"\n## {title}: {len(hits)} instruction(s)")
+        if "MMA" in title and hits:          # by full mnemonic: which operand types the tensor cores are fed
+            kinds = collections.Counter(re.search(r"([A-Z]*MMA[A-Z0-9_.]*)", ln).group(1) for ln in hits)
+            print("    by variant: " + ", ".join(f"{k} x {n}" for k, n in kinds.most_common()))
         for ln in hits[:12]:
             print("   ", re.sub(r"\s+/\* 0x[0-9a-f]+ \*/\s*$", "", ln))
         if len(hits) > 12:
