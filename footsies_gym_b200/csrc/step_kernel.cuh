@@ -8,6 +8,11 @@
 // shared memory; CTAs are persistent (grid-stride over chunks of 256 envs) and the state planes of the next chunk
 // stream into shared memory with TMA bulk copies while the current chunk is simulated.
 // No tensor cores: nothing here is a contraction.  Bounds: the ALU pipe first, then HBM bandwidth (K = 1).
+// Results go back with per-thread 128-bit stores on purpose: staging a chunk's state and output planes in shared memory and
+// writing them with TMA bulk stores (cp.async.bulk.global.shared::cta, the mirror of the load side) was built and measured
+// in round 2 -- tools/probes/bulk_store_experiment.patch, profiles/r02v_bulk_store_ab.log -- and LOST: 143.5 vs 116.3 us per
+// launch at 4 Mi battles, 44.8 vs 35.1 at 1 Mi, 9.8 vs 7.6 at 65 536 (the warps of a group get coupled through the staging
+// block and its elected thread, where now they only meet at the load barrier).
 #include "device_once.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -67,12 +72,6 @@ constexpr int kLargeShapeMinEnvs = 768 * 1024;
 #endif
 #ifndef FG_REVERSE
 #define FG_REVERSE 1
-#endif
-// Experiment (measured and NOT shipped, profiles/r02v_bulk_store_ab.log): write a chunk's state and output planes back with TMA
-// bulk stores from shared memory (the mirror of the load side) instead of per-thread 128-bit stores.  K = 1, unmasked,
-// autoreset launches only.
-#ifndef FG_BULK_STORE
-#define FG_BULK_STORE 0
 #endif
 constexpr int kThreads = 256;                    // reset / seed kernels
 constexpr uint32_t kFull = 0xffffffffu;
@@ -183,38 +182,12 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void tma_store_1d(void *dst, const void *src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// One chunk's step outputs in the layout of the global planes (bulk-store staging, FG_BULK_STORE)
-template <int G>
-struct __align__(128) OutStage {
-    float4 obs[2 * G];
-    float reward[G];
-    int32_t info_frame[G];
-    uint32_t info_misc[G];
-    uint8_t terminated[G];
-};
-template <int G, int GROUPS, bool ON>
-struct BulkSmem {
-    OutStage<G> out[GROUPS];
-    uint64_t out_full[GROUPS], out_free[GROUPS];
-};
-template <int G, int GROUPS>
-struct BulkSmem<G, GROUPS, false> {};
-
-template <class SH, int PLANES, bool BULK = false>
+template <class SH, int PLANES>
 struct __align__(128) StepSmem {
     Tables T;
     uint4 stage[SH::kGroups][SH::kStages][PLANES][SH::kGroupThreads];
     uint64_t full_bar[SH::kGroups][SH::kStages], empty_bar[SH::kGroups][SH::kStages];
     unsigned long long stats[FG_STAT_COUNT];
-    BulkSmem<SH::kGroupThreads, SH::kGroups, BULK> bulk;
 };
 
 // FootsiesEnv.step for every env: up to K fused fight frames, or the reset of a finished env (autoreset).
@@ -225,13 +198,9 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
     constexpr bool kRng = P1BOT || P2BOT;
     constexpr int kPlanes = kRng ? 4 : 3;
     constexpr int kGroupThreads = SH::kGroupThreads, kGroups = SH::kGroups, kStages = SH::kStages;
-    // FG_BULK_STORE experiment: K = 1, unmasked kernels; per launch only with autoreset (then every battle of a staged
-    // chunk stores its state and all outputs on every step)
-    constexpr bool kBulk = FG_BULK_STORE && !KFUSED && !MASKED;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    StepSmem<SH, kPlanes, kBulk> &S = *reinterpret_cast<StepSmem<SH, kPlanes, kBulk> *>(smem_raw);
+    StepSmem<SH, kPlanes> &S = *reinterpret_cast<StepSmem<SH, kPlanes> *>(smem_raw);
     const Tables &T = S.T;
-    const bool bulk_launch = kBulk && p.autoreset != 0;
     const int lane = threadIdx.x & 31;
     const int g = threadIdx.x / kGroupThreads, lt = threadIdx.x % kGroupThreads;   // pipeline group, thread within it
     const int num_chunks = (p.n + kGroupThreads - 1) / kGroupThreads;
@@ -249,32 +218,11 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
     // battles whose state and output lines the previous launch left in the 126 MB L2.  Only the whole chunks swap places:
     // the ragged tail chunk (plain loads, no TMA stage, no barrier traffic) stays the LAST element of the sequence in both
     // directions, i.e. the final iteration of the group that owns it -- the stage / parity bookkeeping below relies on every
-    // earlier iteration of a group being a staged one.
+    // earlier iteration of a group being a staged one (found in round 2: a batch with a ragged tail AND several chunks per
+    // group made the producer wait forever for a stage nobody had consumed, profiles/r02v_ragged_reverse_before_fix.log).
     auto chunk_of = [&](int c) { return (FG_REVERSE && p.reverse && c < full_chunks) ? full_chunks - 1 - c : c; };
-    // (elected thread of the group) write chunk sequence element `cprev`, processed at iteration kprev, back to global memory
-    auto bulk_flush = [&](int cprev, int kprev) {
-        if constexpr (kBulk) {
-            mbar_wait(&S.bulk.out_full[g], kprev & 1);
-            const size_t e0 = (size_t)chunk_of(cprev) * kGroupThreads;
-            const int sp = kprev % kStages;
-            constexpr uint32_t kPlaneBytes = kGroupThreads * sizeof(uint4);
-            tma_store_1d(p.pl_f1 + e0, S.stage[g][sp][0], kPlaneBytes);
-            tma_store_1d(p.pl_f2 + e0, S.stage[g][sp][1], kPlaneBytes);
-            tma_store_1d(p.pl_env + e0, S.stage[g][sp][2], kPlaneBytes);
-            auto &O = S.bulk.out[g];
-            tma_store_1d(p.obs + 2 * e0, O.obs, 2 * kPlaneBytes);
-            tma_store_1d(p.reward + e0, O.reward, kGroupThreads * 4);
-            tma_store_1d(p.info_frame + e0, O.info_frame, kGroupThreads * 4);
-            tma_store_1d(p.info_misc + e0, O.info_misc, kGroupThreads * 4);
-            tma_store_1d(p.terminated + e0, O.terminated, kGroupThreads);
-            tma_store_commit();
-            tma_store_wait_read();
-            mbar_arrive(&S.bulk.out_free[g]);
-        }
-    };
     if (lt == 0) {
         for (int s = 0; s < kStages; s++) { mbar_init(&S.full_bar[g][s], 1u); mbar_init(&S.empty_bar[g][s], kGroupThreads / 32); }
-        if constexpr (kBulk) { mbar_init(&S.bulk.out_full[g], kGroupThreads / 32); mbar_init(&S.bulk.out_free[g], 1u); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Programmatic dependent launch (p.pdl, large batches): this CTA may have become resident while the previous launch on
@@ -318,16 +266,10 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
         bool valid = staged || i < p.n;
         if (MASKED) valid = valid && p.step_mask[valid ? i : 0] != 0;
         if (lt == 0) {                                                  // producer: chunk k + kStages - 1 -> the stage read at k - 1
-            if constexpr (kBulk) {
-                // chunk k - 1 (always a staged one, see chunk_of) goes back with bulk stores once every warp of the group has
-                // put its battles' new state into the stage and their outputs into the staging block; the stage and the
-                // block are free again when the copies have READ them
-                if (bulk_launch && k >= 1) bulk_flush(cl - stride, k - 1);
-            }
             const int cn = cl + (kStages - 1) * stride;
             if (cn < num_chunks && chunk_of(cn) < full_chunks) {
                 const int sn = (k + kStages - 1) % kStages;
-                if (k >= 1 && !bulk_launch) mbar_wait(&S.empty_bar[g][sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
+                if (k >= 1) mbar_wait(&S.empty_bar[g][sn], ((k - 1) / kStages) & 1);   // every warp has read chunk k-1
                 issue(chunk_of(cn), sn);
             }
         }
@@ -348,10 +290,8 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
             e.frame = (int32_t)cc.x; e.misc = cc.y; e.bq2 = cc.z; e.bq1 = cc.w;
             if (kRng) { const uint4 r = S.stage[g][s][kPlanes - 1][lt]; e.r0 = r.x; e.r1 = r.y; e.r2 = r.z; e.r3 = r.w; }
             e.drew = false;
-            if (!bulk_launch) {                                         // (bulk stores: the stage is released by bulk_flush)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.empty_bar[g][s]);
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.empty_bar[g][s]);
         } else if (valid) {
             load_env<kRng>(p, i, e);                                    // ragged tail chunk: plain loads
         }
@@ -359,10 +299,8 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
             if ((e.misc >> FGM_DONE_SHIFT) & 1u) {
                 if (p.autoreset) {                                      // next-step autoreset: this call only resets
                     reset_env<P1BOT, P2BOT>(T, e, p.stale_intro != 0);
-                    if (!(kBulk && staged)) {
-                        store_env<kRng>(p, i, e);
-                        write_outputs(p, i, e, 0.0f, false);
-                    }
+                    store_env<kRng>(p, i, e);
+                    write_outputs(p, i, e, 0.0f, false);
                     acc.s += 0x10000u;
                 } else {
                     p.reward[i] = 0.0f;                                 // frozen until fg_reset
@@ -405,42 +343,12 @@ __global__ void __launch_bounds__(SH::kThreads, SH::kMinBlocks) step_kernel(cons
                 if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, S.stats, lane); frames_since_flush = 0u; }
             }
         }
-        if (kBulk && bulk_launch && staged) {
-            if constexpr (kBulk) {
-                // every battle of the chunk either ran or was reset: new state into the stage it came from, outputs into the
-                // group's staging block (free once the previous chunk's copies have read it), then hand over to bulk_flush
-                S.stage[g][s][0][lt] = make_uint4(f2u(e.pos1), f2u(e.vel1), e.pk1, e.hist1);
-                S.stage[g][s][1][lt] = make_uint4(f2u(e.pos2), f2u(e.vel2), e.pk2, e.hist2);
-                S.stage[g][s][2][lt] = make_uint4((uint32_t)e.frame, e.misc, e.bq2, e.bq1);
-                if (kRng && (!FG_SKIP_RNG_STORE || e.drew)) p.pl_rng[i] = make_uint4(e.r0, e.r1, e.r2, e.r3);
-                if (k >= 1) mbar_wait(&S.bulk.out_free[g], (k - 1) & 1);
-                StepOutputs o;
-                make_outputs(e, o);
-                auto &O = S.bulk.out[g];
-                O.obs[2 * lt] = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]);
-                O.obs[2 * lt + 1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
-                O.reward[lt] = (float)reward;                           // 0 for a battle that was reset by this step
-                O.terminated[lt] = terminal ? 1 : 0;
-                O.info_frame[lt] = e.frame;
-                O.info_misc[lt] = o.info_misc;
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.bulk.out_full[g]);
-            }
-        } else if (run) {
+        if (run) {
             store_env<kRng>(p, i, e);
             write_outputs(p, i, e, (float)reward, terminal);
         }
         frames_since_flush += (uint32_t)K;                              // uniform across the warp
         if (frames_since_flush >= kStatFlushFrames) { flush_stats(acc, S.stats, lane); frames_since_flush = 0u; }
-    }
-    if constexpr (kBulk) {
-        // the group's last staged chunk (iteration k - 1, unless that was the ragged tail chunk) is still in shared memory
-        if (bulk_launch && lt == 0 && k >= 1) {
-            const int cl_last = first + (k - 1) * stride;
-            if (chunk_of(cl_last) < full_chunks) bulk_flush(cl_last, k - 1);
-            tma_store_wait_all();
-        }
     }
     flush_stats(acc, S.stats, lane);
     __syncthreads();
@@ -483,7 +391,7 @@ static __global__ void __launch_bounds__(kThreads) seed_kernel(const Params p) {
 template <class SH, bool KF, bool B1, bool B2, bool D, bool M>
 cudaError_t launch_step_shape(int sm_count, cudaStream_t s, const Params &p) {
     constexpr int kPlanes = (B1 || B2) ? 4 : 3;
-    constexpr size_t bytes = sizeof(StepSmem<SH, kPlanes, FG_BULK_STORE && !KF && !M>);
+    constexpr size_t bytes = sizeof(StepSmem<SH, kPlanes>);
     static DeviceOnceFlags configured;
     if (cudaError_t e = configure_once_per_device(configured, [] {
             return cudaFuncSetAttribute(step_kernel<SH, KF, B1, B2, D, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }))

@@ -103,14 +103,15 @@ class OracleBatch:
         self.threads = int(threads)
         self.cfg = Config(int(p1_bot), int(p2_bot), int(dense_reward), int(frame_delay), int(autoreset),
                           int(stale_intro_input))
-        self.h = lib().fo_create(self.n, C.byref(self.cfg), int(first_env_index))
+        self._L = lib()                       # kept so that __del__ still works during interpreter shutdown
+        self.h = self._L.fo_create(self.n, C.byref(self.cfg), int(first_env_index))
         self.trace = np.zeros(self.n, dtype=TRACE_DTYPE)
         if seed is not None:
             self.seed(seed)
 
     def __del__(self):
         if getattr(self, "h", None):
-            lib().fo_destroy(self.h)
+            self._L.fo_destroy(self.h)
             self.h = None
 
     def seed(self, seed_base, mask=None):
