@@ -149,39 +149,44 @@ def cpu_engine(kind):
     return "port", ob.OracleBatch, ob.lib()
 
 
-def cpu_throughput(kind, n_envs, threads, seconds=None, steps=None, warmup=3, seed=1234):
+def cpu_throughput(kind, n_envs, threads, seconds=None, steps=None, warmup=3, seed=1234, inner=1):
     """The CPU path on the same workload definition (random P1 vs BattleAI, frame-skip 1, auto-reset) on `threads` host
-    threads; timed for `seconds` or for exactly `steps` steps.  Returns (kind, frames/s, frames, elapsed, steps)."""
+    threads; timed for `seconds` or for exactly `steps` steps, a step being `inner` consecutive env-steps of the sample batch
+    (so that `--steps 20` is seconds of CPU work, not milliseconds).  Returns (kind, frames/s, frames, elapsed, steps)."""
     import numpy as np
     kind, cls, L = cpu_engine(kind)
     orc = cls(n_envs, p2_bot=True, seed=0, threads=threads)
     L.fo_reset(orc.h, None, None)
     rng = np.random.default_rng(seed)
     tapes = [rng.integers(0, 8, size=n_envs, dtype=np.uint8) for _ in range(16)]
-    for i in range(warmup):
+    for i in range(warmup * inner):
         L.fo_step(orc.h, tapes[i % 16].ctypes.data, None, 1, None, threads)
     f0 = orc.frames_simulated()
     t0 = time.perf_counter()
     done = 0
     while True:
-        L.fo_step(orc.h, tapes[done % 16].ctypes.data, None, 1, None, threads)
+        for j in range(inner):
+            L.fo_step(orc.h, tapes[(done * inner + j) % 16].ctypes.data, None, 1, None, threads)
         done += 1
-        if (steps is not None and done >= steps) or (steps is None and time.perf_counter() - t0 >= seconds):
+        if (steps is not None and done >= steps) or (seconds is not None and time.perf_counter() - t0 >= seconds):
             break
     dt = time.perf_counter() - t0
     frames = orc.frames_simulated() - f0
     return kind, frames / dt, frames, dt, done
 
 
+REF_STEP_ENV_STEPS = 256
+REF_MAX_SECONDS = 30.0
 REF_SAMPLE_ENVS = {"reference": 4096, "port": 32768}     # a transliterated game object graph is ~0.6 MB per battle
 
 
-def cpu_baseline_entry(kind, threads, seconds=None, steps=None, warmup=3):
-    kind, v, frames, dt, done = cpu_throughput(kind, REF_SAMPLE_ENVS[kind], threads, seconds=seconds, steps=steps, warmup=warmup)
+def cpu_baseline_entry(kind, threads, seconds=None, steps=None, warmup=3, inner=1):
+    kind, v, frames, dt, done = cpu_throughput(kind, REF_SAMPLE_ENVS[kind], threads, seconds=seconds, steps=steps, warmup=warmup,
+                                               inner=inner)
     what = ("oracle/_ref: the reference's own Assets/Script battle code (BattleCore, Fighter, BattleAI, ...) transliterated "
             "mechanically into C++ (tools/cs2cpp.py) and compiled natively" if kind == "reference"
             else "oracle/: scalar C restatement of the reference's battle code")
-    sample = (f"{REF_SAMPLE_ENVS[kind]} envs x {done} steps ({frames} env-frames, {dt:.1f} s) of the same random-vs-bot workload "
+    sample = (f"{REF_SAMPLE_ENVS[kind]} envs x {done * inner} steps ({frames} env-frames, {dt:.1f} s) of the same random-vs-bot workload "
               f"on {threads} host threads; {what} (the Unity game binary itself cannot run offline)")
     return {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}, dt, done
 
@@ -192,12 +197,16 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    base, dt, done = cpu_baseline_entry("reference", threads, steps=args.steps, warmup=args.warmup)
+    # one `step` of this arm = REF_STEP_ENV_STEPS consecutive env-steps of the 4096-battle sample (~1 M env-frames: a few
+    # tenths of a second on the box's cores), so that the driver's `--steps 20` times seconds of CPU work
+    # (bounded: at most REF_MAX_SECONDS, whatever --steps says; the line reports the steps that were timed)
+    base, dt, done = cpu_baseline_entry("reference", threads, steps=args.steps, seconds=REF_MAX_SECONDS, warmup=min(args.warmup, 3),
+                                        inner=REF_STEP_ENV_STEPS)
     port, _, _ = cpu_baseline_entry("port", threads, seconds=3.0)
     value = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / max(done, 1) * 1e3,
+        "steps": done, "warmup": min(args.warmup, 3), "ms_per_step": dt / max(done, 1) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+fp32", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(n=args.envs_per_gpu), "reference_sample": base["sample"],
                    "note": "reference game binary + FootsiesEnv not runnable offline (no Unity/mono, no binary); this is its "
