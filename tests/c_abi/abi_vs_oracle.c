@@ -268,7 +268,9 @@ static void case_host(const char *name, int n, int steps) {
     free_bufs(&b);
 }
 
-int main(void) {
+int main(int argc, char **argv) {
+    /* optional argument: divide every case's step count (runs under compute-sanitizer) */
+    const int div = argc > 1 && atoi(argv[1]) > 0 ? atoi(argv[1]) : 1;
     printf("libfootsies_b200 ABI version %d (header %d)\n", fg_abi_version(), FG_ABI_VERSION);
     if (fg_abi_version() != FG_ABI_VERSION) { fprintf(stderr, "ABI version mismatch\n"); return 2; }
     {
@@ -281,10 +283,10 @@ int main(void) {
         if (fg_step(h, NULL) != FG_ERR_NOT_BOUND) { fprintf(stderr, "fg_step on an unbound handle was not refused\n"); return 2; }
         fg_destroy(h);
     }
-    case_device("device buffers, random P1 vs BattleAI", 5000, 400, 0, 1, 1, 1, 0);
-    case_device("device buffers, self-play, fused frame-skip 3, sparse reward", 3001, 250, 0, 0, 0, 3, 0);
-    case_host("host buffers, random P1 vs BattleAI", 4099, 300);
-    case_device("device buffers, by_example (both bots), masked RESET + SEED", 1537, 300, 1, 1, 1, 1, 1);
+    case_device("device buffers, random P1 vs BattleAI", 5000, 400 / div, 0, 1, 1, 1, 0);
+    case_device("device buffers, self-play, fused frame-skip 3, sparse reward", 3001, 250 / div, 0, 0, 0, 3, 0);
+    case_host("host buffers, random P1 vs BattleAI", 4099, 300 / div);
+    case_device("device buffers, by_example (both bots), masked RESET + SEED", 1537, 300 / div, 1, 1, 1, 1, 1);
     if (mismatches) { fprintf(stderr, "%lld mismatches\n", mismatches); return 1; }
     printf("ABI PARITY OK\n");
     return 0;
