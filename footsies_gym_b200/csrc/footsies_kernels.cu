@@ -36,6 +36,7 @@ struct fg_handle {
     // host-buffer path (fg_step_host*): slices of host_chunk_envs battles are pipelined over two library-owned
     // streams, so that the D2H copies of slice c run while slice c+1 is being simulated and its actions uploaded
     int host_chunk_envs;
+    int host_lead_div;      // the first slice of a sliced call is host_chunk_envs / host_lead_div battles (see SlicePlan)
     uint4 *d_packed;       // [num_envs] packed host layout (fg_packed_result)
     float *d_reward_table; // [FG_PACKED_REWARD_TABLE_SIZE] ascending; h_reward_table is the host copy
     uint32_t *d_pack_error;
@@ -233,6 +234,23 @@ __global__ void __launch_bounds__(256) pack_records_kernel(const float4 *__restr
 }
 
 // Library-owned resources of the host-buffer path, created on first use.
+// Slices of a host-buffer call: [0, lead), then whole chunks from there on.  The first device->host copy can only start when
+// the first slice has been stepped and packed, and nothing overlaps that: a SHORT first slice starts the copy stream earlier
+// at the price of one more copy.  Measured on a 4 Mi-battle packed call (profiles/r02z_e2e_lead_slice.log, ms per call,
+// interleaved): whole first chunk 1.303 / 1.308 / 1.307, half 1.287 / 1.288 / 1.289, quarter 1.302 / 1.296 / 1.353 -> half.
+struct SlicePlan {
+    size_t n, chunk, lead;
+    int count;
+    SlicePlan(const fg_handle *h) {
+        n = (size_t)h->cfg.num_envs; chunk = (size_t)h->host_chunk_envs;
+        if (n <= chunk) { lead = n; count = 1; return; }
+        lead = chunk / (size_t)h->host_lead_div;
+        count = 1 + (int)((n - lead + chunk - 1) / chunk);
+    }
+    size_t first(int c) const { return c == 0 ? 0 : lead + (size_t)(c - 1) * chunk; }
+    size_t size(int c) const { const size_t f = first(c), want = c == 0 ? lead : chunk; return n - f < want ? n - f : want; }
+};
+
 int host_path_init(fg_handle *h, bool compact, int slices) {
     if (compact && !h->d_position) {
         CUDA_TRY(cudaMalloc(&h->d_position, sizeof(float2) * (size_t)h->cfg.num_envs));
@@ -285,8 +303,8 @@ int host_step(fg_handle *h, const uint8_t *a1, const uint8_t *a2, const HostOut 
     if (!h->cfg.p2_bot && !a2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
     const bool compact = o.position || o.obs_u8;
     if (compact && !(o.position && o.obs_u8)) return fail(FG_ERR_INVALID_ARGUMENT, "position and obs_u8 go together%s");
-    const size_t n = (size_t)h->cfg.num_envs, chunk = (size_t)h->host_chunk_envs;
-    const int slices = (int)((n + chunk - 1) / chunk);
+    const SlicePlan plan(h);
+    const int slices = plan.count;
     if (int rc = host_path_init(h, compact, slices)) return rc;
     cudaStream_t sc = user, sd = user;
     if (slices > 1) {
@@ -295,7 +313,7 @@ int host_step(fg_handle *h, const uint8_t *a1, const uint8_t *a2, const HostOut 
         CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_fork, 0));
     }
     for (int c = 0; c < slices; c++) {
-        const size_t first = (size_t)c * chunk, m = n - first < chunk ? n - first : chunk;
+        const size_t first = plan.first(c), m = plan.size(c);
         if (!h->cfg.p1_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p1 + first), a1 + first, m, cudaMemcpyHostToDevice, sc));
         if (!h->cfg.p2_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p2 + first), a2 + first, m, cudaMemcpyHostToDevice, sc));
         if (int rc = step_range(h, (int)first, (int)m, sc)) return rc;
@@ -369,8 +387,8 @@ int host_step_packed(fg_handle *h, const uint8_t *a1, const uint8_t *a2, fg_pack
     if (!h->cfg.p1_bot && !a1) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p1 is required unless p1_bot%s");
     if (!h->cfg.p2_bot && !a2) return fail(FG_ERR_INVALID_ARGUMENT, "actions_p2 is required unless p2_bot%s");
     if (int rc = packed_init(h)) return rc;
-    const size_t n = (size_t)h->cfg.num_envs, chunk = (size_t)h->host_chunk_envs;
-    const int slices = (int)((n + chunk - 1) / chunk);
+    const SlicePlan plan(h);
+    const int slices = plan.count;
     if (int rc = host_path_init(h, false, slices)) return rc;
     cudaStream_t sc = user, sd = user;
     if (slices > 1) {
@@ -380,7 +398,7 @@ int host_step_packed(fg_handle *h, const uint8_t *a1, const uint8_t *a2, fg_pack
     }
     h->step_calls++;
     for (int c = 0; c < slices; c++) {
-        const size_t first = (size_t)c * chunk, m = n - first < chunk ? n - first : chunk;
+        const size_t first = plan.first(c), m = plan.size(c);
         if (!h->cfg.p1_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p1 + first), a1 + first, m, cudaMemcpyHostToDevice, sc));
         if (!h->cfg.p2_bot) CUDA_TRY(cudaMemcpyAsync((void *)(h->buf.actions_p2 + first), a2 + first, m, cudaMemcpyHostToDevice, sc));
         if (int rc = step_range(h, (int)first, (int)m, sc)) return rc;
@@ -559,6 +577,8 @@ int32_t fg_create(const fg_config *cfg, fg_handle **out) {
     // slice size of the pipelined host-buffer path (measured, tools/e2e_bench.py, 4 Mi battles: no slices 2.28 ms, 2 Mi 2.20, 1 Mi 2.21,
     // 512 Ki 2.27, 256 Ki 2.45, 128 Ki 2.84: below 1 Mi the six copies per slice cost more than the overlap wins)
     h->host_chunk_envs = 1024 * 1024;
+    h->host_lead_div = 2;
+    if (const char *v = getenv("FOOTSIES_B200_HOST_LEAD_DIV")) { const int d = atoi(v); if (d == 1 || d == 2 || d == 4) h->host_lead_div = d; }
     if (const char *v = getenv("FOOTSIES_B200_HOST_CHUNK_ENVS")) {
         const long long c = atoll(v);
         if (c >= 256) h->host_chunk_envs = (int)((c > (1ll << 30) ? (1ll << 30) : c) / 256 * 256);

@@ -28,6 +28,9 @@ def child(n, steps, layout):
         def one(i):
             _capi.check(env._lib.fg_step_host(env._handle, C.c_void_p(tapes[i % 4].data_ptr()), None,
                                               *[C.c_void_p(b.data_ptr()) for b in bufs], None))
+    elif layout == "packed":
+        def one(i):
+            env.step_host_packed(tapes[i % 4])
     else:
         def one(i):
             env.step_host(tapes[i % 4])
@@ -43,7 +46,10 @@ def child(n, steps, layout):
     h2d, d2h = env.host_io_bytes_per_step()
     if layout == "f32":
         d2h = n * 45
+    if layout == "packed":
+        h2d, d2h = env.host_io_bytes_per_step(packed=True)
     print(json.dumps({"layout": layout, "chunk_envs": os.environ.get("FOOTSIES_B200_HOST_CHUNK_ENVS", "default"),
+                      "lead_div": os.environ.get("FOOTSIES_B200_HOST_LEAD_DIV", "default"),
                       "env_frames_per_sec": frames / dt, "ms_per_step": dt / steps * 1e3,
                       "d2h_GBps": d2h * steps / dt / 1e9}))
 
@@ -51,6 +57,13 @@ def child(n, steps, layout):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--child":
         child(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4])
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "--lead":
+        # packed layout: first slice = chunk / div (FOOTSIES_B200_HOST_LEAD_DIV), interleaved repetitions
+        for rep in range(3):
+            for div in (1, 2, 4):
+                env = dict(os.environ, FOOTSIES_B200_HOST_LEAD_DIV=str(div))
+                subprocess.run([sys.executable, os.path.abspath(__file__), "--child", str(4 * 1024 * 1024), "60", "packed"], env=env, check=False)
         sys.exit(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4 * 1024 * 1024
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
