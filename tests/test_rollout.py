@@ -62,6 +62,24 @@ def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip, skip)
     every rollout buffer, the final battle state and the episode statistics are bit-identical, over several horizons
     (ragged batch sizes: 1000 and 333 are not multiples of the 64 battles a CTA owns); skip = the fused
     FootsiesFrameSkipped stepping (fg_config.skip_unactionable) inside both."""
+    _horizon_equals_per_step(hidden, n, dense, frame_skip, skip)
+
+
+@pytest.mark.parametrize("hidden,n,dense,frame_skip,skip", [(64, 1000, True, 1, False), (32, 333, True, 2, True),
+                                                            (64, 97, False, 1, False)])
+def test_horizon_kernel_with_32_battle_warps_on_small_ragged_batches(monkeypatch, hidden, n, dense, frame_skip, skip):
+    """From 131 072 battles up the whole-horizon kernel gives a warp two 16-row M tiles (32 battles, every lane simulates
+    one).  That shape forced onto small ragged batches (FOOTSIES_B200_ROLLOUT_MT, read per launch) must not change a bit."""
+    monkeypatch.setenv("FOOTSIES_B200_ROLLOUT_MT", "2")
+    _horizon_equals_per_step(hidden, n, dense, frame_skip, skip)
+
+
+def test_horizon_kernel_at_the_size_that_selects_32_battle_warps():
+    """131 072 + 37 battles: the launcher picks the 32-battle-warp shape by itself, with a ragged last warp."""
+    _horizon_equals_per_step(64, 131072 + 37, True, 1, False, horizon=24, rounds=2, min_launch_ratio=10)
+
+
+def _horizon_equals_per_step(hidden, n, dense, frame_skip, skip, horizon=150, rounds=3, min_launch_ratio=50):
     from footsies_gym_b200 import FootsiesEnv
     from footsies_gym_b200.rollout import MLPPolicy, RolloutCollector
     if not torch.cuda.is_available():
@@ -72,30 +90,39 @@ def test_horizon_kernel_equals_per_step_path(hidden, n, dense, frame_skip, skip)
     with torch.no_grad():
         for prm in policy.net.parameters():
             prm.mul_(2.0)
-    horizon = 150                                           # > 120 frames: the statistics byte lanes are folded mid-horizon
+    # default horizon 150 > 120 frames: the statistics byte lanes are folded mid-horizon
     envs, cols = [], []
     for mode in ("step", "horizon"):
         env = FootsiesEnv(num_envs=n, device=dev, seed=3, dense_reward=dense, frame_skip=frame_skip, skip_unactionable=skip)
         envs.append(env)
         cols.append(RolloutCollector(env, policy, horizon=horizon, use_cuda_graph=False, fused=mode, seed=17))
     assert [c.mode for c in cols] == ["step", "horizon"]
-    for r in range(3):
+    for r in range(rounds):
         outs = [c.collect() for c in cols]
         torch.cuda.synchronize()
         for k in ("obs", "actions", "logp", "rewards", "dones", "last_obs"):
             assert torch.equal(outs[0][k], outs[1][k]), (r, k)
-        assert outs[0]["dones"].any()
+        assert outs[0]["dones"].any() or horizon < 100
         s0, s1 = envs[0].get_state(), envs[1].get_state()
         assert s0.tobytes() == s1.tobytes(), r
         assert envs[0].episode_stats() == envs[1].episode_stats(), r
         assert torch.equal(envs[0].info_frame, envs[1].info_frame) and torch.equal(envs[0].info_misc, envs[1].info_misc)
     launches = [e.launch_count() for e in envs]
-    assert launches[1] < launches[0] // 50                  # 1 launch per horizon instead of 1 per step (+ the policy's)
+    assert launches[1] < launches[0] // min_launch_ratio    # 1 launch per horizon instead of 1 per step (+ the policy's)
 
 
 @pytest.mark.parametrize("hidden,n,mirror,shared", [(64, 1000, False, False), (64, 777, True, True), (32, 130, True, False),
                                                     (128, 200, False, False)])
 def test_self_play_rollout_with_a_policy_for_p2(hidden, n, mirror, shared):
+    _self_play_rollout(hidden, n, mirror, shared)
+
+
+def test_self_play_rollout_with_32_battle_warps(monkeypatch):
+    monkeypatch.setenv("FOOTSIES_B200_ROLLOUT_MT", "2")
+    _self_play_rollout(64, 777, True, True)
+
+
+def _self_play_rollout(hidden, n, mirror, shared):
     """P2 driven by a second MLP policy (optionally on the mirrored observation, optionally the same network): the
     whole-horizon kernel equals the per-step path (fg_policy_mlp_sample + fg_policy_mlp_sample_p2 + fg_step) bit for bit,
     P2's log-probabilities equal torch's for the (mirrored) observation, and the collected actions replay."""
