@@ -40,6 +40,12 @@
 #ifndef FG_POLICY_F16
 #define FG_POLICY_F16 1
 #endif
+// Layer 2 with the OUTPUT tile as the outer loop (profiles/r03e_rollout_l2_order.log: 1 Mi battles 144.7 -> 138.8 us per step,
+// 131 072: 19.3 -> 18.9, 16 384: unchanged; same bits -- a tile's k-steps keep their order): acc[nt] is final after its own
+// k-steps, so its tanh (two MUFU per value, the XU pipe) runs under the next tiles' MMAs instead of after all of them.
+#ifndef FG_POLICY_L2_NT_OUTER
+#define FG_POLICY_L2_NT_OUTER 1
+#endif
 
 namespace fgp {
 
@@ -257,6 +263,30 @@ __device__ __forceinline__ void policy_mma_logits(const float *sm, const float *
 #if FG_POLICY_F16
     constexpr int KT = L::KT;
     const uint4 *hfrag = reinterpret_cast<const uint4 *>(sm);
+#if FG_POLICY_L2_NT_OUTER
+    // all A fragments first, then one output tile at a time (its k-steps in the same order, hence the same bits): acc[nt]
+    // is final after its own KT k-steps, so its tanh can run under the next tiles' MMAs
+    uint32_t ahi[KT][MT][4], alo[KT][MT][4];
+#pragma unroll
+    for (int kt = 0; kt < KT; kt++) {
+#pragma unroll
+        for (int m = 0; m < MT; m++) {
+            f16_split2(h[m][2 * kt][0], h[m][2 * kt][1], ahi[kt][m][0], alo[kt][m][0]);
+            f16_split2(h[m][2 * kt][2], h[m][2 * kt][3], ahi[kt][m][1], alo[kt][m][1]);
+            f16_split2(h[m][2 * kt + 1][0], h[m][2 * kt + 1][1], ahi[kt][m][2], alo[kt][m][2]);
+            f16_split2(h[m][2 * kt + 1][2], h[m][2 * kt + 1][3], ahi[kt][m][3], alo[kt][m][3]);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+#pragma unroll
+        for (int kt = 0; kt < KT; kt++) {
+            const uint4 b = hfrag[L::kW2 + (kt * NT + nt) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < MT; m++) mma_3xf16(acc[m][nt], ahi[kt][m], alo[kt][m], b);
+        }
+    }
+#else
 #pragma unroll
     for (int kt = 0; kt < KT; kt++) {
         uint32_t ahi[MT][4], alo[MT][4];
@@ -274,6 +304,7 @@ __device__ __forceinline__ void policy_mma_logits(const float *sm, const float *
             for (int m = 0; m < MT; m++) mma_3xf16(acc[m][nt], ahi[m], alo[m], b);
         }
     }
+#endif
     // ---- layer 3 on tanh(layer 2); the accumulators are in units of 1 / inv2, the logits of 1 / inv3 ----
     const float c2 = sm[L::kInv2] * kTwoLog2e, inv3 = sm[L::kInv3];
     float lg[MT][4];

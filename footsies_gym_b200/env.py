@@ -148,6 +148,8 @@ class FootsiesEnv:
         self.observation_space = footsies_observation_space(len(relevant), max(m.value.duration for m in relevant))
         self.action_space = footsies_action_space()
         self.reward_range = (-1, 1)
+        # the spaces above describe ONE battle, as in the reference; the names a gymnasium VectorEnv user looks for
+        self.single_observation_space, self.single_action_space = self.observation_space, self.action_space
 
         self._lib = _capi.load()
         self._handle = None
