@@ -204,8 +204,14 @@ struct RolloutMmaSmem {
     static constexpr size_t kBytes = kStats + sizeof(unsigned long long) * FG_STAT_COUNT;
 };
 
+// developer knob: CTAs per SM the 32-battle-warp shape is compiled for.  Measured (profiles/r03f_rollout_mt2_blocks.log): forcing 3
+// (168 registers instead of 190, 24 bytes of spill, 12 instead of 8 warps per SM) LOSES -- 1 Mi battles 143.1 vs 137.5 us per
+// step, 131 072: 19.3 vs 18.7.
+#ifndef FG_ROLLOUT_MT2_MIN_BLOCKS
+#define FG_ROLLOUT_MT2_MIN_BLOCKS 1
+#endif
 template <int H, int W, int MT, bool DENSE, bool P2POL, bool SKIP>
-__global__ void __launch_bounds__(32 * W) rollout_mma_kernel(const RolloutParams rp) {
+__global__ void __launch_bounds__(32 * W, (MT == 2 && !P2POL) ? FG_ROLLOUT_MT2_MIN_BLOCKS : 1) rollout_mma_kernel(const RolloutParams rp) {
     using SM = RolloutMmaSmem<H, W, P2POL>;
     constexpr bool kP2Bot = !P2POL;
     constexpr int kWarpEnvs = 16 * MT, kEnvs = kWarpEnvs * W;
