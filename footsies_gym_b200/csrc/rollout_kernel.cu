@@ -369,6 +369,11 @@ static cudaError_t launch_rollout_mma(cudaStream_t s, const RolloutParams &rp) {
     int mt = rp.sim.n >= 131072 ? 2 : 1;
     if (const char *v = getenv("FOOTSIES_B200_ROLLOUT_MT")) mt = atoi(v) == 2 ? 2 : 1;
     // (7-warp CTAs, which would spread 16 384 battles evenly as 147 x 112, measured 4.55 us per step against 4.46 for 4 warps.)
+    // (8-battle warps -- half-empty M tiles, twice the warps, 124 registers -- are the same bits and SLOWER from 8192 battles up:
+    // 16 384 battles 4.98 vs 3.35 us per step; only 4096 battles gain, 2.30 vs 2.46.  A one-off start stagger between the two
+    // CTAs of an SM changes nothing: 3.33 vs 3.32.  tools/probes/half_tile_and_stagger_experiment.patch,
+    // profiles/r03h_rollout_half_tiles.log, r03i_rollout_stagger.log.  Step time against batch size -- 4096: 2.46, 8192: 2.48,
+    // 16 384: 3.35, 32 768: 6.33 -- says the kernel leaves the latency-bound regime right at one CTA per SM.)
     // Two policies (self-play): 32-battle warps from 131 072 battles up (1 Mi: 479 us per step against 567).
     return launch_rollout_mma_w<H, 4, DENSE>(mt, s, rp);
 }
