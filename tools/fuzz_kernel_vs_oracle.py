@@ -63,7 +63,8 @@ while time.time() < t_end:
                seed=int(rng.integers(-10 ** 6, 10 ** 6)), frame_skip=int(rng.choice([1, 1, 1, 2, 3, 4, 7])))
     n = int(rng.choice([33, 64, 255, 257, 300, 512, 777, 1024]))        # ragged tails and whole chunks of 256
     steps = int(rng.choice([300, 800, 1500]))
-    if rng.random() < 0.08:                                              # several chunks per pipeline group + a ragged tail
+    # several chunks per pipeline group + a ragged tail (not with --engine ref: a transliterated game object graph is ~0.6 MB per battle)
+    if rng.random() < 0.08 and args.engine != "ref":
         n, steps = int(rng.integers(120000, 260000)), 60
     resets = bool(rng.random() < 0.4)                                    # masked RESET + SEED commands in mid-round
     maker = [pc.tape_uniform, pc.tape_sticky, pc.tape_profiles][int(rng.integers(0, 3))]
