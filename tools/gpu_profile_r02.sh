@@ -24,6 +24,6 @@ ncu --replay-mode application --cache-control none --clock-control none \
     -k regex:step_kernel -s 700 -c 4 --csv --log-file $OUT/traffic_$TAG.csv \
     python bench.py $STEADY > $OUT/ncu_traffic_$TAG.log 2>&1
 python tools/rollout_sweep.py --one 16384 64 > $OUT/rollout_plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 2 -c 1 -f -o $OUT/prof_rollout_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:rollout_ -s 2 -c 1 -f -o $OUT/prof_rollout_$TAG \
     python tools/rollout_sweep.py --one 16384 64 > $OUT/ncu_rollout_$TAG.log 2>&1
 echo done
