@@ -88,7 +88,9 @@ class FootsiesEnv:
         ----------
         num_envs: battles stepped per call on this GPU
         device: CUDA device (default: current device)
-        frame_delay: observations / info are delayed by this many frames (reward and termination are not)
+        frame_delay: observations / info are delayed by this many env steps (reward and termination are not): frames when
+                     frame_skip is 1, as in the reference (footsies.py:129-131, 533-535); with K fused frames per step the queue
+                     still advances once per step() call, i.e. the delay is frame_delay x K frames
         by_example: P1 is driven by the in-game bot, actions passed to step() are ignored
         opponent: None or "bot" -> in-game BattleAI (reference default); a callable `(obs, info) -> actions`
             -> custom policy queried every step like the reference's `opponent`; "self_play" / "remote"

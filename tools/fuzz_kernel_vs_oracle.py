@@ -21,7 +21,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 import parity_cases as pc                                   # noqa: E402
-from parity import compare_state_and_outputs, compare_stats  # noqa: E402
+from parity import compare_state_and_outputs, compare_states, compare_stats, _eq  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("minutes", nargs="?", type=float, default=3.0)
@@ -67,31 +67,52 @@ while time.time() < t_end:
     if rng.random() < 0.08 and args.engine != "ref":
         n, steps = int(rng.integers(120000, 260000)), 60
     resets = bool(rng.random() < 0.4)                                    # masked RESET + SEED commands in mid-round
+    # FootsiesEnv frame_delay (footsies.py:129-131, 533-535: observation and info arrive `delay` steps late, reward and
+    # termination do not): the delay ring kernel, CUDA path only (the host-compiled logic has no ring)
+    # (only with frame_skip = 1, the reference's case: with K fused frames per step FootsiesEnv counts the delay in env steps,
+    # while the oracle's repeat = K is K reference steps, each of which pushes to the queue)
+    delay = int(rng.choice([0, 0, 0, 1, 3, 7])) if args.backend == "gpu" and n <= 1024 and cfg["frame_skip"] == 1 else 0
     maker = [pc.tape_uniform, pc.tape_sticky, pc.tape_profiles][int(rng.integers(0, 3))]
     t1, t2 = maker(rng, steps, n), maker(rng, steps, n)
     env = make_env(num_envs=n, by_example=p1_bot, opponent=None if p2_bot else "self_play", dense_reward=cfg["dense"],
                    frame_skip=cfg["frame_skip"], autoreset=cfg["autoreset"], seed=cfg["seed"],
-                   first_env_index=cfg["first_env_index"], stale_intro_input=cfg["stale"])
-    orc = Batch(n, p1_bot=p1_bot, p2_bot=p2_bot, dense_reward=cfg["dense"], autoreset=cfg["autoreset"],
+                   first_env_index=cfg["first_env_index"], stale_intro_input=cfg["stale"], **({"frame_delay": delay} if delay else {}))
+    orc = Batch(n, p1_bot=p1_bot, p2_bot=p2_bot, dense_reward=cfg["dense"], autoreset=cfg["autoreset"], frame_delay=delay,
                 stale_intro_input=cfg["stale"], first_env_index=cfg["first_env_index"], seed=cfg["seed"], threads=8)
-    env.reset()
+    cfg["frame_delay"] = delay
+
+    def check(ret, where, with_reward=True):
+        """delay = 0: every field of state and outputs; delay > 0: the battle state as it is now, the DELAYED observation and
+        info the call returned, the undelayed reward and termination."""
+        if not delay:
+            compare_state_and_outputs(env, orc.trace, where=where)
+            return
+        compare_states(env.get_state(), orc.trace, where)
+        obs, info = (ret[0], ret[-1])
+        _eq(where, "delayed obs", torch.cat([obs[k].float() for k in ("guard", "move", "move_frame", "position")], 1).cpu().numpy(), orc.trace["obs"])
+        _eq(where, "delayed info frame", info["frame"].cpu().numpy(), orc.trace["info_frame"])
+        if with_reward:
+            _eq(where, "reward", ret[1].cpu().numpy(), orc.trace["reward"])
+            _eq(where, "terminated", ret[2].cpu().numpy().astype(np.int32), orc.trace["terminated"])
+
+    ret = env.reset()
     orc.reset()
     where = f"seed {seed} {cfg} n={n}"
-    compare_state_and_outputs(env, orc.trace, where=where + " reset")
+    check(ret, where + " reset", with_reward=False)
     for t in range(steps):
         if resets and rng.random() < 0.01:
             mask = rng.random(n) < 0.3
             new_seed = int(rng.integers(-10 ** 6, 10 ** 6)) if rng.random() < 0.5 else None
-            env.reset(seed=new_seed, options={"mask": torch.from_numpy(mask) if args.backend == "gpu" else mask})
+            ret = env.reset(seed=new_seed, options={"mask": torch.from_numpy(mask) if args.backend == "gpu" else mask})
             if new_seed is not None:
                 orc.seed(new_seed, mask)
             orc.reset(mask)
-            compare_state_and_outputs(env, orc.trace, where=where + f" masked reset before step {t}")
+            check(ret, where + f" masked reset before step {t}", with_reward=False)
         a1 = None if p1_bot else t1[t]
         a2 = None if p2_bot else t2[t]
-        env.step(None if a1 is None else torch.from_numpy(a1), None if a2 is None else torch.from_numpy(a2))
+        ret = env.step(None if a1 is None else torch.from_numpy(a1), None if a2 is None else torch.from_numpy(a2))
         orc.step(a1 if a1 is not None else np.zeros(n, np.uint8), a2, repeat=cfg["frame_skip"])
-        compare_state_and_outputs(env, orc.trace, where=where + f" step {t}")
+        check(ret, where + f" step {t}")
     if not resets:
         compare_stats(env, orc, where=where + " end")
     st = env.episode_stats()

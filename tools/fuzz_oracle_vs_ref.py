@@ -2,7 +2,7 @@
 """Differential fuzzing of the two CPU engines beyond the fixed tapes of the test-suite: the hand-written oracle
 (oracle/footsies_oracle.c) against the transliterated reference (oracle/_ref, tools/cs2cpp.py) on randomly drawn
 configurations, seeds and input personalities, every field of every trace after every step (tests/test_oracle_vs_ref.py
-holds the comparison).  Usage: python tools/fuzz_oracle_vs_ref.py [minutes] > profiles/rNN_oracle_vs_ref_fuzz.log"""
+holds the comparison).  Usage: python tools/fuzz_oracle_vs_ref.py [minutes] [master seed] > profiles/rNN_oracle_vs_ref_fuzz.log"""
 import os
 import sys
 import time
@@ -17,7 +17,9 @@ import ref_binding as rb      # noqa: E402
 from test_oracle_vs_ref import assert_traces_equal   # noqa: E402
 
 minutes = float(sys.argv[1]) if len(sys.argv) > 1 else 5.0
-master = np.random.default_rng(20261018)
+master_seed = int(sys.argv[2]) if len(sys.argv) > 2 else 20261018
+print(f"# master_seed={master_seed}", flush=True)
+master = np.random.default_rng(master_seed)
 t_end = time.time() + 60 * minutes
 total_frames = total_episodes = rounds = 0
 while time.time() < t_end:
