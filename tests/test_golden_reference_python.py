@@ -106,6 +106,20 @@ def test_oracle_matches_reference_python(oracle, path):
     assert n > 1000
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=_ids(GOLDEN))
+def test_transliterated_reference_engine_matches_reference_python(path):
+    """The same goldens with the reference's OWN C# battle code (oracle/_ref, tools/cs2cpp.py) playing the game: what the
+    unmodified reference FootsiesEnv computed in Python is reproduced when its C# engine -- not the hand-written oracle --
+    produces the states (closes the triangle reference Python <-> reference C# <-> oracle on these tapes)."""
+    import types
+    import ref_binding
+    if not ref_binding.available():
+        pytest.skip("oracle/_ref not built")
+    dense, delay, p2_remote, _ = np.load(path)["config"].tolist()
+    n = replay(path, OracleDriver(types.SimpleNamespace(OracleBatch=ref_binding.RefBatch), bool(dense), int(delay), bool(p2_remote)))
+    assert n > 1000
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", GOLDEN, ids=_ids(GOLDEN))
 def test_kernel_matches_reference_python(path):
